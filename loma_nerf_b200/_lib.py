@@ -1,0 +1,95 @@
+"""ctypes binding of libloma_nerf_b200.so (include/loma_nerf_b200.h).
+
+The CUDA library IS the product: importing this module fails loudly when the library has not been
+built, and nothing here (or anywhere in the package) falls back to a CPU implementation.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libloma_nerf_b200.so")
+
+LNB_MAX_LAYERS = 16
+LNB_OK, LNB_ERR_CUDA, LNB_ERR_ARG, LNB_ERR_UNSUPPORTED = 0, 1, 2, 3
+HEAD_NERF, HEAD_SIGMOID = 0, 1
+SEED_VALUE, SEED_LOSS = 0, 1
+PATH_F32, PATH_TC, PATH_F32_LAYERWISE = 0, 1, 2
+
+c_float_p = POINTER(c_float)
+
+
+class LnbMlp(Structure):
+    _fields_ = [("n_layers", c_int), ("dims", c_int * (LNB_MAX_LAYERS + 1)), ("max_in", c_int),
+                ("max_out", c_int), ("head", c_int)]
+
+
+class LnbStepArgs(Structure):
+    """Mirror of lnb_step_args; field order and types must match the header exactly
+    (tests/test_abi.py compares sizeof and offsets with the values the library reports)."""
+    _fields_ = [
+        ("R", c_int), ("S", c_int), ("n_rows", c_int), ("rows", c_int), ("target_w", c_int),
+        ("X", c_void_p), ("ws", c_void_p), ("bs", c_void_p), ("target", c_void_p),
+        ("dists", c_void_p),
+        ("inter", c_void_p), ("inter_rows", c_int), ("inter_ld", c_int),
+        ("inter_accumulate", c_int),
+        ("rgba", c_void_p), ("alpha", c_void_p), ("cumprod", c_void_p), ("weights", c_void_p),
+        ("color", c_void_p), ("color_accumulate", c_int),
+        ("loss", c_void_p),
+        ("want_grad", c_int), ("seed_mode", c_int), ("seed", c_float),
+        ("d_ws", c_void_p), ("d_bs", c_void_p), ("d_X", c_void_p), ("d_target", c_void_p),
+        ("d_dists", c_void_p), ("d_color", c_void_p), ("d_inter", c_void_p),
+        ("path", c_int),
+    ]
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the library (once) and set argtypes for the flat API."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryMissing(
+            "%s not found: build it with `python -m loma_nerf_b200.build` (nvcc, sm_100a). "
+            "There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    P = POINTER
+    lib.lnb_abi_version.restype = c_int
+    lib.lnb_device_count.restype = c_int
+    lib.lnb_create.argtypes = [P(c_void_p), c_int]
+    lib.lnb_create.restype = c_int
+    lib.lnb_destroy.argtypes = [c_void_p]
+    lib.lnb_destroy.restype = None
+    lib.lnb_set_stream.argtypes = [c_void_p, c_void_p]
+    lib.lnb_synchronize.argtypes = [c_void_p]
+    lib.lnb_last_error.argtypes = [c_void_p]
+    lib.lnb_last_error.restype = c_char_p
+    lib.lnb_launch_count.argtypes = [c_void_p]
+    lib.lnb_launch_count.restype = c_longlong
+    lib.lnb_host_alloc.argtypes = [c_size_t]
+    lib.lnb_host_alloc.restype = c_void_p
+    lib.lnb_host_free.argtypes = [c_void_p]
+    lib.lnb_host_free.restype = None
+    for name in ("lnb_nerf_step", "lnb_fit_step", "lnb_nerf_step_host", "lnb_fit_step_host"):
+        fn = getattr(lib, name)
+        fn.argtypes = [c_void_p, P(LnbMlp), P(LnbStepArgs)]
+        fn.restype = c_int
+    lib.lnb_pos_encoding.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p]
+    lib.lnb_sample_encode.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                      c_void_p, c_void_p]
+    lib.lnb_mult_a_b.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]
+    lib.lnb_adam_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
+                                  c_int, c_float, c_float, c_float, c_float]
+    lib.lnb_sgd_step.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_float]
+    lib.lnb_default_ctx.restype = c_void_p
+    lib.lnb_struct_layout.argtypes = [P(c_int), c_int]
+    lib.lnb_struct_layout.restype = c_int
+    _lib = lib
+    return lib

@@ -1,0 +1,208 @@
+"""Host-side mirror of the flat API of libloma_nerf_b200.so.
+
+`Context.nerf_step` / `Context.fit_step` evaluate the reference's two loma programs
+(/root/reference/scripts/nerf.py:1-306, scripts/mlp_fit.py:1-174) on the GPU: MLP forward,
+compositing / loss, and (grad=True) the reverse-mode gradients, with the reference's buffer
+layouts (padded weights [L][max_in][max_out], features [N][C_in], dists [R][S] ...).
+
+Inputs are either all torch CUDA tensors (device pointers, asynchronous on the context's stream)
+or all numpy / CPU tensors (host pointers: staged through pinned memory, synchronous).  PyTorch is
+only used as the owner of device memory; the arithmetic is in the CUDA library.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib as L
+
+try:  # torch is plumbing (device memory / streams); the host-pointer path works without it
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+FWD_OUTPUTS = ("inter", "rgba", "alpha", "cumprod", "weights", "color", "loss")
+GRAD_OUTPUTS = ("d_ws", "d_bs", "d_X", "d_target", "d_dists", "d_color", "d_inter")
+PATHS = {"f32": L.PATH_F32, "tc": L.PATH_TC, "f32_layerwise": L.PATH_F32_LAYERWISE}
+
+
+class LnbError(RuntimeError):
+    pass
+
+
+def make_mlp(dims, ws_shape, head):
+    m = L.LnbMlp()
+    dims = [int(d) for d in dims]
+    if len(dims) - 1 > L.LNB_MAX_LAYERS:
+        raise ValueError("too many layers")
+    m.n_layers = len(dims) - 1
+    for i, d in enumerate(dims):
+        m.dims[i] = d
+    m.max_in, m.max_out = int(ws_shape[1]), int(ws_shape[2])
+    m.head = head
+    return m
+
+
+def _is_cuda(x):
+    return torch is not None and isinstance(x, torch.Tensor) and x.is_cuda
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if torch is not None and isinstance(x, torch.Tensor):
+        assert x.is_contiguous() and x.dtype in (torch.float32, torch.float64)
+        return x.data_ptr()
+    assert x.flags.c_contiguous
+    return x.ctypes.data
+
+
+class Context:
+    """One lnb_ctx: a device, a stream and a grow-only workspace."""
+
+    def __init__(self, device=None, stream=None):
+        self.lib = L.load()
+        if self.lib.lnb_device_count() <= 0:
+            raise LnbError("no CUDA device: libloma_nerf_b200 has no CPU fallback")
+        if device is None:
+            device = torch.cuda.current_device() if torch is not None and torch.cuda.is_available() else 0
+        self.device = int(device)
+        h = ctypes.c_void_p()
+        rc = self.lib.lnb_create(ctypes.byref(h), self.device)
+        if rc != L.LNB_OK:
+            raise LnbError("lnb_create failed (%d)" % rc)
+        self.h = h
+        if stream is not None:
+            self.set_stream(stream)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lnb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, stream):
+        """stream: a torch.cuda.Stream, a raw cudaStream_t int, or None (the context's own)."""
+        raw = getattr(stream, "cuda_stream", stream)
+        self._check(self.lib.lnb_set_stream(self.h, ctypes.c_void_p(raw or 0)))
+
+    def use_current_torch_stream(self):
+        self.set_stream(torch.cuda.current_stream(self.device))
+
+    def synchronize(self):
+        self._check(self.lib.lnb_synchronize(self.h))
+
+    @property
+    def launches(self):
+        return int(self.lib.lnb_launch_count(self.h))
+
+    def _check(self, rc):
+        if rc != L.LNB_OK:
+            raise LnbError("libloma_nerf_b200 error %d: %s" % (rc, self.lib.lnb_last_error(self.h).decode()))
+
+    # -------------------------------------------------------------------------------------------
+    def _step(self, nerf, dims, X, ws, bs, target, dists, R, S, grad, seed, outputs, out, rows,
+              path, inter_accumulate, color_accumulate, head):
+        dev = _is_cuda(X)
+        mlp = make_mlp(dims, ws.shape, head)
+        Ln, mi, mo = mlp.n_layers, mlp.max_in, mlp.max_out
+        N = int(X.shape[0])
+        M = max(int(rows or 0), N)
+        Wt = int(target.shape[1]) if target is not None else 3
+        a = L.LnbStepArgs()
+        a.R, a.S, a.n_rows, a.rows, a.target_w = int(R), int(S), N, M, Wt
+        a.X, a.ws, a.bs = _ptr(X), _ptr(ws), _ptr(bs)
+        a.target, a.dists = _ptr(target), _ptr(dists)
+        a.inter_rows, a.inter_ld = M, mo
+        a.inter_accumulate, a.color_accumulate = int(inter_accumulate), int(color_accumulate)
+        a.want_grad = int(bool(grad))
+        if isinstance(seed, str):
+            assert seed == "loss"
+            a.seed_mode, a.seed = L.SEED_LOSS, 1.0
+        else:
+            a.seed_mode, a.seed = L.SEED_VALUE, float(seed)
+        a.path = PATHS[path]
+        shapes = dict(inter=(Ln, M, mo), rgba=(R, S, 4), alpha=(R, S), cumprod=(R, S),
+                      weights=(R, S), color=(R, 3), loss=(1,), d_ws=(Ln, mi, mo), d_bs=(Ln, mo),
+                      d_X=(N, int(X.shape[1])), d_target=(R, Wt), d_dists=(R, S),
+                      d_color=(R, Wt), d_inter=(Ln, M, mo))
+        res = {}
+        out = out or {}
+        want = list(outputs)
+        if grad:
+            want += [k for k in ("d_ws", "d_bs") if k not in want]
+        for k in want:
+            if k not in shapes:
+                raise ValueError("unknown output " + k)
+            if not nerf and k in ("rgba", "alpha", "cumprod", "weights", "color", "d_dists"):
+                continue
+            buf = out.get(k)
+            if buf is None:
+                if dev:
+                    buf = torch.zeros(shapes[k], dtype=torch.float32, device=X.device)
+                else:
+                    buf = np.zeros(shapes[k], np.float32)
+            else:
+                assert tuple(buf.shape) == tuple(shapes[k]), (k, tuple(buf.shape), shapes[k])
+            res[k] = buf
+            setattr(a, k, _ptr(buf))
+        fn = {(True, True): self.lib.lnb_nerf_step, (True, False): self.lib.lnb_nerf_step_host,
+              (False, True): self.lib.lnb_fit_step, (False, False): self.lib.lnb_fit_step_host}[(nerf, dev)]
+        self._check(fn(self.h, ctypes.byref(mlp), ctypes.byref(a)))
+        return res
+
+    def nerf_step(self, dims, X, ws, bs, dists, target=None, R=None, S=None, grad=False, seed=1.0,
+                  outputs=("color", "loss"), out=None, rows=None, path="f32",
+                  inter_accumulate=False, color_accumulate=False):
+        """MLP -> compositing -> SSE loss [-> gradients] (scripts/nerf.py:67-306).
+        X [R*S][C_in] features, dists [R][S], target [R][3]; returns {name: buffer}.  Gradient
+        outputs ACCUMULATE into buffers passed through `out` (the reference's += semantics)."""
+        R = int(dists.shape[0]) if R is None else R
+        S = int(dists.shape[1]) if S is None else S
+        return self._step(True, dims, X, ws, bs, target, dists, R, S, grad, seed, outputs, out,
+                          rows, path, inter_accumulate, color_accumulate, L.HEAD_NERF)
+
+    def fit_step(self, dims, X, ws, bs, target, grad=False, seed=1.0, outputs=("loss",), out=None,
+                 rows=None, path="f32", inter_accumulate=False):
+        """MLP (sigmoid head) -> SSE loss vs target [-> gradients] (scripts/mlp_fit.py:39-174)."""
+        return self._step(False, dims, X, ws, bs, target, None, int(target.shape[0]), 1, grad, seed,
+                          outputs, out, rows, path, inter_accumulate, False, L.HEAD_SIGMOID)
+
+    # -------------------------------------------------------------------------------------------
+    def pos_encoding(self, x, E):
+        """pos_encoding.py:4-70 on the device: x (..., F) float64 cuda -> (..., F*(1+2E)) float32."""
+        assert _is_cuda(x) and x.dtype == torch.float64 and x.is_contiguous()
+        F = int(x.shape[-1])
+        n = x.numel() // F
+        o = torch.empty(tuple(x.shape[:-1]) + (F * (1 + 2 * E),), dtype=torch.float32, device=x.device)
+        self._check(self.lib.lnb_pos_encoding(self.h, x.data_ptr(), n, F, int(E), o.data_ptr()))
+        return o
+
+    def sample_encode(self, rays_o, rays_d, t, E):
+        """train_nerf.py:289-311 + pos_encoding_3d: returns X [R*S][3+6E] f32 and dists [R][S]."""
+        assert all(_is_cuda(v) and v.dtype == torch.float64 and v.is_contiguous() for v in (rays_o, rays_d, t))
+        R, S = int(t.shape[0]), int(t.shape[1])
+        X = torch.empty((R * S, 3 + 6 * E), dtype=torch.float32, device=t.device)
+        dists = torch.empty((R, S), dtype=torch.float32, device=t.device)
+        self._check(self.lib.lnb_sample_encode(self.h, rays_o.data_ptr(), rays_d.data_ptr(),
+                                               t.data_ptr(), R, S, int(E), X.data_ptr(), dists.data_ptr()))
+        return X, dists
+
+    def mult_a_b(self, a, b, c):
+        """c += a @ b on the device (scripts/mlp_fit.py:150-172)."""
+        self._check(self.lib.lnb_mult_a_b(self.h, a.data_ptr(), int(a.shape[0]), int(a.shape[1]),
+                                          b.data_ptr(), int(b.shape[1]), c.data_ptr()))
+        return c
+
+    def adam_step(self, param, grad, m, v, t, lr=5e-4, beta1=0.9, beta2=0.999, eps=1e-8):
+        """AdamOptimizer.update of train_nerf.py:133-161 (double bias correction kept), in place."""
+        self._check(self.lib.lnb_adam_step(self.h, param.data_ptr(), grad.data_ptr(), m.data_ptr(),
+                                           v.data_ptr(), param.numel(), int(t), lr, beta1, beta2, eps))
+
+    def sgd_step(self, param, grad, lr):
+        """ws -= lr * d_ws (fit_img.py:512-513), in place."""
+        self._check(self.lib.lnb_sgd_step(self.h, param.data_ptr(), grad.data_ptr(), param.numel(), lr))

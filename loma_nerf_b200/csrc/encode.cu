@@ -1,0 +1,77 @@
+// encode.cu -- sample generation and positional encoding on the device.
+// Reference: /root/reference/pos_encoding.py:4-70 (float64 sin/cos of 2^i x, cast to float32,
+// feature index = slot*F + coord) and train_nerf.py:289-311 (pts = o + d t, dists, last = 1e8).
+// The exact variants here compute in float64 like the reference; the fused tensor-core path has
+// its own fp32 prologue (fused_tc.cu) with the error bound stated in DESIGN.md.
+#include "lnb_internal.h"
+
+namespace {
+
+__global__ void pos_encoding_kernel(const double *__restrict__ x, long long n, int F, int E,
+                                    float *__restrict__ out)
+{
+    // one thread per (point, coord): writes 1 + 2E features with stride F
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * F) return;
+    long long p = e / F;
+    int f = (int)(e % F);
+    const int C = F * (1 + 2 * E);
+    double v = x[e];
+    float *o = out + p * C;
+    o[f] = (float)v;
+    double freq = 1.0;
+    for (int i = 0; i < E; ++i) {
+        double s, c;
+        sincos(freq * v, &s, &c);
+        o[(2 * i + 1) * F + f] = (float)s;
+        o[(2 * i + 2) * F + f] = (float)c;
+        freq *= 2.0;
+    }
+}
+
+__global__ void sample_encode_kernel(const double *__restrict__ o, const double *__restrict__ d,
+                                     const double *__restrict__ t, int R, int S, int E,
+                                     float *__restrict__ X, float *__restrict__ dists)
+{
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)R * S * 3) return;
+    long long smp = e / 3;
+    int f = (int)(e % 3);
+    int r = (int)(smp / S), s = (int)(smp % S);
+    const int C = 3 * (1 + 2 * E);
+    double tt = t[smp];
+    double v = o[r * 3 + f] + d[r * 3 + f] * tt;
+    float *x = X + smp * C;
+    x[f] = (float)v;
+    double freq = 1.0;
+    for (int i = 0; i < E; ++i) {
+        double sn, cs;
+        sincos(freq * v, &sn, &cs);
+        x[(2 * i + 1) * 3 + f] = (float)sn;
+        x[(2 * i + 2) * 3 + f] = (float)cs;
+        freq *= 2.0;
+    }
+    if (f == 0 && dists) dists[smp] = (s + 1 < S) ? (float)(t[smp + 1] - tt) : (float)1e8;
+}
+
+} // namespace
+
+int lnb_launch_pos_encoding(lnb_ctx *ctx, const double *x, long long n, int F, int E, float *out)
+{
+    long long tot = n * F;
+    if (tot <= 0) return LNB_OK;
+    pos_encoding_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(x, n, F, E, out);
+    LNB_CHECK_LAUNCH();
+    return LNB_OK;
+}
+
+int lnb_launch_sample_encode(lnb_ctx *ctx, const double *o, const double *d, const double *t,
+                             int R, int S, int E, float *X, float *dists)
+{
+    long long tot = (long long)R * S * 3;
+    if (tot <= 0) return LNB_OK;
+    sample_encode_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(o, d, t, R, S, E,
+                                                                                X, dists);
+    LNB_CHECK_LAUNCH();
+    return LNB_OK;
+}

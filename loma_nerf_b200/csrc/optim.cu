@@ -1,0 +1,53 @@
+// optim.cu -- the two optimisers the reference hosts apply to the padded weight arrays.
+//   Adam: /root/reference/train_nerf.py:133-161, INCLUDING its double bias correction
+//         (lr_t already carries sqrt(1-b2^t)/(1-b1^t), and m_hat/v_hat divide again).
+//   SGD : /root/reference/fit_img.py:512-513.
+// The reference evaluates these in numpy float32 arrays with Python-float (double) scalars; the
+// scalar factors are computed in double on the host here and passed down as floats.
+#include <math.h>
+
+#include "lnb_internal.h"
+
+namespace {
+__global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g,
+                            float *__restrict__ m, float *__restrict__ v, long long n, float b1,
+                            float b2, float omb1, float omb2, float lr_t, float inv_c1,
+                            float inv_c2, float eps)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float gi = g[i];
+    float mi = b1 * m[i] + omb1 * gi;
+    float vi = b2 * v[i] + omb2 * (gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    float m_hat = mi * inv_c1, v_hat = vi * inv_c2;
+    p[i] -= lr_t * m_hat / (sqrtf(v_hat) + eps);
+}
+__global__ void sgd_kernel(float *__restrict__ p, const float *__restrict__ g, long long n, float lr)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] -= lr * g[i];
+}
+} // namespace
+
+int lnb_launch_adam(lnb_ctx *ctx, float *p, const float *g, float *m, float *v, long long n, int t,
+                    float lr, float b1, float b2, float eps)
+{
+    if (n <= 0) return LNB_OK;
+    double c1 = 1.0 - pow((double)b1, t), c2 = 1.0 - pow((double)b2, t);
+    double lr_t = (double)lr * (sqrt(c2) / c1);
+    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+        p, g, m, v, n, b1, b2, (float)(1.0 - (double)b1), (float)(1.0 - (double)b2), (float)lr_t,
+        (float)(1.0 / c1), (float)(1.0 / c2), eps);
+    LNB_CHECK_LAUNCH();
+    return LNB_OK;
+}
+
+int lnb_launch_sgd(lnb_ctx *ctx, float *p, const float *g, long long n, float lr)
+{
+    if (n <= 0) return LNB_OK;
+    sgd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(p, g, n, lr);
+    LNB_CHECK_LAUNCH();
+    return LNB_OK;
+}

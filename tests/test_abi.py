@@ -1,0 +1,108 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library builds, loads, exports every symbol
+include/loma_nerf_b200.h declares, the Python struct mirror matches the C layout, the
+`compiler.compile` shim binds the reference's argtypes, and nothing falls back to the CPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, "include", "loma_nerf_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from loma_nerf_b200 import build, _lib
+    build.build_library()
+    return _lib.load()
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"LNB_API\s+[\w\s\*]+?\b(\w+)\s*\(", src)))
+
+
+def test_header_declares_the_reference_symbols():
+    syms = declared_symbols()
+    for s in ["nerf_evaluate_and_march", "grad_nerf_evaluate_and_march", "mlp_fit", "grad_mlp_fit",
+              "mult_a_b", "lnb_nerf_step", "lnb_fit_step", "lnb_nerf_step_host"]:
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for s in declared_symbols():
+        assert hasattr(lib, s), s
+
+
+def test_struct_mirror_matches_c_layout(lib):
+    from loma_nerf_b200 import _lib as L
+    out = (ctypes.c_int * 16)()
+    n = lib.lnb_struct_layout(out, 16)
+    A = L.LnbStepArgs
+    mine = [ctypes.sizeof(L.LnbMlp), ctypes.sizeof(A), A.X.offset, A.inter.offset, A.rgba.offset,
+            A.loss.offset, A.want_grad.offset, A.d_ws.offset, A.path.offset]
+    assert n == len(mine)
+    assert list(out[:n]) == mine
+    assert lib.lnb_abi_version() == 1
+
+
+def test_compile_shim_binds_reference_argtypes(lib):
+    from loma_nerf_b200 import compiler
+    src = "def nerf_evaluate_and_march(a):\n    pass\ngrad_nerf_evaluate_and_march = rev_diff(nerf_evaluate_and_march)\n"
+    structs, l2 = compiler.compile(src, target="c", output_filename="_code/nerf")
+    assert structs == {}
+    assert len(l2.nerf_evaluate_and_march.argtypes) == 20          # scripts/nerf.py:1-22
+    assert len(l2.grad_nerf_evaluate_and_march.argtypes) == 41     # reverse_diff.py:504-517
+    assert len(l2.mlp_fit.argtypes) == 14 and len(l2.grad_mlp_fit.argtypes) == 29
+    assert l2.nerf_evaluate_and_march.restype is ctypes.c_float
+    assert l2.grad_mlp_fit.restype is None
+    with pytest.raises(NotImplementedError):
+        compiler.compile("def something_else(x):\n    pass\n")
+
+
+def test_reference_sources_are_accepted_by_the_shim(lib):
+    """The function names of the reference's two loma programs (scripts/nerf.py:1,306;
+    scripts/mlp_fit.py:1,150,174), as the hosts pass them."""
+    from loma_nerf_b200 import compiler
+    nerf = "def nerf_evaluate_and_march(x):\n    pass\n\ngrad_nerf_evaluate_and_march = rev_diff(nerf_evaluate_and_march)\n"
+    fit = ("def mlp_fit(x):\n    pass\n\ndef mult_a_b(a):\n    pass\n\n"
+           "grad_mlp_fit = rev_diff(mlp_fit)\n# fwd_mlp_fit = fwd_diff(mlp_fit)\n")
+    compiler.compile(nerf)
+    compiler.compile(fit)
+
+
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device the product must refuse to run, not compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from loma_nerf_b200 import api
+    assert lib.lnb_device_count() == 0
+    with pytest.raises(api.LnbError):
+        api.Context()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "loma_nerf_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+                assert "nerf_oracle" not in txt and "liboracle" not in txt, f
+
+
+def test_marshal_views_are_zero_copy():
+    import numpy as np
+    from loma_nerf_b200 import marshal
+    a = np.arange(24, dtype=np.float32).reshape(2, 3, 4)
+    r = marshal.as_ragged(a)
+    assert r.ptr[1][2][3] == 23.0
+    r.ptr[1][2][3] = -1.0
+    assert r.array[1, 2, 3] == -1.0
+    b = marshal.as_ragged(np.arange(6, dtype=np.int32).reshape(3, 2))
+    assert b.ptr[2][1] == 5
+    assert np.array_equal(marshal.ragged_to_numpy(r.ptr, (2, 3, 4)), r.array)
