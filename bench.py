@@ -1,0 +1,322 @@
+#!/usr/bin/env python3
+"""bench.py -- NeRF train-step throughput (forward + backward + optimiser) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (host cores)
+
+Workload (BASELINE.json configs[1], "C2"): the reference MLP 33->30->30->4 (5-band positional
+encoding of xyz), 64 stratified samples per ray, 4096-ray batches, synthetic rays (data/lego is not
+shipped).  A step = MLP forward, compositing, SSE loss, full reverse-mode gradient (d_ws, d_bs),
+[N>1: NCCL all-reduce of the gradient buffer], Adam update -- per GPU on its own 4096-ray shard
+(weak scaling).  `value` = samples/s over all GPUs with inputs resident in HBM; `e2e` = the same
+step through the host-pointer C-ABI call (features, dists, targets copied from pinned host memory
+every step, loss and gradients copied back).  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "nerf_train_samples_per_s"
+UNIT = "samples/s"
+WORKLOADS = {
+    # name: (E bands, width, layers, rays per batch, samples per ray)
+    "c2": dict(E=5, width=30, layers=3, R=4096, S=64),
+    "c5": dict(E=10, width=256, layers=9, R=4096, S=192),
+}
+
+
+def workload_config(name, n_gpus, extra=None):
+    w = WORKLOADS[name]
+    c_in = 3 + 6 * w["E"]
+    cfg = {"workload": "nerf-train %s: MLP %d->%s->4, %d rays x %d samples per GPU per step" % (
+        name.upper(), c_in, "x".join([str(w["width"])] * (w["layers"] - 1)), w["R"], w["S"]),
+        "rays_per_gpu": w["R"], "samples_per_ray": w["S"], "global_rays": w["R"] * n_gpus,
+        "sharding": "rays across %d GPU(s), gradient all-reduce" % n_gpus if n_gpus > 1 else "single GPU"}
+    cfg.update(extra or {})
+    return cfg
+
+
+def flops_per_sample(dims):
+    return 3 * 2 * sum(dims[l] * dims[l + 1] for l in range(len(dims) - 1))  # F_train
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation on the host cores
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import cpu_bench
+    import multiprocessing as mp
+    w = WORKLOADS[args.workload]
+    if args.workload != "c2":
+        print(json.dumps({"impl": "reference", "unavailable": "reference arm is timed on the C2 workload only"}))
+        return 0
+    cores = cpu_bench.host_cores()
+    chunks = 24   # per core per step: 24 chunks x 256 samples, ~0.25 s of C time
+    with mp.get_context("fork").Pool(cores) as pool:
+        for _ in range(args.warmup):
+            cpu_bench.run(cores, 2, S=w["S"], pool=pool)
+        tot_s, tot_n = 0.0, 0
+        for _ in range(args.steps):
+            r = cpu_bench.run(cores, chunks, S=w["S"], pool=pool)
+            tot_s += r["seconds"]
+            tot_n += r["samples"]
+    value = tot_n / tot_s
+    sample = ("each step: %d cores x %d chunks x 256 samples (4 rays x 64) of the C2 workload, forward call + grad call "
+              "per chunk as train_nerf.py does, time inside the C calls only" % (cores, chunks))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args.workload, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": r["kind"], "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from loma_nerf_b200 import api, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the CUDA library has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    w = WORKLOADS[args.workload]
+    E, R, S = w["E"], w["R"], w["S"]
+    c_in = 3 + 6 * E
+    dims = synthetic.mlp_dims(c_in, w["width"], w["layers"], 4)
+    N = R * S
+    path = args.path
+
+    ctx = api.Context(local)
+    stream = torch.cuda.current_stream(device)
+    ctx.set_stream(stream)
+
+    # ---- synthetic inputs: a pool of batches larger than L2 (126 MB), rotated every step
+    rng = np.random.default_rng(215 + 1000 * rank)          # the reference seeds numpy with 215
+    bytes_per_batch = N * c_in * 4 + N * 4 + R * 12
+    n_pool = max(2, int(np.ceil(160e6 / bytes_per_batch)) + 1)
+    batches = []
+    for _ in range(n_pool):
+        o, d = synthetic.random_rays(rng, R)
+        t = synthetic.stratified_t(rng, R, S)
+        X, dists = ctx.sample_encode(torch.as_tensor(o, device=device), torch.as_tensor(d, device=device),
+                                     torch.as_tensor(t, device=device), E)
+        target = torch.as_tensor(rng.uniform(0, 1, (R, 3)).astype(np.float32), device=device)
+        batches.append((X, dists, target))
+    ws_np, bs_np = synthetic.init_mlp(np.random.default_rng(216), dims)   # same weights on every rank
+    nW, nB = ws_np.size, bs_np.size
+    params = torch.empty(nW + nB, dtype=torch.float32, device=device)
+    params[:nW] = torch.as_tensor(ws_np.ravel(), device=device)
+    params[nW:] = torch.as_tensor(bs_np.ravel(), device=device)
+    ws, bs = params[:nW].view(ws_np.shape), params[nW:].view(bs_np.shape)
+    grads = torch.zeros(nW + nB + 1, dtype=torch.float32, device=device)   # [d_ws, d_bs, loss]
+    out = {"d_ws": grads[:nW].view(ws_np.shape), "d_bs": grads[nW:nW + nB].view(bs_np.shape),
+           "loss": grads[nW + nB:]}
+    adam_m, adam_v = torch.zeros_like(params), torch.zeros_like(params)
+    state = {"t": 0}
+
+    def step(i):
+        X, dists, target = batches[i % n_pool]
+        grads.zero_()
+        ctx.nerf_step(dims, X, ws, bs, dists, target, R=R, S=S, grad=True, seed=1.0, outputs=("loss",),
+                      out=out, path=path)
+        if world > 1:
+            dist.all_reduce(grads)                      # NCCL sum over NVLink: gradients + loss
+        state["t"] += 1
+        ctx.adam_step(params, grads[:nW + nB], adam_m, adam_v, state["t"], lr=5e-4)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for i in range(steps):
+            fn(i)
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.15)
+    l0 = ctx.launches
+    ms = timed(step, args.steps)
+    launches = ctx.launches - l0
+    loss_now = float(grads[nW + nB].item())
+    value = world * N * args.steps / (ms * 1e-3)
+
+    # ---- dominant-kernel roofline: CUDA events around that kernel alone, same inputs
+    prof = ctx.profile_dominant(lambda: [step(i) for i in range(args.steps)]) if hasattr(ctx, "profile_dominant") else None
+
+    # ---- e2e: the host-pointer C-ABI call, pinned host buffers, copies inside the timed region
+    hb = []
+    for b in range(2):
+        Xh, dh, th = (t.cpu().pin_memory() for t in batches[b])
+        hb.append((Xh, dh, th))
+    ws_h, bs_h = ws.cpu().pin_memory(), bs.cpu().pin_memory()
+    g_ws = torch.zeros(ws_np.shape).pin_memory()
+    g_bs = torch.zeros(bs_np.shape).pin_memory()
+    loss_h = torch.zeros(1).pin_memory()
+    hout = {"d_ws": g_ws.numpy(), "d_bs": g_bs.numpy(), "loss": loss_h.numpy()}
+
+    def e2e_step(i):
+        Xh, dh, th = hb[i % 2]
+        g_ws.zero_(); g_bs.zero_()
+        ctx.nerf_step(dims, Xh.numpy(), ws_h.numpy(), bs_h.numpy(), dh.numpy(), th.numpy(), R=R, S=S, grad=True,
+                      seed=1.0, outputs=("loss",), out=hout, path=path)
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    torch.cuda.synchronize(device)
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=device)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * N * e2e_steps / float(e2e_s.item())
+    h2d = (N * c_in + N + R * 3 + nW + nB) * 4
+    d2h = (nW + nB + 1) * 4
+    clk = clocks.stop() if rank == 0 else None
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if path != "tc" else "bf16",
+                "data": "synthetic",
+                "config": workload_config(args.workload, world, {
+                    "path": path, "l2": "inputs rotate over %d batches (%.0f MB) > 126 MB L2" % (n_pool, n_pool * bytes_per_batch / 1e6),
+                    "optimizer": "Adam (train_nerf.py:133-161) inside the step", "loss_last_step": loss_now}),
+                "clocks": clk, "gpu_launches": launches,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": e2e_steps, "api": "lnb_nerf_step_host (pinned host buffers)"}}
+        fl = flops_per_sample(dims)
+        if prof:
+            peak_tf = peaks.get("bf16_tflops", 1590.0)
+            ach = prof["units_per_launch"] * fl / (prof["ms_per_launch"] * 1e-3) / 1e12
+            line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                                "traffic": None, "kernel": prof["kernel"], "ms_per_launch": prof["ms_per_launch"],
+                                "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.59 PFLOP/s"}
+        else:
+            # no single dominant kernel on the layerwise path: report the whole step against HBM
+            peak = peaks.get("hbm_gbs", 6650.0)
+            alg_bytes = N * (c_in * 4 + 4) + R * 12
+            ach = alg_bytes / (ms / args.steps * 1e-3) / 1e9
+            line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                "traffic": None, "kernel": "whole step (layerwise kernels)",
+                                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import cpu_bench
+            cores = cpu_bench.host_cores()
+            r = cpu_bench.run(cores, 40, S=S)
+            line["cpu_baseline"] = {"value": r["samples"] / r["seconds"], "unit": UNIT, "cores": cores, "kind": r["kind"],
+                                    "sample": "%d cores x 40 chunks x 256 samples (4 rays x 64), forward + grad call per chunk, "
+                                              "time inside the C calls only" % cores}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--path", default="f32", choices=["f32", "tc", "f32_layerwise"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

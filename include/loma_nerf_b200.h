@@ -205,10 +205,12 @@ LNB_API int lnb_mult_a_b(lnb_ctx *ctx, const float *a, int a_h, int a_w, const f
 /* Optimisers the reference hosts apply to the padded arrays, n floats each.
  * lnb_adam_step reproduces AdamOptimizer.update (train_nerf.py:133-161) including its double
  * bias correction; t is the 1-based step count AFTER increment.  lnb_sgd_step: p -= lr * g
- * (fit_img.py:512-513).  Device pointers. */
+ * (fit_img.py:512-513).  Device pointers.  The hyper-parameters are doubles because the
+ * reference holds them as Python floats and derives (1-beta), the bias corrections and lr_t in
+ * double before they meet the float32 arrays. */
 LNB_API int lnb_adam_step(lnb_ctx *ctx, float *param, const float *grad, float *m, float *v, long long n,
-                  int t, float lr, float beta1, float beta2, float eps);
-LNB_API int lnb_sgd_step(lnb_ctx *ctx, float *param, const float *grad, long long n, float lr);
+                  int t, double lr, double beta1, double beta2, double eps);
+LNB_API int lnb_sgd_step(lnb_ctx *ctx, float *param, const float *grad, long long n, double lr);
 
 /* Process-wide default context used by the compat symbols (created lazily on first call,
  * device from LOMA_NERF_B200_DEVICE or 0). Returns NULL when no CUDA device is usable. */

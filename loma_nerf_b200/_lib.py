@@ -86,8 +86,8 @@ def load():
                                       c_void_p, c_void_p]
     lib.lnb_mult_a_b.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]
     lib.lnb_adam_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
-                                  c_int, c_float, c_float, c_float, c_float]
-    lib.lnb_sgd_step.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_float]
+                                  c_int, c_double, c_double, c_double, c_double]
+    lib.lnb_sgd_step.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_double]
     lib.lnb_default_ctx.restype = c_void_p
     lib.lnb_struct_layout.argtypes = [P(c_int), c_int]
     lib.lnb_struct_layout.restype = c_int

@@ -483,7 +483,9 @@ int step_host(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, bool ner
             const void *src = b.host_in;
             if (b.pin) { memcpy(b.pin, b.host_in, b.bytes); src = b.pin; }
             LNB_CUDA(cudaMemcpyAsync(dptr, src, b.bytes, cudaMemcpyHostToDevice, ctx->stream));
-        } else if (b.kind == BUF_OUT_ACC) {
+        } else {
+            // accumulating outputs start from zero; overwritten outputs too, so that the parts a
+            // kernel never writes (padding columns of inter) come back as zeros, not stale bytes
             LNB_CUDA(cudaMemsetAsync(dptr, 0, b.bytes, ctx->stream));
         }
     }
@@ -556,7 +558,7 @@ extern "C" int lnb_mult_a_b(lnb_ctx *ctx, const float *a, int a_h, int a_w, cons
 }
 
 extern "C" int lnb_adam_step(lnb_ctx *ctx, float *param, const float *grad, float *m, float *v,
-                             long long n, int t, float lr, float beta1, float beta2, float eps)
+                             long long n, int t, double lr, double beta1, double beta2, double eps)
 {
     if (!ctx) return LNB_ERR_ARG;
     LNB_ARG(param && grad && m && v && n >= 0 && t >= 1, "adam arguments");
@@ -564,7 +566,7 @@ extern "C" int lnb_adam_step(lnb_ctx *ctx, float *param, const float *grad, floa
     return lnb_launch_adam(ctx, param, grad, m, v, n, t, lr, beta1, beta2, eps);
 }
 
-extern "C" int lnb_sgd_step(lnb_ctx *ctx, float *param, const float *grad, long long n, float lr)
+extern "C" int lnb_sgd_step(lnb_ctx *ctx, float *param, const float *grad, long long n, double lr)
 {
     if (!ctx) return LNB_ERR_ARG;
     LNB_ARG(param && grad && n >= 0, "sgd arguments");

@@ -134,5 +134,5 @@ int lnb_launch_pos_encoding(lnb_ctx *ctx, const double *x, long long n, int F, i
 int lnb_launch_sample_encode(lnb_ctx *ctx, const double *o, const double *d, const double *t,
                              int R, int S, int E, float *X, float *dists);
 int lnb_launch_adam(lnb_ctx *ctx, float *p, const float *g, float *m, float *v, long long n, int t,
-                    float lr, float b1, float b2, float eps);
-int lnb_launch_sgd(lnb_ctx *ctx, float *p, const float *g, long long n, float lr);
+                    double lr, double b1, double b2, double eps);
+int lnb_launch_sgd(lnb_ctx *ctx, float *p, const float *g, long long n, double lr);

@@ -11,8 +11,8 @@
 namespace {
 __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g,
                             float *__restrict__ m, float *__restrict__ v, long long n, float b1,
-                            float b2, float omb1, float omb2, float lr_t, float inv_c1,
-                            float inv_c2, float eps)
+                            float b2, float omb1, float omb2, float lr_t, float c1,
+                            float c2, float eps)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -21,7 +21,7 @@ __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g,
     float vi = b2 * v[i] + omb2 * (gi * gi);
     m[i] = mi;
     v[i] = vi;
-    float m_hat = mi * inv_c1, v_hat = vi * inv_c2;
+    float m_hat = mi / c1, v_hat = vi / c2;
     p[i] -= lr_t * m_hat / (sqrtf(v_hat) + eps);
 }
 __global__ void sgd_kernel(float *__restrict__ p, const float *__restrict__ g, long long n, float lr)
@@ -32,22 +32,23 @@ __global__ void sgd_kernel(float *__restrict__ p, const float *__restrict__ g, l
 } // namespace
 
 int lnb_launch_adam(lnb_ctx *ctx, float *p, const float *g, float *m, float *v, long long n, int t,
-                    float lr, float b1, float b2, float eps)
+                    double lr, double b1, double b2, double eps)
 {
     if (n <= 0) return LNB_OK;
-    double c1 = 1.0 - pow((double)b1, t), c2 = 1.0 - pow((double)b2, t);
-    double lr_t = (double)lr * (sqrt(c2) / c1);
+    // python-float scalars meet float32 arrays: each scalar is rounded to float32 once
+    double c1 = 1.0 - pow(b1, t), c2 = 1.0 - pow(b2, t);
+    double lr_t = lr * (sqrt(c2) / c1);
     adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
-        p, g, m, v, n, b1, b2, (float)(1.0 - (double)b1), (float)(1.0 - (double)b2), (float)lr_t,
-        (float)(1.0 / c1), (float)(1.0 / c2), eps);
+        p, g, m, v, n, (float)b1, (float)b2, (float)(1.0 - b1), (float)(1.0 - b2), (float)lr_t,
+        (float)c1, (float)c2, (float)eps);
     LNB_CHECK_LAUNCH();
     return LNB_OK;
 }
 
-int lnb_launch_sgd(lnb_ctx *ctx, float *p, const float *g, long long n, float lr)
+int lnb_launch_sgd(lnb_ctx *ctx, float *p, const float *g, long long n, double lr)
 {
     if (n <= 0) return LNB_OK;
-    sgd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(p, g, n, lr);
+    sgd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(p, g, n, (float)lr);
     LNB_CHECK_LAUNCH();
     return LNB_OK;
 }
