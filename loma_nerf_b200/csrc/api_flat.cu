@@ -359,19 +359,18 @@ int step_layerwise(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, boo
 
 } // namespace
 
-// fused paths (fused_f32.cu); return LNB_ERR_UNSUPPORTED when the problem does not fit them
-int lnb_fused_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, bool nerf);
+// fused tensor-core step (fused_tc.cu); LNB_ERR_UNSUPPORTED when the problem does not fit it
+int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, bool nerf);
 
 static int step_dispatch(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, bool nerf)
 {
     if (!ctx) return LNB_ERR_ARG;
     LNB_ARG(a, "null args");
-    if (a->path == LNB_PATH_F32_LAYERWISE) return step_layerwise(ctx, mlp, a, nerf);
-    if (a->path == LNB_PATH_F32 || a->path == LNB_PATH_TC) {
-        int rc = lnb_fused_step(ctx, mlp, a, nerf);
-        if (rc != LNB_ERR_UNSUPPORTED) return rc;
-        if (a->path == LNB_PATH_TC) return rc; // never silently change arithmetic
-        return step_layerwise(ctx, mlp, a, nerf);
+    if (a->path == LNB_PATH_F32 || a->path == LNB_PATH_F32_LAYERWISE) return step_layerwise(ctx, mlp, a, nerf);
+    if (a->path == LNB_PATH_TC) {
+        StepDims d;
+        LNB_TRY(validate(ctx, mlp, a, nerf, &d));
+        return lnb_fused_tc_step(ctx, mlp, a, nerf); // never silently changes arithmetic
     }
     LNB_ARG(false, "unknown path");
     return LNB_ERR_ARG;

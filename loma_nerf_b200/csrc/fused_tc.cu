@@ -1,0 +1,601 @@
+// fused_tc.cu -- the fused tensor-core train / render step for small coordinate MLPs (sm_100a).
+//
+// ONE kernel does, per 128-sample tile held by a persistent CTA:
+//   features -> bf16 A tile in shared memory            (scripts/nerf.py layer_input)
+//   L x [ tcgen05.mma (M=128 samples, N=width, fp32 accumulators in TMEM)
+//         -> tcgen05.ld epilogue: +bias, ReLU -> bf16 -> next layer's A tile ]  (nerf.py:67-146)
+//   head: sigmoid rgb / ReLU sigma (nerf.py:147-167) or sigmoid (mlp_fit.py:121-132)
+//   per-ray compositing with warp-shuffle product scans (nerf.py:176-288), SSE loss (:297-302)
+//   reverse: compositing adjoint (reverse affine scan, no division), then per layer
+//         dH = dZ W^T on tcgen05 (the SAME shared-memory copy of W, addressed MN-major),
+//         ReLU mask from the stored activations, and
+//         dW_l += H_l^T dZ_l on tcgen05 with the contraction over the tile's 128 samples,
+//         accumulated in TMEM across ALL tiles of the CTA (bias gradient = an all-ones feature).
+//   one write of the CTA's dW / loss partials at the end; a tiny second kernel reduces the
+//   partials over CTAs in a fixed order and applies the seed (grads are linear
+//   in _dreturn, the hosts pass the loss).
+//
+// Operands are bf16 (8-bit mantissa), accumulation fp32: this is LNB_PATH_TC, with the error
+// bound stated in DESIGN.md and asserted in tests/test_gpu_tc.py.  The exact fp32 path is
+// kernels_f32.cu.
+//
+// Shared-memory operand layout ("slab" layout, no swizzle): a [128 rows][F features] bf16 matrix
+// is stored as F/8 slabs of 2048 B; slab c holds features 8c..8c+7 of every row, row r at byte
+// r*16.  One 8x8 block (8 rows x 16 B) is exactly a UMMA core matrix, so the same bytes are
+//   * a K-major  operand with rows as M/N   (SBO = 128 B between 8-row groups, LBO = slab stride)
+//   * an MN-major operand with rows as K    (SBO = slab stride, LBO = 128 B)
+// which is what lets H_l serve as A for the forward MMA and as A^T for the dW MMA, and W_l as B
+// for forward and B^T for backward, without any transposed copy.
+#include <cuda_bf16.h>
+
+#include "lnb_internal.h"
+
+namespace {
+
+constexpr int TILE = 128;          // samples per tile = UMMA M
+constexpr int SLAB = TILE * 16;    // bytes per 8-feature slab
+constexpr int MAXL = 4;            // layers supported by the fused kernel
+
+struct TcParams {
+    const float *X, *dists, *target, *ws, *bs;
+    float *color;      // [R][3] or NULL
+    float *part;       // [grid][part_stride]
+    float *dbg;        // optional [N][4] head outputs (debug)
+    long long N;       // samples (rows of X)
+    int R, S, G, rows_per_tile, n_tiles;
+    int L, dims[MAXL + 1], max_in, max_out;
+    int K0P;           // padded input width (multiple of 16, <= 64)
+    int head, want_grad, Wt;
+    int part_stride;
+    int part_off[MAXL]; // offset of layer l's [(in_l+1) x out_l] block inside a partial
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (uint32_t it = 0; !done; ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (it > (1u << 24)) __trap(); // never hang the GPU: a lost arrival is a bug, fail loudly
+    }
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, SWIZZLE_NONE (cute::UMMA::SmemDescriptor): start>>4 [0,14),
+// LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout_type=0 [61,64)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16
+__device__ __forceinline__ uint32_t instr_desc(int M, int N, int a_mn_major, int b_mn_major)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b)
+{
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+__device__ __forceinline__ float sigmoid_f(float z) { return 1.0f / (1.0f + __expf(0.0f - z)); }
+
+__device__ __forceinline__ float warp_incl_prod(float p, int lane)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        float o = __shfl_up_sync(0xffffffffu, p, d);
+        if (lane >= d) p *= o;
+    }
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel.  HP = padded hidden width (16/32/64): every hidden layer has width+1 <= HP.
+// 128 threads: thread r owns row r of the tile (TMEM lane r).  Thread 0 issues the MMAs.
+// ---------------------------------------------------------------------------------------------
+template <int HP>
+__global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int L = p.L;
+    constexpr int HSL = HP / 8;         // slabs per hidden activation
+    const int K0SL = p.K0P / 8;
+    // ---- carve shared memory
+    // [A0][A1..A_{L-1}][dZ_0..dZ_{L-2}][dZ_{L-1} (2 slabs)][slack 8 slabs][W_0..W_{L-1}][bias][stage][bar]
+    uint8_t *A[MAXL], *DZ[MAXL], *W[MAXL];
+    uint8_t *q = smem;
+    A[0] = q; q += K0SL * SLAB;
+    for (int l = 1; l < L; ++l) { A[l] = q; q += HSL * SLAB; }
+    for (int l = 0; l < L - 1; ++l) { DZ[l] = q; q += HSL * SLAB; }
+    DZ[L - 1] = q; q += 2 * SLAB;
+    uint8_t *act_end = q;
+    q += 8 * SLAB; // M=64 MN-major descriptors read 8 slabs from the start of an A buffer
+    int Np[MAXL], Kp[MAXL];
+    for (int l = 0; l < L; ++l) {
+        Np[l] = (l < L - 1) ? HP : 16;
+        Kp[l] = (l == 0) ? p.K0P : HP;
+        W[l] = q; q += Np[l] * Kp[l] * 2;
+    }
+    float *bias_s = reinterpret_cast<float *>(q); q += MAXL * HP * sizeof(float);
+    float4 *head_s = reinterpret_cast<float4 *>(q); q += TILE * sizeof(float4);
+    float4 *dzh_s = reinterpret_cast<float4 *>(q); q += TILE * sizeof(float4);
+    float *dist_s = reinterpret_cast<float *>(q); q += TILE * sizeof(float);
+    float *red_s = reinterpret_cast<float *>(q); q += 8 * sizeof(float);
+    uint64_t *bar_p = reinterpret_cast<uint64_t *>(q); q += 8;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(q); q += 8;
+    const uint32_t bar = smem_u32(bar_p);
+
+    // ---- one-time setup: zero activations, stage weights (fp32 -> bf16 slabs) and biases
+    for (uint8_t *z = smem + tid * 16; z < act_end + 8 * SLAB; z += TILE * 16) *reinterpret_cast<uint4 *>(z) = make_uint4(0, 0, 0, 0);
+    for (int l = 0; l < L; ++l) {
+        const int in_l = p.dims[l], out_l = p.dims[l + 1];
+        const float *wl = p.ws + (size_t)l * p.max_in * p.max_out;
+        __nv_bfloat16 *ws_ = reinterpret_cast<__nv_bfloat16 *>(W[l]);
+        for (int e = tid; e < Np[l] * Kp[l]; e += TILE) {
+            int k = e / Np[l], j = e % Np[l]; // consecutive threads -> consecutive j (coalesced global)
+            float v = (k < in_l && j < out_l) ? __ldg(wl + (size_t)k * p.max_out + j) : 0.0f;
+            ws_[(k >> 3) * (Np[l] * 8) + j * 8 + (k & 7)] = __float2bfloat16_rn(v);
+        }
+        for (int j = tid; j < HP; j += TILE) bias_s[l * HP + j] = (j < out_l) ? __ldg(p.bs + (size_t)l * p.max_out + j) : 0.0f;
+    }
+    if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    constexpr uint32_t TMEM_COLS = (2 + MAXL) * HP <= 32 ? 32 : ((2 + MAXL) * HP <= 64 ? 64 : ((2 + MAXL) * HP <= 128 ? 128 : ((2 + MAXL) * HP <= 256 ? 256 : 512)));
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    uint32_t phase = 0;
+    float loss_acc = 0.0f;
+    bool dw_started = false;
+
+    // helper lambdas ---------------------------------------------------------------------------
+    auto a_row_ptr = [&](uint8_t *buf, int slab) { return reinterpret_cast<uint4 *>(buf + slab * SLAB + tid * 16); };
+    // forward MMA for layer l into TMEM region reg (0/1): D[128 x Np] = A_l[128 x Kp] * W_l
+    auto issue_fwd = [&](int l, int reg) {
+        const uint32_t idesc = instr_desc(128, Np[l], 0, 0);
+        const uint32_t a0 = smem_u32(A[l]), b0 = smem_u32(W[l]);
+        for (int k = 0; k < Kp[l] / 16; ++k) {
+            uint64_t ad = smem_desc(a0 + k * 2 * SLAB, SLAB, 128);
+            uint64_t bd = smem_desc(b0 + k * 2 * (Np[l] * 16), Np[l] * 16, 128);
+            umma_bf16(tmem + reg * HP, ad, bd, idesc, k > 0);
+        }
+    };
+    // backward dH_l [128 x Kp_l] = dZ_l [128 x Np_l] * W_l^T into region reg
+    auto issue_dh = [&](int l, int reg) {
+        const uint32_t idesc = instr_desc(128, Kp[l], 0, 1);
+        const uint32_t a0 = smem_u32(DZ[l]), b0 = smem_u32(W[l]);
+        for (int k = 0; k < Np[l] / 16; ++k) {
+            uint64_t ad = smem_desc(a0 + k * 2 * SLAB, SLAB, 128);
+            // B^T: N' = in features (MN groups, stride = W slab), K' = out features (8-row groups of 128 B)
+            uint64_t bd = smem_desc(b0 + k * 2 * 128, 128, Np[l] * 16);
+            umma_bf16(tmem + reg * HP, ad, bd, idesc, k > 0);
+        }
+    };
+    // dW_l [64 x Np_l] += A_l^T [64 feats x 128 samples] * dZ_l [128 samples x Np_l]
+    auto issue_dw = [&](int l) {
+        const uint32_t idesc = instr_desc(64, Np[l], 1, 1);
+        const uint32_t a0 = smem_u32(A[l]), b0 = smem_u32(DZ[l]);
+        for (int k = 0; k < TILE / 16; ++k) {
+            uint64_t ad = smem_desc(a0 + k * 256, 128, SLAB);
+            uint64_t bd = smem_desc(b0 + k * 256, 128, SLAB);
+            umma_bf16(tmem + (2 + l) * HP, ad, bd, idesc, (dw_started || k > 0) ? 1u : 0u);
+        }
+    };
+    auto commit_and_wait = [&]() {
+        if (tid == 0) umma_commit(bar);
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+    };
+    auto publish_smem = [&]() { // generic-proxy smem writes -> visible to the tensor core, all threads
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    };
+
+    const int c_in = p.dims[0];
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const long long row0 = (long long)tile * p.rows_per_tile;
+        long long rem = p.N - row0;
+        const int valid = rem < p.rows_per_tile ? (int)rem : p.rows_per_tile;
+        // ---- stage X: coalesced fp32 loads, bf16 scatter into slabs; column c_in := 1 (bias-grad feature)
+        {
+            const float *xt = p.X + row0 * c_in;
+            const int total = valid * c_in;
+            int r = tid / c_in, c = tid % c_in;
+            const int dr = TILE / c_in, dc = TILE % c_in;
+            __nv_bfloat16 *a0 = reinterpret_cast<__nv_bfloat16 *>(A[0]);
+            for (int e = tid; e < TILE * c_in; e += TILE) {
+                float v = e < total ? __ldg(xt + e) : 0.0f;
+                a0[(c >> 3) * (TILE * 8) + r * 8 + (c & 7)] = __float2bfloat16_rn(v);
+                r += dr; c += dc;
+                if (c >= c_in) { c -= c_in; ++r; }
+            }
+            a0[(c_in >> 3) * (TILE * 8) + tid * 8 + (c_in & 7)] = __float2bfloat16_rn(1.0f);
+        }
+        publish_smem();
+        // ---- forward
+        float hz[4];
+        for (int l = 0; l < L; ++l) {
+            if (tid == 0) issue_fwd(l, l & 1);
+            commit_and_wait();
+            const float *bl = bias_s + l * HP;
+            if (l < L - 1) {
+                const int ones_col = p.dims[l + 1];
+#pragma unroll
+                for (int c16 = 0; c16 < HP / 16; ++c16) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem + lane_base + (l & 1) * HP + c16 * 16, v);
+                    tmem_ld_wait();
+                    float f[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        f[j] = fmaxf(__uint_as_float(v[j]) + bl[c16 * 16 + j], 0.0f);
+                        if (c16 * 16 + j == ones_col) f[j] = 1.0f;
+                    }
+                    *a_row_ptr(A[l + 1], c16 * 2) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                    *a_row_ptr(A[l + 1], c16 * 2 + 1) = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
+                }
+                publish_smem();
+            } else {
+                uint32_t v[16];
+                tmem_ld16(tmem + lane_base + (l & 1) * HP, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hz[j] = __uint_as_float(v[j]) + bl[j];
+            }
+        }
+        // ---- head + loss + adjoint of the head's pre-activation (unit seed)
+        float dz[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.head == LNB_HEAD_SIGMOID) {
+            // mlp_fit: row r <-> target row (scripts/mlp_fit.py:121-145)
+            if (tid < valid && row0 + tid < p.R) {
+                const float *tg = p.target + (row0 + tid) * p.Wt;
+                for (int c = 0; c < p.Wt && c < 4; ++c) {
+                    float y = sigmoid_f(hz[c]);
+                    float d = y - __ldg(tg + c);
+                    loss_acc = fmaf(d, d, loss_acc);
+                    dz[c] = 2.0f * d * (y * (1.0f - y));
+                }
+            }
+        } else {
+            float r_ = sigmoid_f(hz[0]), g_ = sigmoid_f(hz[1]), b_ = sigmoid_f(hz[2]);
+            float sg = fmaxf(hz[3], 0.0f);
+            head_s[tid] = make_float4(r_, g_, b_, sg);
+            dist_s[tid] = tid < valid ? __ldg(p.dists + row0 + tid) : 0.0f;
+            if (p.dbg && tid < valid) reinterpret_cast<float4 *>(p.dbg)[row0 + tid] = make_float4(r_, g_, b_, sg);
+            __syncthreads();
+            // warp w composites rays w, w+4, ... of this tile
+            const int rays_here = valid / p.S;
+            const int S = p.S;
+            for (int ry = warp; ry < rays_here; ry += 4) {
+                const int base = ry * S;
+                const long long ray = row0 / S + ry;
+                const int nch = (S + 31) >> 5;
+                float cin[4];   // prefix product entering each chunk (S <= 128)
+                float carry = 1.0f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    if (ch < nch) {
+                        const int s = ch * 32 + lane;
+                        const bool ok = s < S;
+                        float4 h = ok ? head_s[base + s] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        float dist = ok ? dist_s[base + s] : 0.0f;
+                        float a = 1.0f - __expf((0.0f - h.w) * dist);
+                        float qv = ok ? (1.0f - a) + 1e-10f : 1.0f;
+                        cin[ch] = carry;
+                        float pr = warp_incl_prod(qv, lane) * carry;
+                        carry = __shfl_sync(0xffffffffu, pr, 31);
+                        float T = (s == 0) ? 1.0f : pr;
+                        float w = a * T;
+                        if (ok) { c0 = fmaf(w, h.x, c0); c1 = fmaf(w, h.y, c1); c2 = fmaf(w, h.z, c2); }
+                    }
+                }
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) {
+                    c0 += __shfl_xor_sync(0xffffffffu, c0, d);
+                    c1 += __shfl_xor_sync(0xffffffffu, c1, d);
+                    c2 += __shfl_xor_sync(0xffffffffu, c2, d);
+                }
+                if (p.color && lane == 0) { p.color[ray * 3] = c0; p.color[ray * 3 + 1] = c1; p.color[ray * 3 + 2] = c2; }
+                if (!p.target) continue;
+                const float *tg = p.target + ray * 3;
+                const float d0 = c0 - __ldg(tg), d1 = c1 - __ldg(tg + 1), d2 = c2 - __ldg(tg + 2);
+                if (lane == 0) loss_acc += d0 * d0 + d1 * d1 + d2 * d2;
+                if (!p.want_grad) continue;
+                const float dc0 = 2.0f * d0, dc1 = 2.0f * d1, dc2 = 2.0f * d2;
+                float G_next = 0.0f, q_next = 0.0f;
+#pragma unroll
+                for (int ch = 3; ch >= 0; --ch) {
+                    if (ch < nch) {
+                        const int s = ch * 32 + lane;
+                        const bool ok = s < S;
+                        float4 h = ok ? head_s[base + s] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        float dist = ok ? dist_s[base + s] : 0.0f;
+                        const float e = __expf((0.0f - h.w) * dist);
+                        const float a = 1.0f - e;
+                        const float qv = ok ? (1.0f - a) + 1e-10f : 1.0f;
+                        const float Cpre = warp_incl_prod(qv, lane) * cin[ch];
+                        const float T = (s == 0) ? 1.0f : Cpre;
+                        const float w = a * T;
+                        const float d_w = h.x * dc0 + h.y * dc1 + h.z * dc2;
+                        const float dT = (s == 0 || !ok) ? 0.0f : d_w * a;
+                        float qn = __shfl_down_sync(0xffffffffu, qv, 1);
+                        if (lane == 31) qn = q_next;
+                        float Aa = dT, Bb = (ok && s + 1 < S) ? qn : 0.0f;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            float A2 = __shfl_down_sync(0xffffffffu, Aa, d);
+                            float B2 = __shfl_down_sync(0xffffffffu, Bb, d);
+                            if (lane + d < 32) { Aa = fmaf(Bb, A2, Aa); Bb = Bb * B2; }
+                        }
+                        const float Gv = fmaf(Bb, G_next, Aa);
+                        float Cm1 = __shfl_up_sync(0xffffffffu, Cpre, 1);
+                        if (lane == 0) Cm1 = cin[ch];
+                        const float d_alpha = d_w * T - Cm1 * Gv;
+                        if (ok)
+                            dzh_s[base + s] = make_float4((w * dc0) * (h.x * (1.0f - h.x)), (w * dc1) * (h.y * (1.0f - h.y)),
+                                                          (w * dc2) * (h.z * (1.0f - h.z)), h.w > 0.0f ? d_alpha * e * dist : 0.0f);
+                        G_next = __shfl_sync(0xffffffffu, Gv, 0);
+                        q_next = __shfl_sync(0xffffffffu, qv, 0);
+                    }
+                }
+            }
+            __syncthreads();
+            if (p.want_grad && p.target && tid < rays_here * S) {
+                float4 d4 = dzh_s[tid];
+                dz[0] = d4.x; dz[1] = d4.y; dz[2] = d4.z; dz[3] = d4.w;
+            }
+        }
+        if (!p.want_grad) continue;
+        // ---- backward.  dZ_{L-1}: 4 live features, the rest of the 16 stay zero
+        *a_row_ptr(DZ[L - 1], 0) = make_uint4(pack_bf16(dz[0], dz[1]), pack_bf16(dz[2], dz[3]), 0u, 0u);
+        publish_smem();
+        for (int l = L - 1; l >= 0; --l) {
+            if (tid == 0) {
+                issue_dw(l);
+                if (l > 0) issue_dh(l, l & 1);
+            }
+            commit_and_wait(); // also fences the dW reads of A_l / dZ_l before they are overwritten
+            if (l == 0) break;
+            // dZ_{l-1} = dH_l masked by ReLU'(H_l) ; H_l = A[l] (bf16, post-activation)
+#pragma unroll
+            for (int c16 = 0; c16 < HP / 16; ++c16) {
+                uint32_t v[16];
+                tmem_ld16(tmem + lane_base + (l & 1) * HP + c16 * 16, v);
+                tmem_ld_wait();
+                uint4 h0 = *a_row_ptr(A[l], c16 * 2), h1 = *a_row_ptr(A[l], c16 * 2 + 1);
+                uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                float f[16];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    // bf16 post-ReLU values are >= 0: positive <=> non-zero bits
+                    f[2 * j] = (hw[j] & 0xFFFFu) ? __uint_as_float(v[2 * j]) : 0.0f;
+                    f[2 * j + 1] = (hw[j] >> 16) ? __uint_as_float(v[2 * j + 1]) : 0.0f;
+                }
+                *a_row_ptr(DZ[l - 1], c16 * 2) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                *a_row_ptr(DZ[l - 1], c16 * 2 + 1) = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
+            }
+            publish_smem();
+        }
+        dw_started = true;
+    }
+
+    // ---- epilogue: this CTA's partials.  loss, then per layer the valid (in_l+1) x out_l block.
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    float *part = p.part + (size_t)blockIdx.x * p.part_stride;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, d);
+    if (lane == 0) red_s[warp] = loss_acc;
+    __syncthreads();
+    if (tid == 0) part[0] = red_s[0] + red_s[1] + red_s[2] + red_s[3];
+    if (p.want_grad) {
+        for (int l = 0; l < L; ++l) {
+            // M=64 accumulators live in lanes 0..15 of each 32-lane subpartition: row = 16*warp + lane
+            const int row = warp * 16 + lane;
+            const int in_l = p.dims[l], out_l = p.dims[l + 1];
+            float *o = part + p.part_off[l];
+#pragma unroll
+            for (int c16 = 0; c16 < HP / 16; ++c16) {
+                if (c16 * 16 >= Np[l]) break;
+                uint32_t v[16];
+                tmem_ld16(tmem + lane_base + (2 + l) * HP + c16 * 16, v);
+                tmem_ld_wait();
+                if (lane < 16 && row <= in_l) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        int col = c16 * 16 + j;
+                        if (col < out_l) o[row * out_l + col] = dw_started ? __uint_as_float(v[j]) : 0.0f;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// reduce the per-CTA partials in a fixed order; apply the seed; accumulate into the caller's buffers
+__global__ void tc_reduce_kernel(const float *__restrict__ part, int n_part, int part_stride, TcParams p,
+                                 float *__restrict__ d_ws, float *__restrict__ d_bs, float *__restrict__ loss,
+                                 float seed_value, int seed_is_loss)
+{
+    __shared__ float sloss;
+    // every block sums the loss partials itself (same order everywhere) so the seed needs no second pass
+    if (threadIdx.x < 32) {
+        float s = 0.0f;
+        for (int i = threadIdx.x; i < n_part; i += 32) s += part[(size_t)i * part_stride];
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (threadIdx.x == 0) {
+            sloss = s;
+            if (blockIdx.x == 0 && loss) loss[0] = s;
+        }
+    }
+    __syncthreads();
+    if (!d_ws) return;
+    const float scale = seed_is_loss ? sloss * seed_value : seed_value;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int n_el = part_stride - 1;
+    if (warp >= n_el) return;
+    float s = 0.0f;
+    for (int i = lane; i < n_part; i += 32) s += part[(size_t)i * part_stride + 1 + warp];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0) {
+        int e = warp + 1, l = 0;
+        while (l + 1 < p.L && e >= p.part_off[l + 1]) ++l;
+        e -= p.part_off[l];
+        const int out_l = p.dims[l + 1], k = e / out_l, j = e % out_l;
+        if (k < p.dims[l]) d_ws[((size_t)l * p.max_in + k) * p.max_out + j] += scale * s;
+        else d_bs[(size_t)l * p.max_out + j] += scale * s;
+    }
+}
+
+template <int HP>
+size_t smem_bytes(int L, int K0P)
+{
+    size_t b = (size_t)(K0P / 8) * SLAB + (size_t)(L - 1) * (HP / 8) * SLAB * 2 + 2 * SLAB + 8 * SLAB;
+    for (int l = 0; l < L; ++l) b += (size_t)((l < L - 1) ? HP : 16) * ((l == 0) ? K0P : HP) * 2;
+    b += MAXL * HP * sizeof(float) + 2 * TILE * sizeof(float4) + TILE * sizeof(float) + 8 * sizeof(float) + 16;
+    return b + 1024; // alignment slack
+}
+
+} // namespace
+
+// Returns LNB_ERR_UNSUPPORTED when the problem does not fit the fused tensor-core kernel.
+int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, bool nerf)
+{
+    const int L = mlp->n_layers;
+    auto unsupported = [&](const char *why) {
+        ctx->err = std::string("fused tensor-core path: ") + why;
+        return LNB_ERR_UNSUPPORTED;
+    };
+    if (L < 2 || L > MAXL) return unsupported("needs 2..4 layers");
+    int hw = 0;
+    for (int l = 1; l < L; ++l) hw = mlp->dims[l] > hw ? mlp->dims[l] : hw;
+    const int HP = hw + 1 <= 16 ? 16 : (hw + 1 <= 32 ? 32 : (hw + 1 <= 64 ? 64 : 0));
+    if (!HP) return unsupported("hidden width + 1 must be <= 64");
+    const int K0P = (mlp->dims[0] + 1 + 15) / 16 * 16;
+    if (K0P > 64) return unsupported("input width + 1 must be <= 64");
+    if (mlp->dims[L] > 16) return unsupported("more than 16 output channels");
+    if (a->inter || a->rgba || a->alpha || a->cumprod || a->weights || a->d_X || a->d_target || a->d_dists ||
+        a->d_color || a->d_inter)
+        return unsupported("only loss, colour, d_ws and d_bs are produced (use the fp32 path for the rest)");
+    if (a->color && a->color_accumulate) return unsupported("colour accumulation");
+    const int R = a->R, S = nerf ? a->S : 1;
+    const long long N = a->n_rows > 0 ? a->n_rows : (long long)R * S;
+    if (nerf && (S > TILE || N != (long long)R * S)) return unsupported("needs S <= 128 and n_rows == R*S");
+    if (!nerf && N != R) return unsupported("needs n_rows == R");
+    if (a->rows > N) return unsupported("rows > n_rows");
+    if (!nerf && (a->target_w > 4)) return unsupported("target wider than 4");
+    if (a->want_grad && !a->target) return unsupported("gradient without target");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
+
+    TcParams p{};
+    p.X = a->X; p.dists = a->dists; p.target = a->target; p.ws = a->ws; p.bs = a->bs;
+    p.color = nerf ? a->color : nullptr;
+    p.N = N; p.R = R; p.S = S;
+    p.G = nerf ? TILE / S : TILE;
+    p.rows_per_tile = p.G * S;
+    p.n_tiles = (int)((N + p.rows_per_tile - 1) / p.rows_per_tile);
+    p.L = L;
+    for (int l = 0; l <= L; ++l) p.dims[l] = mlp->dims[l];
+    p.max_in = mlp->max_in; p.max_out = mlp->max_out;
+    p.K0P = K0P;
+    p.head = mlp->head; p.want_grad = a->want_grad; p.Wt = a->target_w > 0 ? a->target_w : 3;
+    int off = 1;
+    for (int l = 0; l < L; ++l) { p.part_off[l] = off; off += (mlp->dims[l] + 1) * mlp->dims[l + 1]; }
+    p.part_stride = off;
+
+    size_t smem = HP == 16 ? smem_bytes<16>(L, K0P) : (HP == 32 ? smem_bytes<32>(L, K0P) : smem_bytes<64>(L, K0P));
+    const int tmem_cols = (2 + MAXL) * HP <= 128 ? 128 : ((2 + MAXL) * HP <= 256 ? 256 : 512);
+    int per_sm = 512 / tmem_cols;
+    int by_smem = (int)((227 * 1024) / smem);
+    if (by_smem < per_sm) per_sm = by_smem;
+    if (per_sm < 1) return unsupported("shared memory");
+    int grid = ctx->sm_count * per_sm;
+    if (grid > p.n_tiles) grid = p.n_tiles;
+    if (grid < 1) grid = 1;
+    LNB_TRY(lnb_arena_reserve(ctx, (size_t)grid * p.part_stride * sizeof(float) + 4096));
+    p.part = (float *)lnb_arena_take(ctx, (size_t)grid * p.part_stride * sizeof(float));
+    float *loss = a->loss ? a->loss : (float *)lnb_arena_take(ctx, 16);
+    if (N > 0) {
+#define LNB_TC(HPV)                                                                              \
+    do {                                                                                         \
+        LNB_CUDA(cudaFuncSetAttribute(fused_tc_kernel<HPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        fused_tc_kernel<HPV><<<grid, TILE, smem, ctx->stream>>>(p);                              \
+    } while (0)
+        if (HP == 16) LNB_TC(16);
+        else if (HP == 32) LNB_TC(32);
+        else LNB_TC(64);
+#undef LNB_TC
+        LNB_CHECK_LAUNCH();
+    } else {
+        grid = 0;
+    }
+    const int n_el = p.part_stride - 1;
+    const int seed_is_loss = a->seed_mode == LNB_SEED_LOSS;
+    const float seed_val = seed_is_loss ? 1.0f : a->seed;
+    int blocks = a->want_grad ? (n_el * 32 + 255) / 256 : 1;
+    tc_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(p.part, grid, p.part_stride, p, a->want_grad ? a->d_ws : nullptr,
+                                                      a->want_grad ? a->d_bs : nullptr, loss, seed_val, seed_is_loss);
+    LNB_CHECK_LAUNCH();
+    return LNB_OK;
+}
