@@ -179,17 +179,44 @@ def run_ours(args):
     out = {"d_ws": grads[:nW].view(ws_np.shape), "d_bs": grads[nW:nW + nB].view(bs_np.shape),
            "loss": grads[nW + nB:]}
     adam_m, adam_v = torch.zeros_like(params), torch.zeros_like(params)
-    state = {"t": 0}
+    t_dev = torch.zeros(1, dtype=torch.int32, device=device)
 
-    def step(i):
-        X, dists, target = batches[i % n_pool]
+    def step_body(b):
+        X, dists, target = batches[b]
         grads.zero_()
         ctx.nerf_step(dims, X, ws, bs, dists, target, R=R, S=S, grad=True, seed=1.0, outputs=("loss",),
                       out=out, path=path)
         if world > 1:
             dist.all_reduce(grads)                      # NCCL sum over NVLink: gradients + loss
-        state["t"] += 1
-        ctx.adam_step(params, grads[:nW + nB], adam_m, adam_v, state["t"], lr=5e-4)
+        ctx.adam_step_dev(params, grads[:nW + nB], adam_m, adam_v, t_dev, lr=5e-4)
+
+    # one CUDA graph per input batch (zero -> step kernels -> [all-reduce] -> Adam): one launch per step
+    graphs, launch_mode = [], "cuda-graph per step"
+    if not args.eager:
+        try:
+            for b in range(2):
+                step_body(b)
+            torch.cuda.synchronize(device)
+            for b in range(n_pool):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    ctx.set_stream(torch.cuda.current_stream(device))
+                    step_body(b)
+                graphs.append(g)
+            ctx.set_stream(stream)
+        except Exception as e:  # report, never hide: fall back to eager launches
+            graphs, launch_mode = [], "eager (graph capture failed: %s)" % str(e)[:80]
+            ctx.set_stream(stream)
+            torch.cuda.synchronize(device)
+    else:
+        launch_mode = "eager"
+    kernels_per_step = [0]
+
+    def step(i):
+        if graphs:
+            graphs[i % n_pool].replay()
+        else:
+            step_body(i % n_pool)
 
     def barrier():
         if world > 1:
@@ -217,13 +244,16 @@ def run_ours(args):
         clocks.start()
         time.sleep(0.15)
     l0 = ctx.launches
+    step_body(0)                               # count this library's kernels in one step (eagerly)
+    per_step = ctx.launches - l0
+    barrier()
     ms = timed(step, args.steps)
-    launches = ctx.launches - l0
+    launches = per_step * args.steps
     loss_now = float(grads[nW + nB].item())
     value = world * N * args.steps / (ms * 1e-3)
 
     # ---- dominant-kernel roofline: CUDA events around that kernel alone, same inputs
-    prof = ctx.profile_dominant(lambda: [step(i) for i in range(args.steps)]) if hasattr(ctx, "profile_dominant") else None
+    prof = ctx.profile_dominant(lambda: [step_body(i % n_pool) for i in range(args.steps)])
 
     # ---- e2e: the host-pointer C-ABI call, pinned host buffers, copies inside the timed region
     hb = []
@@ -270,17 +300,23 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": workload_config(args.workload, world, {
                     "path": path, "l2": "inputs rotate over %d batches (%.0f MB) > 126 MB L2" % (n_pool, n_pool * bytes_per_batch / 1e6),
-                    "optimizer": "Adam (train_nerf.py:133-161) inside the step", "loss_last_step": loss_now}),
+                    "optimizer": "Adam (train_nerf.py:133-161) inside the step", "launch": launch_mode,
+                    "loss_last_step": loss_now}),
                 "clocks": clk, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "api": "lnb_nerf_step_host (pinned host buffers)"}}
         fl = flops_per_sample(dims)
         if prof:
-            peak_tf = peaks.get("bf16_tflops", 1590.0)
-            ach = prof["units_per_launch"] * fl / (prof["ms_per_launch"] * 1e-3) / 1e12
-            line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                                "traffic": None, "kernel": prof["kernel"], "ms_per_launch": prof["ms_per_launch"],
-                                "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.59 PFLOP/s"}
+            # the fused kernel reads pre-encoded features: HBM-bound by SURVEY.md 8d's per-unit bytes
+            peak = peaks.get("hbm_gbs", 6650.0)
+            alg_bytes = N * (c_in * 4 + 4) + R * 12          # features + dist per sample, target per ray
+            sec = prof["ms_per_launch"] * 1e-3
+            ach = alg_bytes / sec / 1e9
+            line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                "traffic": None, "kernel": prof["kernel"], "us_per_launch": prof["ms_per_launch"] * 1e3,
+                                "launches_timed": prof["launches"], "algorithmic_bytes_per_launch": alg_bytes,
+                                "algorithmic_tflops": N * fl / sec / 1e12,
+                                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"}
         else:
             # no single dominant kernel on the layerwise path: report the whole step against HBM
             peak = peaks.get("hbm_gbs", 6650.0)
@@ -312,6 +348,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--path", default="f32", choices=["f32", "tc", "f32_layerwise"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

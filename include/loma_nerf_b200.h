@@ -169,12 +169,18 @@ LNB_API int lnb_device_count(void);
 /* device < 0: the current CUDA device. */
 LNB_API int lnb_create(lnb_ctx **out, int device);
 LNB_API void lnb_destroy(lnb_ctx *ctx);
-/* stream is a cudaStream_t (NULL = the context's own non-blocking stream). */
+/* stream is a cudaStream_t: NULL = CUDA's legacy default stream, (void*)-1 = the context's own
+ * non-blocking stream (the initial setting). */
 LNB_API int lnb_set_stream(lnb_ctx *ctx, void *stream);
 LNB_API int lnb_synchronize(lnb_ctx *ctx);
 LNB_API const char *lnb_last_error(lnb_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 LNB_API long long lnb_launch_count(lnb_ctx *ctx);
+/* Kernel timing for roofline reports: while enabled, every launch of the dominant (fused)
+ * kernel is bracketed by CUDA events on the context's stream.  lnb_profile_read synchronises and
+ * returns the summed duration, the launch count and the kernel's name. */
+LNB_API int lnb_profile(lnb_ctx *ctx, int enable);
+LNB_API int lnb_profile_read(lnb_ctx *ctx, double *ms_total, long long *launches, char *name, int name_len);
 /* page-locked host memory for the *_host entry points (they copy straight from / to such
  * buffers; pageable buffers bounce through the context's own pinned staging). */
 LNB_API void *lnb_host_alloc(size_t bytes);
@@ -210,6 +216,10 @@ LNB_API int lnb_mult_a_b(lnb_ctx *ctx, const float *a, int a_h, int a_w, const f
  * double before they meet the float32 arrays. */
 LNB_API int lnb_adam_step(lnb_ctx *ctx, float *param, const float *grad, float *m, float *v, long long n,
                   int t, double lr, double beta1, double beta2, double eps);
+/* Same update with the step counter kept on the device (t = *t_dev + 1, then *t_dev += 1), so a
+ * whole train step can be captured in a CUDA graph and replayed. */
+LNB_API int lnb_adam_step_dev(lnb_ctx *ctx, float *param, const float *grad, float *m, float *v, long long n,
+                      int *t_dev, double lr, double beta1, double beta2, double eps);
 LNB_API int lnb_sgd_step(lnb_ctx *ctx, float *param, const float *grad, long long n, double lr);
 
 /* Process-wide default context used by the compat symbols (created lazily on first call,

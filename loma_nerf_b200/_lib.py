@@ -73,6 +73,8 @@ def load():
     lib.lnb_last_error.restype = c_char_p
     lib.lnb_launch_count.argtypes = [c_void_p]
     lib.lnb_launch_count.restype = c_longlong
+    lib.lnb_profile.argtypes = [c_void_p, c_int]
+    lib.lnb_profile_read.argtypes = [c_void_p, P(c_double), P(c_longlong), c_char_p, c_int]
     lib.lnb_host_alloc.argtypes = [c_size_t]
     lib.lnb_host_alloc.restype = c_void_p
     lib.lnb_host_free.argtypes = [c_void_p]
@@ -87,6 +89,8 @@ def load():
     lib.lnb_mult_a_b.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]
     lib.lnb_adam_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
                                   c_int, c_double, c_double, c_double, c_double]
+    lib.lnb_adam_step_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
+                                      c_void_p, c_double, c_double, c_double, c_double]
     lib.lnb_sgd_step.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_double]
     lib.lnb_default_ctx.restype = c_void_p
     lib.lnb_struct_layout.argtypes = [P(c_int), c_int]

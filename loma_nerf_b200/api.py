@@ -86,9 +86,10 @@ class Context:
             pass
 
     def set_stream(self, stream):
-        """stream: a torch.cuda.Stream, a raw cudaStream_t int, or None (the context's own)."""
-        raw = getattr(stream, "cuda_stream", stream)
-        self._check(self.lib.lnb_set_stream(self.h, ctypes.c_void_p(raw or 0)))
+        """stream: a torch.cuda.Stream, a raw cudaStream_t int (0 = the legacy default stream), or
+        None (the context's own non-blocking stream)."""
+        raw = ctypes.c_void_p(-1) if stream is None else ctypes.c_void_p(getattr(stream, "cuda_stream", stream))
+        self._check(self.lib.lnb_set_stream(self.h, raw))
 
     def use_current_torch_stream(self):
         self.set_stream(torch.cuda.current_stream(self.device))
@@ -99,6 +100,21 @@ class Context:
     @property
     def launches(self):
         return int(self.lib.lnb_launch_count(self.h))
+
+    def profile_dominant(self, fn):
+        """Run fn() with CUDA events around every launch of the dominant (fused) kernel.
+        Returns dict(kernel, launches, ms_per_launch) or None when that kernel never ran."""
+        self._check(self.lib.lnb_profile(self.h, 1))
+        try:
+            fn()
+            ms, n = ctypes.c_double(), ctypes.c_longlong()
+            name = ctypes.create_string_buffer(128)
+            self._check(self.lib.lnb_profile_read(self.h, ctypes.byref(ms), ctypes.byref(n), name, 128))
+        finally:
+            self.lib.lnb_profile(self.h, 0)
+        if n.value == 0:
+            return None
+        return dict(kernel=name.value.decode(), launches=int(n.value), ms_per_launch=ms.value / n.value)
 
     def _check(self, rc):
         if rc != L.LNB_OK:
@@ -202,6 +218,11 @@ class Context:
         """AdamOptimizer.update of train_nerf.py:133-161 (double bias correction kept), in place."""
         self._check(self.lib.lnb_adam_step(self.h, param.data_ptr(), grad.data_ptr(), m.data_ptr(),
                                            v.data_ptr(), param.numel(), int(t), lr, beta1, beta2, eps))
+
+    def adam_step_dev(self, param, grad, m, v, t_dev, lr=5e-4, beta1=0.9, beta2=0.999, eps=1e-8):
+        """adam_step with the step counter in device memory (int32 tensor): graph-capturable."""
+        self._check(self.lib.lnb_adam_step_dev(self.h, param.data_ptr(), grad.data_ptr(), m.data_ptr(),
+                                               v.data_ptr(), param.numel(), t_dev.data_ptr(), lr, beta1, beta2, eps))
 
     def sgd_step(self, param, grad, lr):
         """ws -= lr * d_ws (fit_img.py:512-513), in place."""

@@ -131,13 +131,16 @@ extern "C" void lnb_destroy(lnb_ctx *ctx)
     if (ctx->dstage) cudaFree(ctx->dstage);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     delete ctx;
 }
 
 extern "C" int lnb_set_stream(lnb_ctx *ctx, void *stream)
 {
     if (!ctx) return LNB_ERR_ARG;
-    ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+    // (void*)-1 selects the context's own non-blocking stream; NULL is CUDA's legacy default
+    // stream (what torch.cuda.current_stream() is unless the caller changed it)
+    ctx->stream = stream == (void *)-1 ? ctx->own_stream : (cudaStream_t)stream;
     return LNB_OK;
 }
 
@@ -150,6 +153,52 @@ extern "C" int lnb_synchronize(lnb_ctx *ctx)
 
 extern "C" const char *lnb_last_error(lnb_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 extern "C" long long lnb_launch_count(lnb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+void lnb_prof_begin(lnb_ctx *ctx, const char *name)
+{
+    if (!ctx->prof_on) return;
+    if (ctx->prof_used + 2 > ctx->prof_ev.size()) {
+        cudaEvent_t a, b;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+        ctx->prof_ev.push_back(a);
+        ctx->prof_ev.push_back(b);
+    }
+    ctx->prof_name = name;
+    cudaEventRecord(ctx->prof_ev[ctx->prof_used], ctx->stream);
+}
+void lnb_prof_end(lnb_ctx *ctx)
+{
+    if (!ctx->prof_on || ctx->prof_used + 2 > ctx->prof_ev.size()) return;
+    cudaEventRecord(ctx->prof_ev[ctx->prof_used + 1], ctx->stream);
+    ctx->prof_used += 2;
+}
+
+extern "C" int lnb_profile(lnb_ctx *ctx, int enable)
+{
+    if (!ctx) return LNB_ERR_ARG;
+    ctx->prof_on = enable != 0;
+    ctx->prof_used = 0;
+    return LNB_OK;
+}
+
+extern "C" int lnb_profile_read(lnb_ctx *ctx, double *ms_total, long long *launches, char *name, int name_len)
+{
+    if (!ctx) return LNB_ERR_ARG;
+    LNB_CUDA(cudaStreamSynchronize(ctx->stream));
+    double tot = 0.0;
+    for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
+        float ms = 0.f;
+        LNB_CUDA(cudaEventElapsedTime(&ms, ctx->prof_ev[i], ctx->prof_ev[i + 1]));
+        tot += ms;
+    }
+    if (ms_total) *ms_total = tot;
+    if (launches) *launches = (long long)(ctx->prof_used / 2);
+    if (name && name_len > 0) {
+        strncpy(name, ctx->prof_name.c_str(), (size_t)name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    return LNB_OK;
+}
 
 extern "C" void *lnb_host_alloc(size_t bytes)
 {
@@ -563,6 +612,15 @@ extern "C" int lnb_adam_step(lnb_ctx *ctx, float *param, const float *grad, floa
     LNB_ARG(param && grad && m && v && n >= 0 && t >= 1, "adam arguments");
     if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
     return lnb_launch_adam(ctx, param, grad, m, v, n, t, lr, beta1, beta2, eps);
+}
+
+extern "C" int lnb_adam_step_dev(lnb_ctx *ctx, float *param, const float *grad, float *m, float *v,
+                                 long long n, int *t_dev, double lr, double beta1, double beta2, double eps)
+{
+    if (!ctx) return LNB_ERR_ARG;
+    LNB_ARG(param && grad && m && v && t_dev && n >= 0, "adam arguments");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
+    return lnb_launch_adam_dev(ctx, param, grad, m, v, n, t_dev, lr, beta1, beta2, eps);
 }
 
 extern "C" int lnb_sgd_step(lnb_ctx *ctx, float *param, const float *grad, long long n, double lr)

@@ -582,9 +582,11 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
         LNB_CUDA(cudaFuncSetAttribute(fused_tc_kernel<HPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         fused_tc_kernel<HPV><<<grid, TILE, smem, ctx->stream>>>(p);                              \
     } while (0)
+        lnb_prof_begin(ctx, "fused_tc_kernel");
         if (HP == 16) LNB_TC(16);
         else if (HP == 32) LNB_TC(32);
         else LNB_TC(64);
+        lnb_prof_end(ctx);
 #undef LNB_TC
         LNB_CHECK_LAUNCH();
     } else {

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/loma_nerf_b200.h"
 
@@ -25,7 +26,16 @@ struct lnb_ctx {
     size_t dstage_cap = 0;
     long long launches = 0;
     std::string err;
+    // optional timing of the dominant (fused) kernel: CUDA-event pairs around each launch
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev; // [2*i] start, [2*i+1] stop
+    size_t prof_used = 0;
+    std::string prof_name;
 };
+
+// time the next launch of the dominant kernel when profiling is enabled (api_flat.cu)
+void lnb_prof_begin(lnb_ctx *ctx, const char *name);
+void lnb_prof_end(lnb_ctx *ctx);
 
 #define LNB_CUDA(call)                                                                          \
     do {                                                                                        \
@@ -135,4 +145,6 @@ int lnb_launch_sample_encode(lnb_ctx *ctx, const double *o, const double *d, con
                              int R, int S, int E, float *X, float *dists);
 int lnb_launch_adam(lnb_ctx *ctx, float *p, const float *g, float *m, float *v, long long n, int t,
                     double lr, double b1, double b2, double eps);
+int lnb_launch_adam_dev(lnb_ctx *ctx, float *p, const float *g, float *m, float *v, long long n,
+                        int *t_dev, double lr, double b1, double b2, double eps);
 int lnb_launch_sgd(lnb_ctx *ctx, float *p, const float *g, long long n, double lr);
