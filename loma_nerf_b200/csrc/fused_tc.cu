@@ -139,134 +139,222 @@ __device__ __forceinline__ float warp_incl_prod(float p, int lane)
 
 // ---------------------------------------------------------------------------------------------
 // the kernel.  HP = padded hidden width (16/32/64): every hidden layer has width+1 <= HP.
-// 128 threads: thread r owns row r of the tile (TMEM lane r).  Thread 0 issues the MMAs.
+// 128 threads: thread r owns row r of the tile (TMEM lane r).  Thread 0 issues the MMAs and the
+// bulk-async (TMA) prefetch of the next tile's features.
+//
+// Shared memory (bytes), in this order so that an M=64 MN-major read of A_l (8 slabs from its
+// start) always stays inside live shared memory:
+//   A0 [K0P/8 slabs] | A1 .. A_{L-1} [HP/8 slabs each] | dZ_0 .. dZ_{L-2} [HP/8 each] | dZ_{L-1} [2]
+//   | W_0 .. W_{L-1} (bf16) | bias (fp32) | stage (fp32 features of the NEXT tile, TMA target)
+//   | small per-tile scratch | mbarriers
+// head_s / dzh_s / dist_s (compositing scratch) alias dZ_0, which is only written by the last
+// backward epilogue of a tile.
+// TMEM (128 columns when HP <= 32): R0 [0,HP) and R1 [HP,2HP) ping-pong layer outputs / dH;
+// dW accumulators (M=64: 16 lanes per 32-lane subpartition) pair up two per column range using
+// lane offsets 0 and 16: dW_l at columns 2HP + (l/2)*HP, lanes + 16*(l&1).
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+
+template <int HP>
+struct TcLayout {
+    static constexpr int HSL = HP / 8;
+    static constexpr int DW_GROUPS = (MAXL + 1) / 2;
+    static constexpr int TMEM_NEED = 2 * HP + DW_GROUPS * HP;
+    static constexpr uint32_t TMEM_COLS = TMEM_NEED <= 32 ? 32 : (TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512)));
+    __host__ __device__ static int a_off(int l, int K0P) { return l == 0 ? 0 : (K0P / 8 + (l - 1) * HSL) * SLAB; }
+    __host__ __device__ static int dz_off(int l, int L, int K0P) { return (K0P / 8 + (L - 1) * HSL + l * HSL) * SLAB; }
+    __host__ __device__ static int act_bytes(int L, int K0P) { return (K0P / 8 + 2 * (L - 1) * HSL + 2) * SLAB; }
+    __host__ __device__ static int np(int l, int L) { return l < L - 1 ? HP : 16; }
+    __host__ __device__ static int kp(int l, int K0P) { return l == 0 ? K0P : HP; }
+    __host__ __device__ static int w_off(int l, int L, int K0P)
+    {
+        int o = 0;
+        for (int i = 0; i < l; ++i) o += np(i, L) * kp(i, K0P) * 2;
+        return o;
+    }
+    __host__ __device__ static int stage_bytes(int c_in) { return (TILE * c_in * 4 + 32 + 15) / 16 * 16; }
+    __host__ __device__ static size_t total(int L, int K0P, int c_in)
+    {
+        return (size_t)act_bytes(L, K0P) + w_off(L, L, K0P) + MAXL * HP * 4 + stage_bytes(c_in) + TILE * 4 /*tgt*/ + 8 * 4 + 32;
+    }
+};
+
 template <int HP>
 __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
 {
+    using LY = TcLayout<HP>;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int L = p.L;
-    constexpr int HSL = HP / 8;         // slabs per hidden activation
-    const int K0SL = p.K0P / 8;
-    // ---- carve shared memory
-    // [A0][A1..A_{L-1}][dZ_0..dZ_{L-2}][dZ_{L-1} (2 slabs)][slack 8 slabs][W_0..W_{L-1}][bias][stage][bar]
-    uint8_t *A[MAXL], *DZ[MAXL], *W[MAXL];
-    uint8_t *q = smem;
-    A[0] = q; q += K0SL * SLAB;
-    for (int l = 1; l < L; ++l) { A[l] = q; q += HSL * SLAB; }
-    for (int l = 0; l < L - 1; ++l) { DZ[l] = q; q += HSL * SLAB; }
-    DZ[L - 1] = q; q += 2 * SLAB;
-    uint8_t *act_end = q;
-    q += 8 * SLAB; // M=64 MN-major descriptors read 8 slabs from the start of an A buffer
-    int Np[MAXL], Kp[MAXL];
-    for (int l = 0; l < L; ++l) {
-        Np[l] = (l < L - 1) ? HP : 16;
-        Kp[l] = (l == 0) ? p.K0P : HP;
-        W[l] = q; q += Np[l] * Kp[l] * 2;
-    }
-    float *bias_s = reinterpret_cast<float *>(q); q += MAXL * HP * sizeof(float);
-    float4 *head_s = reinterpret_cast<float4 *>(q); q += TILE * sizeof(float4);
-    float4 *dzh_s = reinterpret_cast<float4 *>(q); q += TILE * sizeof(float4);
-    float *dist_s = reinterpret_cast<float *>(q); q += TILE * sizeof(float);
-    float *red_s = reinterpret_cast<float *>(q); q += 8 * sizeof(float);
-    uint64_t *bar_p = reinterpret_cast<uint64_t *>(q); q += 8;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(q); q += 8;
-    const uint32_t bar = smem_u32(bar_p);
+    const int L = p.L, K0P = p.K0P, c_in = p.dims[0];
+    constexpr int HSL = HP / 8;
+    const int act_bytes = LY::act_bytes(L, K0P);
+    uint8_t *const Wbase = smem + act_bytes;
+    float *const bias_s = reinterpret_cast<float *>(Wbase + LY::w_off(L, L, K0P));
+    float *const stage = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(bias_s) + MAXL * HP * 4);
+    float *const tgt_s = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(stage) + LY::stage_bytes(c_in));
+    float *const red_s = tgt_s + TILE;
+    uint64_t *const bar_p = reinterpret_cast<uint64_t *>(red_s + 8);
+    uint32_t *const tmem_slot = reinterpret_cast<uint32_t *>(bar_p + 2);
+    const uint32_t bar_mma = smem_u32(bar_p), bar_x = smem_u32(bar_p + 1);
+    // compositing scratch aliases dZ_0
+    uint8_t *const dz0 = smem + LY::dz_off(0, L, K0P);
+    float4 *const head_s = reinterpret_cast<float4 *>(dz0);
+    float4 *const dzh_s = head_s + TILE;
+    float *const dist_s = reinterpret_cast<float *>(dzh_s + TILE);
+    static_assert(HSL * SLAB >= 2 * TILE * 16 + TILE * 4 || HP < 32, "scratch must fit in dZ_0");
 
-    // ---- one-time setup: zero activations, stage weights (fp32 -> bf16 slabs) and biases
-    for (uint8_t *z = smem + tid * 16; z < act_end + 8 * SLAB; z += TILE * 16) *reinterpret_cast<uint4 *>(z) = make_uint4(0, 0, 0, 0);
+    // TMA prefetch of a tile's features into `stage` (16 B aligned source, `lead` floats of slack)
+    auto x_src = [&](int tile, int &lead, uint32_t &bytes) -> const void * {
+        const long long row0 = (long long)tile * p.rows_per_tile;
+        long long rem = p.N - row0;
+        const int valid = rem < p.rows_per_tile ? (int)rem : p.rows_per_tile;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p.X + row0 * c_in);
+        const uintptr_t a16 = a & ~(uintptr_t)15;
+        lead = (int)((a - a16) >> 2);
+        bytes = (uint32_t)(((a - a16) + (uintptr_t)valid * c_in * 4 + 15) & ~(uintptr_t)15);
+        return reinterpret_cast<const void *>(a16);
+    };
+
+    // ---- one-time setup
+    if (tid == 0) {
+        mbar_init(bar_mma, 1);
+        mbar_init(bar_x, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        int lead; uint32_t bytes;
+        const void *src = x_src(blockIdx.x, lead, bytes);
+        mbar_expect_tx(bar_x, bytes);
+        bulk_g2s(smem_u32(stage), src, bytes, bar_x);
+    }
+    for (uint8_t *z = smem + tid * 16; z < smem + act_bytes; z += TILE * 16) *reinterpret_cast<uint4 *>(z) = make_uint4(0, 0, 0, 0);
     for (int l = 0; l < L; ++l) {
-        const int in_l = p.dims[l], out_l = p.dims[l + 1];
+        const int in_l = p.dims[l], out_l = p.dims[l + 1], Np = LY::np(l, L), Kp = LY::kp(l, K0P);
         const float *wl = p.ws + (size_t)l * p.max_in * p.max_out;
-        __nv_bfloat16 *ws_ = reinterpret_cast<__nv_bfloat16 *>(W[l]);
-        for (int e = tid; e < Np[l] * Kp[l]; e += TILE) {
-            int k = e / Np[l], j = e % Np[l]; // consecutive threads -> consecutive j (coalesced global)
-            float v = (k < in_l && j < out_l) ? __ldg(wl + (size_t)k * p.max_out + j) : 0.0f;
-            ws_[(k >> 3) * (Np[l] * 8) + j * 8 + (k & 7)] = __float2bfloat16_rn(v);
+        __nv_bfloat16 *ws_ = reinterpret_cast<__nv_bfloat16 *>(Wbase + LY::w_off(l, L, K0P));
+        const int tot = Np * Kp;
+        for (int e0 = tid; e0 < tot; e0 += 4 * TILE) { // 4 independent loads in flight per thread
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * TILE, k = e / Np, j = e % Np;
+                v[u] = (e < tot && k < in_l && j < out_l) ? __ldg(wl + (size_t)k * p.max_out + j) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * TILE, k = e / Np, j = e % Np;
+                if (e < tot) ws_[(k >> 3) * (Np * 8) + j * 8 + (k & 7)] = __float2bfloat16_rn(v[u]);
+            }
         }
         for (int j = tid; j < HP; j += TILE) bias_s[l * HP + j] = (j < out_l) ? __ldg(p.bs + (size_t)l * p.max_out + j) : 0.0f;
     }
-    if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    constexpr uint32_t TMEM_COLS = (2 + MAXL) * HP <= 32 ? 32 : ((2 + MAXL) * HP <= 64 ? 64 : ((2 + MAXL) * HP <= 128 ? 128 : ((2 + MAXL) * HP <= 256 ? 256 : 512)));
-    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), LY::TMEM_COLS);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    uint32_t phase = 0;
+    uint32_t phase = 0, xphase = 0;
     float loss_acc = 0.0f;
     bool dw_started = false;
 
-    // helper lambdas ---------------------------------------------------------------------------
-    auto a_row_ptr = [&](uint8_t *buf, int slab) { return reinterpret_cast<uint4 *>(buf + slab * SLAB + tid * 16); };
-    // forward MMA for layer l into TMEM region reg (0/1): D[128 x Np] = A_l[128 x Kp] * W_l
+    auto a_buf = [&](int l) { return smem + LY::a_off(l, K0P); };
+    auto dz_buf = [&](int l) { return smem + LY::dz_off(l, L, K0P); };
+    auto row_ptr = [&](uint8_t *buf, int slab) { return reinterpret_cast<uint4 *>(buf + slab * SLAB + tid * 16); };
+    auto dw_taddr = [&](int l) { return tmem + (uint32_t)(2 * HP + (l >> 1) * HP) + ((uint32_t)(16 * (l & 1)) << 16); };
     auto issue_fwd = [&](int l, int reg) {
-        const uint32_t idesc = instr_desc(128, Np[l], 0, 0);
-        const uint32_t a0 = smem_u32(A[l]), b0 = smem_u32(W[l]);
-        for (int k = 0; k < Kp[l] / 16; ++k) {
-            uint64_t ad = smem_desc(a0 + k * 2 * SLAB, SLAB, 128);
-            uint64_t bd = smem_desc(b0 + k * 2 * (Np[l] * 16), Np[l] * 16, 128);
-            umma_bf16(tmem + reg * HP, ad, bd, idesc, k > 0);
-        }
+        const int Np = LY::np(l, L), Kp = LY::kp(l, K0P);
+        const uint32_t idesc = instr_desc(128, Np, 0, 0);
+        const uint32_t a0 = smem_u32(a_buf(l)), b0 = smem_u32(Wbase + LY::w_off(l, L, K0P));
+        for (int k = 0; k < Kp / 16; ++k)
+            umma_bf16(tmem + reg * HP, smem_desc(a0 + k * 2 * SLAB, SLAB, 128), smem_desc(b0 + k * 2 * (Np * 16), Np * 16, 128), idesc, k > 0);
     };
-    // backward dH_l [128 x Kp_l] = dZ_l [128 x Np_l] * W_l^T into region reg
     auto issue_dh = [&](int l, int reg) {
-        const uint32_t idesc = instr_desc(128, Kp[l], 0, 1);
-        const uint32_t a0 = smem_u32(DZ[l]), b0 = smem_u32(W[l]);
-        for (int k = 0; k < Np[l] / 16; ++k) {
-            uint64_t ad = smem_desc(a0 + k * 2 * SLAB, SLAB, 128);
-            // B^T: N' = in features (MN groups, stride = W slab), K' = out features (8-row groups of 128 B)
-            uint64_t bd = smem_desc(b0 + k * 2 * 128, 128, Np[l] * 16);
-            umma_bf16(tmem + reg * HP, ad, bd, idesc, k > 0);
-        }
+        const int Np = LY::np(l, L), Kp = LY::kp(l, K0P);
+        const uint32_t idesc = instr_desc(128, Kp, 0, 1);
+        const uint32_t a0 = smem_u32(dz_buf(l)), b0 = smem_u32(Wbase + LY::w_off(l, L, K0P));
+        for (int k = 0; k < Np / 16; ++k)
+            umma_bf16(tmem + reg * HP, smem_desc(a0 + k * 2 * SLAB, SLAB, 128), smem_desc(b0 + k * 2 * 128, 128, Np * 16), idesc, k > 0);
     };
-    // dW_l [64 x Np_l] += A_l^T [64 feats x 128 samples] * dZ_l [128 samples x Np_l]
     auto issue_dw = [&](int l) {
-        const uint32_t idesc = instr_desc(64, Np[l], 1, 1);
-        const uint32_t a0 = smem_u32(A[l]), b0 = smem_u32(DZ[l]);
-        for (int k = 0; k < TILE / 16; ++k) {
-            uint64_t ad = smem_desc(a0 + k * 256, 128, SLAB);
-            uint64_t bd = smem_desc(b0 + k * 256, 128, SLAB);
-            umma_bf16(tmem + (2 + l) * HP, ad, bd, idesc, (dw_started || k > 0) ? 1u : 0u);
-        }
+        const int Np = LY::np(l, L);
+        const uint32_t idesc = instr_desc(64, Np, 1, 1);
+        const uint32_t a0 = smem_u32(a_buf(l)), b0 = smem_u32(dz_buf(l));
+        const uint32_t d = dw_taddr(l);
+        for (int k = 0; k < TILE / 16; ++k)
+            umma_bf16(d, smem_desc(a0 + k * 256, 128, SLAB), smem_desc(b0 + k * 256, 128, SLAB), idesc, (dw_started || k > 0) ? 1u : 0u);
     };
     auto commit_and_wait = [&]() {
-        if (tid == 0) umma_commit(bar);
-        mbar_wait(bar, phase);
+        if (tid == 0) umma_commit(bar_mma);
+        mbar_wait(bar_mma, phase);
         phase ^= 1;
         tc_fence_after();
     };
-    auto publish_smem = [&]() { // generic-proxy smem writes -> visible to the tensor core, all threads
+    auto publish_smem = [&]() {
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
     };
 
-    const int c_in = p.dims[0];
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const long long row0 = (long long)tile * p.rows_per_tile;
         long long rem = p.N - row0;
         const int valid = rem < p.rows_per_tile ? (int)rem : p.rows_per_tile;
-        // ---- stage X: coalesced fp32 loads, bf16 scatter into slabs; column c_in := 1 (bias-grad feature)
-        {
-            const float *xt = p.X + row0 * c_in;
-            const int total = valid * c_in;
-            int r = tid / c_in, c = tid % c_in;
-            const int dr = TILE / c_in, dc = TILE % c_in;
-            __nv_bfloat16 *a0 = reinterpret_cast<__nv_bfloat16 *>(A[0]);
-            for (int e = tid; e < TILE * c_in; e += TILE) {
-                float v = e < total ? __ldg(xt + e) : 0.0f;
-                a0[(c >> 3) * (TILE * 8) + r * 8 + (c & 7)] = __float2bfloat16_rn(v);
-                r += dr; c += dc;
-                if (c >= c_in) { c -= c_in; ++r; }
-            }
-            a0[(c_in >> 3) * (TILE * 8) + tid * 8 + (c_in & 7)] = __float2bfloat16_rn(1.0f);
+        const int rays_here = valid / p.S;
+        // early, latency-tolerant loads for this tile (consumed after the MLP forward)
+        float my_dist = 0.0f, my_tgt = 0.0f;
+        if (p.head == LNB_HEAD_NERF) {
+            if (tid < valid) my_dist = __ldg(p.dists + row0 + tid);
+            if (p.target && tid < rays_here * 3) my_tgt = __ldg(p.target + (row0 / p.S) * 3 + tid);
         }
-        publish_smem();
+        // ---- features: wait for the TMA, convert this thread's row to bf16 slabs, ones column
+        {
+            int lead; uint32_t bytes;
+            (void)x_src(tile, lead, bytes);
+            mbar_wait(bar_x, xphase);
+            xphase ^= 1;
+            uint8_t *a0 = a_buf(0);
+            const float *xr = stage + lead + tid * c_in;
+            const bool live = tid < valid;
+            for (int c8 = 0; c8 < K0P / 8; ++c8) {
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = c8 * 8 + j;
+                    f[j] = (live && c < c_in) ? xr[c] : (c == c_in ? 1.0f : 0.0f);
+                }
+                *row_ptr(a0, c8) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+            }
+        }
+        publish_smem(); // also: every thread is done reading `stage`
+        if (tid == 0) {
+            const int nt = tile + gridDim.x;
+            if (nt < p.n_tiles) {
+                int lead; uint32_t bytes;
+                const void *src = x_src(nt, lead, bytes);
+                mbar_expect_tx(bar_x, bytes);
+                bulk_g2s(smem_u32(stage), src, bytes, bar_x);
+            }
+        }
         // ---- forward
         float hz[4];
         for (int l = 0; l < L; ++l) {
@@ -275,6 +363,7 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
             const float *bl = bias_s + l * HP;
             if (l < L - 1) {
                 const int ones_col = p.dims[l + 1];
+                uint8_t *an = a_buf(l + 1);
 #pragma unroll
                 for (int c16 = 0; c16 < HP / 16; ++c16) {
                     uint32_t v[16];
@@ -286,8 +375,8 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
                         f[j] = fmaxf(__uint_as_float(v[j]) + bl[c16 * 16 + j], 0.0f);
                         if (c16 * 16 + j == ones_col) f[j] = 1.0f;
                     }
-                    *a_row_ptr(A[l + 1], c16 * 2) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-                    *a_row_ptr(A[l + 1], c16 * 2 + 1) = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
+                    *row_ptr(an, c16 * 2) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                    *row_ptr(an, c16 * 2 + 1) = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
                 }
                 publish_smem();
             } else {
@@ -315,11 +404,11 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
             float r_ = sigmoid_f(hz[0]), g_ = sigmoid_f(hz[1]), b_ = sigmoid_f(hz[2]);
             float sg = fmaxf(hz[3], 0.0f);
             head_s[tid] = make_float4(r_, g_, b_, sg);
-            dist_s[tid] = tid < valid ? __ldg(p.dists + row0 + tid) : 0.0f;
+            dist_s[tid] = my_dist;
+            if (tid < rays_here * 3) tgt_s[tid] = my_tgt;
             if (p.dbg && tid < valid) reinterpret_cast<float4 *>(p.dbg)[row0 + tid] = make_float4(r_, g_, b_, sg);
             __syncthreads();
             // warp w composites rays w, w+4, ... of this tile
-            const int rays_here = valid / p.S;
             const int S = p.S;
             for (int ry = warp; ry < rays_here; ry += 4) {
                 const int base = ry * S;
@@ -352,8 +441,10 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
                 }
                 if (p.color && lane == 0) { p.color[ray * 3] = c0; p.color[ray * 3 + 1] = c1; p.color[ray * 3 + 2] = c2; }
                 if (!p.target) continue;
-                const float *tg = p.target + ray * 3;
-                const float d0 = c0 - __ldg(tg), d1 = c1 - __ldg(tg + 1), d2 = c2 - __ldg(tg + 2);
+                float t0, t1, t2;
+                if (ry < 42) { t0 = tgt_s[ry * 3]; t1 = tgt_s[ry * 3 + 1]; t2 = tgt_s[ry * 3 + 2]; }
+                else { const float *tg = p.target + ray * 3; t0 = __ldg(tg); t1 = __ldg(tg + 1); t2 = __ldg(tg + 2); }
+                const float d0 = c0 - t0, d1 = c1 - t1, d2 = c2 - t2;
                 if (lane == 0) loss_acc += d0 * d0 + d1 * d1 + d2 * d2;
                 if (!p.want_grad) continue;
                 const float dc0 = 2.0f * d0, dc1 = 2.0f * d1, dc2 = 2.0f * d2;
@@ -399,25 +490,26 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
                 float4 d4 = dzh_s[tid];
                 dz[0] = d4.x; dz[1] = d4.y; dz[2] = d4.z; dz[3] = d4.w;
             }
+            __syncthreads(); // the scratch aliases dZ_0: everyone has read it before anyone moves on
         }
         if (!p.want_grad) continue;
         // ---- backward.  dZ_{L-1}: 4 live features, the rest of the 16 stay zero
-        *a_row_ptr(DZ[L - 1], 0) = make_uint4(pack_bf16(dz[0], dz[1]), pack_bf16(dz[2], dz[3]), 0u, 0u);
+        *row_ptr(dz_buf(L - 1), 0) = make_uint4(pack_bf16(dz[0], dz[1]), pack_bf16(dz[2], dz[3]), 0u, 0u);
         publish_smem();
         for (int l = L - 1; l >= 0; --l) {
             if (tid == 0) {
                 issue_dw(l);
                 if (l > 0) issue_dh(l, l & 1);
             }
-            commit_and_wait(); // also fences the dW reads of A_l / dZ_l before they are overwritten
+            commit_and_wait(); // also orders the dW reads of A_l / dZ_l before they are overwritten
             if (l == 0) break;
-            // dZ_{l-1} = dH_l masked by ReLU'(H_l) ; H_l = A[l] (bf16, post-activation)
+            uint8_t *al = a_buf(l), *dzn = dz_buf(l - 1);
 #pragma unroll
             for (int c16 = 0; c16 < HP / 16; ++c16) {
                 uint32_t v[16];
                 tmem_ld16(tmem + lane_base + (l & 1) * HP + c16 * 16, v);
                 tmem_ld_wait();
-                uint4 h0 = *a_row_ptr(A[l], c16 * 2), h1 = *a_row_ptr(A[l], c16 * 2 + 1);
+                uint4 h0 = *row_ptr(al, c16 * 2), h1 = *row_ptr(al, c16 * 2 + 1);
                 uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
                 float f[16];
 #pragma unroll
@@ -426,8 +518,8 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
                     f[2 * j] = (hw[j] & 0xFFFFu) ? __uint_as_float(v[2 * j]) : 0.0f;
                     f[2 * j + 1] = (hw[j] >> 16) ? __uint_as_float(v[2 * j + 1]) : 0.0f;
                 }
-                *a_row_ptr(DZ[l - 1], c16 * 2) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-                *a_row_ptr(DZ[l - 1], c16 * 2 + 1) = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
+                *row_ptr(dzn, c16 * 2) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                *row_ptr(dzn, c16 * 2 + 1) = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
             }
             publish_smem();
         }
@@ -446,17 +538,18 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
     if (tid == 0) part[0] = red_s[0] + red_s[1] + red_s[2] + red_s[3];
     if (p.want_grad) {
         for (int l = 0; l < L; ++l) {
-            // M=64 accumulators live in lanes 0..15 of each 32-lane subpartition: row = 16*warp + lane
-            const int row = warp * 16 + lane;
-            const int in_l = p.dims[l], out_l = p.dims[l + 1];
+            // M=64 accumulator l sits in lanes [16*(l&1), 16*(l&1)+16) of every 32-lane subpartition
+            const int sub = lane - 16 * (l & 1);
+            const int row = warp * 16 + sub;
+            const int in_l = p.dims[l], out_l = p.dims[l + 1], Np = LY::np(l, L);
             float *o = part + p.part_off[l];
 #pragma unroll
             for (int c16 = 0; c16 < HP / 16; ++c16) {
-                if (c16 * 16 >= Np[l]) break;
+                if (c16 * 16 >= Np) break;
                 uint32_t v[16];
-                tmem_ld16(tmem + lane_base + (2 + l) * HP + c16 * 16, v);
+                tmem_ld16(tmem + lane_base + (uint32_t)(2 * HP + (l >> 1) * HP + c16 * 16), v);
                 tmem_ld_wait();
-                if (lane < 16 && row <= in_l) {
+                if (sub >= 0 && sub < 16 && row <= in_l) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         int col = c16 * 16 + j;
@@ -468,7 +561,7 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+    if (warp == 0) tmem_dealloc(tmem, LY::TMEM_COLS);
 }
 
 // reduce the per-CTA partials in a fixed order; apply the seed; accumulate into the caller's buffers
@@ -506,15 +599,6 @@ __global__ void tc_reduce_kernel(const float *__restrict__ part, int n_part, int
         if (k < p.dims[l]) d_ws[((size_t)l * p.max_in + k) * p.max_out + j] += scale * s;
         else d_bs[(size_t)l * p.max_out + j] += scale * s;
     }
-}
-
-template <int HP>
-size_t smem_bytes(int L, int K0P)
-{
-    size_t b = (size_t)(K0P / 8) * SLAB + (size_t)(L - 1) * (HP / 8) * SLAB * 2 + 2 * SLAB + 8 * SLAB;
-    for (int l = 0; l < L; ++l) b += (size_t)((l < L - 1) ? HP : 16) * ((l == 0) ? K0P : HP) * 2;
-    b += MAXL * HP * sizeof(float) + 2 * TILE * sizeof(float4) + TILE * sizeof(float) + 8 * sizeof(float) + 16;
-    return b + 1024; // alignment slack
 }
 
 } // namespace
@@ -564,10 +648,12 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     for (int l = 0; l < L; ++l) { p.part_off[l] = off; off += (mlp->dims[l] + 1) * mlp->dims[l + 1]; }
     p.part_stride = off;
 
-    size_t smem = HP == 16 ? smem_bytes<16>(L, K0P) : (HP == 32 ? smem_bytes<32>(L, K0P) : smem_bytes<64>(L, K0P));
-    const int tmem_cols = (2 + MAXL) * HP <= 128 ? 128 : ((2 + MAXL) * HP <= 256 ? 256 : 512);
+    const int c_in = mlp->dims[0];
+    size_t smem = (HP == 16 ? TcLayout<16>::total(L, K0P, c_in) : (HP == 32 ? TcLayout<32>::total(L, K0P, c_in) : TcLayout<64>::total(L, K0P, c_in)));
+    const int tmem_cols = (int)(HP == 16 ? TcLayout<16>::TMEM_COLS : (HP == 32 ? TcLayout<32>::TMEM_COLS : TcLayout<64>::TMEM_COLS));
+    if ((reinterpret_cast<uintptr_t>(a->X) & 3) != 0) return unsupported("X must be 4-byte aligned");
     int per_sm = 512 / tmem_cols;
-    int by_smem = (int)((227 * 1024) / smem);
+    int by_smem = (int)((227 * 1024) / (smem + 1024));
     if (by_smem < per_sm) per_sm = by_smem;
     if (per_sm < 1) return unsupported("shared memory");
     int grid = ctx->sm_count * per_sm;
