@@ -41,6 +41,7 @@ struct TcParams {
     float *color;      // [R][3] or NULL
     float *part;       // [grid][part_stride]
     float *dbg;        // optional [N][4] head outputs (debug)
+    const void *wimg;  // weight image built by tc_prep_kernel (TcLayout::wimg_bytes)
     long long N;       // samples (rows of X)
     int R, S, G, rows_per_tile, n_tiles;
     int L, dims[MAXL + 1], max_in, max_out;
@@ -63,12 +64,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t done = 0;
     for (uint32_t it = 0; !done; ++it) {
+        // the suspend-time hint lets the warp sleep in hardware instead of burning issue slots
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (it > (1u << 24)) __trap(); // never hang the GPU: a lost arrival is a bug, fail loudly
+            : "=r"(done) : "r"(bar), "r"(parity), "r"(100000u) : "memory");
+        if (it > (1u << 22)) __trap(); // never hang the GPU: a lost arrival is a bug, fail loudly
     }
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -140,15 +142,14 @@ __device__ __forceinline__ float warp_incl_prod(float p, int lane)
 // ---------------------------------------------------------------------------------------------
 // the kernel.  HP = padded hidden width (16/32/64): every hidden layer has width+1 <= HP.
 // 128 threads: thread r owns row r of the tile (TMEM lane r).  Thread 0 issues the MMAs and the
-// bulk-async (TMA) prefetch of the next tile's features.
+// bulk-async (TMA) copies: the weight image once, the next tile's features every tile.
 //
-// Shared memory (bytes), in this order so that an M=64 MN-major read of A_l (8 slabs from its
-// start) always stays inside live shared memory:
+// Shared memory, in this order so that an M=64 MN-major read of A_l (8 slabs from its start)
+// always stays inside live shared memory:
 //   A0 [K0P/8 slabs] | A1 .. A_{L-1} [HP/8 slabs each] | dZ_0 .. dZ_{L-2} [HP/8 each] | dZ_{L-1} [2]
-//   | W_0 .. W_{L-1} (bf16) | bias (fp32) | stage (fp32 features of the NEXT tile, TMA target)
-//   | small per-tile scratch | mbarriers
-// head_s / dzh_s / dist_s (compositing scratch) alias dZ_0, which is only written by the last
-// backward epilogue of a tile.
+//   | weight image: W_0 .. W_{L-1} (bf16 slabs), biases (fp32)      <- one TMA per CTA
+//   | stage: fp32 features of the next tile                          <- one TMA per tile
+//   | compositing scratch | mbarriers
 // TMEM (128 columns when HP <= 32): R0 [0,HP) and R1 [HP,2HP) ping-pong layer outputs / dH;
 // dW accumulators (M=64: 16 lanes per 32-lane subpartition) pair up two per column range using
 // lane offsets 0 and 16: dW_l at columns 2HP + (l/2)*HP, lanes + 16*(l&1).
@@ -161,17 +162,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr) : "memory");
 }
 
 template <int HP>
@@ -191,12 +181,39 @@ struct TcLayout {
         for (int i = 0; i < l; ++i) o += np(i, L) * kp(i, K0P) * 2;
         return o;
     }
-    __host__ __device__ static int stage_bytes(int c_in) { return (TILE * c_in * 4 + 32 + 15) / 16 * 16; }
+    // weight image = [W_0 .. W_{L-1} bf16 slabs][bias fp32 MAXL x HP], built once per step by
+    // tc_prep_kernel in global memory
+    __host__ __device__ static int wimg_bytes(int L, int K0P) { return w_off(L, L, K0P) + MAXL * HP * 4; }
+    __host__ __device__ static int stage_bytes(int c_in, int K0P) { return (TILE * c_in * 4 + 32 + K0P * 4 + 15) / 16 * 16; }
+    static constexpr int SCRATCH_FLOATS = 2 * TILE * 3 + 40; // colour + target per ray, scan carries, loss
     __host__ __device__ static size_t total(int L, int K0P, int c_in)
     {
-        return (size_t)act_bytes(L, K0P) + w_off(L, L, K0P) + MAXL * HP * 4 + stage_bytes(c_in) + TILE * 4 /*tgt*/ + 8 * 4 + 32;
+        return (size_t)act_bytes(L, K0P) + wimg_bytes(L, K0P) + stage_bytes(c_in, K0P) + SCRATCH_FLOATS * 4 + 48;
     }
 };
+
+// fp32 padded weights -> the bf16 slab image + fp32 biases every CTA of the fused kernel copies
+template <int HP>
+__global__ void tc_prep_kernel(const TcParams p, uint8_t *__restrict__ img)
+{
+    using LY = TcLayout<HP>;
+    const int L = p.L, K0P = p.K0P;
+    for (int l = 0; l < L; ++l) {
+        const int in_l = p.dims[l], out_l = p.dims[l + 1], Np = LY::np(l, L), Kp = LY::kp(l, K0P);
+        const float *wl = p.ws + (size_t)l * p.max_in * p.max_out;
+        __nv_bfloat16 *w = reinterpret_cast<__nv_bfloat16 *>(img + LY::w_off(l, L, K0P));
+        for (int e = threadIdx.x; e < Np * Kp; e += blockDim.x) {
+            const int k = e / Np, j = e % Np; // consecutive threads -> consecutive j (coalesced reads)
+            const float v = (k < in_l && j < out_l) ? __ldg(wl + (size_t)k * p.max_out + j) : 0.0f;
+            w[(k >> 3) * (Np * 8) + j * 8 + (k & 7)] = __float2bfloat16_rn(v);
+        }
+    }
+    float *b = reinterpret_cast<float *>(img + LY::w_off(L, L, K0P));
+    for (int e = threadIdx.x; e < MAXL * HP; e += blockDim.x) {
+        const int l = e / HP, j = e % HP;
+        b[e] = (l < L && j < p.dims[l + 1]) ? __ldg(p.bs + (size_t)l * p.max_out + j) : 0.0f;
+    }
+}
 
 template <int HP>
 __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
@@ -204,25 +221,24 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
     using LY = TcLayout<HP>;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int L = p.L, K0P = p.K0P, c_in = p.dims[0];
-    constexpr int HSL = HP / 8;
+    const int L = p.L, K0P = p.K0P, c_in = p.dims[0], S = p.S;
     const int act_bytes = LY::act_bytes(L, K0P);
     uint8_t *const Wbase = smem + act_bytes;
-    float *const bias_s = reinterpret_cast<float *>(Wbase + LY::w_off(L, L, K0P));
-    float *const stage = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(bias_s) + MAXL * HP * 4);
-    float *const tgt_s = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(stage) + LY::stage_bytes(c_in));
-    float *const red_s = tgt_s + TILE;
-    uint64_t *const bar_p = reinterpret_cast<uint64_t *>(red_s + 8);
-    uint32_t *const tmem_slot = reinterpret_cast<uint32_t *>(bar_p + 2);
-    const uint32_t bar_mma = smem_u32(bar_p), bar_x = smem_u32(bar_p + 1);
-    // compositing scratch aliases dZ_0
-    uint8_t *const dz0 = smem + LY::dz_off(0, L, K0P);
-    float4 *const head_s = reinterpret_cast<float4 *>(dz0);
-    float4 *const dzh_s = head_s + TILE;
-    float *const dist_s = reinterpret_cast<float *>(dzh_s + TILE);
-    static_assert(HSL * SLAB >= 2 * TILE * 16 + TILE * 4 || HP < 32, "scratch must fit in dZ_0");
+    const float *const bias_s = reinterpret_cast<const float *>(Wbase + LY::w_off(L, L, K0P));
+    float *const stage = reinterpret_cast<float *>(Wbase + LY::wimg_bytes(L, K0P));
+    float *const color_s = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(stage) + LY::stage_bytes(c_in, K0P));
+    float *const tgt_s = color_s + TILE * 3;
+    float *const tailp = tgt_s + TILE * 3;                   // [4] inclusive product at lane 31 of each warp
+    int *const tail_s = reinterpret_cast<int *>(tailp + 4);  // [4] sample index at lane 31
+    float *const headq = tailp + 8;                          // [5] q at lane 0 of each warp
+    float *const headA = tailp + 13;                         // [5]
+    float *const headB = tailp + 18;                         // [5]
+    float *const red_s = tailp + 24;                         // [8]
+    uint64_t *const bar_p = reinterpret_cast<uint64_t *>(tailp + 40);
+    uint32_t *const tmem_slot = reinterpret_cast<uint32_t *>(bar_p + 3);
+    const uint32_t bar_mma = smem_u32(bar_p), bar_x = smem_u32(bar_p + 1), bar_w = smem_u32(bar_p + 2);
 
-    // TMA prefetch of a tile's features into `stage` (16 B aligned source, `lead` floats of slack)
+    // TMA source of a tile's features (16 B aligned start, `lead` floats in front of the tile)
     auto x_src = [&](int tile, int &lead, uint32_t &bytes) -> const void * {
         const long long row0 = (long long)tile * p.rows_per_tile;
         long long rem = p.N - row0;
@@ -234,52 +250,42 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
         return reinterpret_cast<const void *>(a16);
     };
 
-    // ---- one-time setup
+    // ---- one-time setup: zero activations and stage, then TMA the weight image and the first tile
+    for (uint8_t *z = smem + tid * 16; z < smem + act_bytes; z += TILE * 16) *reinterpret_cast<uint4 *>(z) = make_uint4(0, 0, 0, 0);
+    for (uint8_t *z = reinterpret_cast<uint8_t *>(stage) + tid * 16; z < reinterpret_cast<uint8_t *>(color_s); z += TILE * 16)
+        *reinterpret_cast<uint4 *>(z) = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         mbar_init(bar_mma, 1);
         mbar_init(bar_x, 1);
+        mbar_init(bar_w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        int lead; uint32_t bytes;
-        const void *src = x_src(blockIdx.x, lead, bytes);
-        mbar_expect_tx(bar_x, bytes);
-        bulk_g2s(smem_u32(stage), src, bytes, bar_x);
-    }
-    for (uint8_t *z = smem + tid * 16; z < smem + act_bytes; z += TILE * 16) *reinterpret_cast<uint4 *>(z) = make_uint4(0, 0, 0, 0);
-    for (int l = 0; l < L; ++l) {
-        const int in_l = p.dims[l], out_l = p.dims[l + 1], Np = LY::np(l, L), Kp = LY::kp(l, K0P);
-        const float *wl = p.ws + (size_t)l * p.max_in * p.max_out;
-        __nv_bfloat16 *ws_ = reinterpret_cast<__nv_bfloat16 *>(Wbase + LY::w_off(l, L, K0P));
-        const int tot = Np * Kp;
-        for (int e0 = tid; e0 < tot; e0 += 4 * TILE) { // 4 independent loads in flight per thread
-            float v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = e0 + u * TILE, k = e / Np, j = e % Np;
-                v[u] = (e < tot && k < in_l && j < out_l) ? __ldg(wl + (size_t)k * p.max_out + j) : 0.0f;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = e0 + u * TILE, k = e / Np, j = e % Np;
-                if (e < tot) ws_[(k >> 3) * (Np * 8) + j * 8 + (k & 7)] = __float2bfloat16_rn(v[u]);
-            }
-        }
-        for (int j = tid; j < HP; j += TILE) bias_s[l * HP + j] = (j < out_l) ? __ldg(p.bs + (size_t)l * p.max_out + j) : 0.0f;
     }
     if (warp == 0) tmem_alloc(smem_u32(tmem_slot), LY::TMEM_COLS);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (tid == 0) {
+        const uint32_t wb = (uint32_t)LY::wimg_bytes(L, K0P);
+        mbar_expect_tx(bar_w, wb);
+        bulk_g2s(smem_u32(Wbase), p.wimg, wb, bar_w);
+        int lead; uint32_t bytes;
+        const void *src = x_src(blockIdx.x, lead, bytes);
+        mbar_expect_tx(bar_x, bytes);
+        bulk_g2s(smem_u32(stage), src, bytes, bar_x);
+    }
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     uint32_t phase = 0, xphase = 0;
     float loss_acc = 0.0f;
     bool dw_started = false;
+    mbar_wait(bar_w, 0); // weights + biases have landed
 
     auto a_buf = [&](int l) { return smem + LY::a_off(l, K0P); };
     auto dz_buf = [&](int l) { return smem + LY::dz_off(l, L, K0P); };
     auto row_ptr = [&](uint8_t *buf, int slab) { return reinterpret_cast<uint4 *>(buf + slab * SLAB + tid * 16); };
     auto dw_taddr = [&](int l) { return tmem + (uint32_t)(2 * HP + (l >> 1) * HP) + ((uint32_t)(16 * (l & 1)) << 16); };
+    // D[128 x Np] = A_l[128 x Kp] * W_l            (A, B K-major)
     auto issue_fwd = [&](int l, int reg) {
         const int Np = LY::np(l, L), Kp = LY::kp(l, K0P);
         const uint32_t idesc = instr_desc(128, Np, 0, 0);
@@ -287,6 +293,7 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
         for (int k = 0; k < Kp / 16; ++k)
             umma_bf16(tmem + reg * HP, smem_desc(a0 + k * 2 * SLAB, SLAB, 128), smem_desc(b0 + k * 2 * (Np * 16), Np * 16, 128), idesc, k > 0);
     };
+    // dH_l[128 x Kp] = dZ_l[128 x Np] * W_l^T      (B^T = the same bytes read MN-major)
     auto issue_dh = [&](int l, int reg) {
         const int Np = LY::np(l, L), Kp = LY::kp(l, K0P);
         const uint32_t idesc = instr_desc(128, Kp, 0, 1);
@@ -294,6 +301,7 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
         for (int k = 0; k < Np / 16; ++k)
             umma_bf16(tmem + reg * HP, smem_desc(a0 + k * 2 * SLAB, SLAB, 128), smem_desc(b0 + k * 2 * 128, 128, Np * 16), idesc, k > 0);
     };
+    // dW_l[64 x Np] += A_l^T[64 feats x 128 samples] * dZ_l[128 samples x Np]   (both MN-major)
     auto issue_dw = [&](int l) {
         const int Np = LY::np(l, L);
         const uint32_t idesc = instr_desc(64, Np, 1, 1);
@@ -308,7 +316,7 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
         phase ^= 1;
         tc_fence_after();
     };
-    auto publish_smem = [&]() {
+    auto publish_smem = [&]() { // generic-proxy smem writes -> visible to the tensor core, all threads
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -319,14 +327,21 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
         const long long row0 = (long long)tile * p.rows_per_tile;
         long long rem = p.N - row0;
         const int valid = rem < p.rows_per_tile ? (int)rem : p.rows_per_tile;
-        const int rays_here = valid / p.S;
+        const int rays_here = valid / S;
+        const int smp = tid % S, ray_l = tid / S;        // this thread's sample within its ray
+        const bool live = tid < rays_here * S;
         // early, latency-tolerant loads for this tile (consumed after the MLP forward)
-        float my_dist = 0.0f, my_tgt = 0.0f;
-        if (p.head == LNB_HEAD_NERF) {
-            if (tid < valid) my_dist = __ldg(p.dists + row0 + tid);
-            if (p.target && tid < rays_here * 3) my_tgt = __ldg(p.target + (row0 / p.S) * 3 + tid);
+        float my_dist = 0.0f, tg0 = 0.0f, tg1 = 0.0f, tg2 = 0.0f;
+        if (p.head == LNB_HEAD_NERF && live) {
+            my_dist = __ldg(p.dists + row0 + tid);
+            if (p.target && smp == 0) {
+                const float *tg = p.target + (row0 / S + ray_l) * 3;
+                tg0 = __ldg(tg); tg1 = __ldg(tg + 1); tg2 = __ldg(tg + 2);
+            }
         }
-        // ---- features: wait for the TMA, convert this thread's row to bf16 slabs, ones column
+        // ---- features: wait for the TMA, convert this thread's row to bf16 slabs.  Columns beyond
+        // c_in read the following floats of `stage` (finite: next row / zeroed slack) and meet zero
+        // weights; column c_in is then patched to 1 (the bias-gradient feature).
         {
             int lead; uint32_t bytes;
             (void)x_src(tile, lead, bytes);
@@ -334,16 +349,18 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
             xphase ^= 1;
             uint8_t *a0 = a_buf(0);
             const float *xr = stage + lead + tid * c_in;
-            const bool live = tid < valid;
-            for (int c8 = 0; c8 < K0P / 8; ++c8) {
-                float f[8];
+            if (tid < valid) {
+                for (int c8 = 0; c8 < K0P / 8; ++c8) {
+                    float f[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int c = c8 * 8 + j;
-                    f[j] = (live && c < c_in) ? xr[c] : (c == c_in ? 1.0f : 0.0f);
+                    for (int j = 0; j < 8; ++j) f[j] = xr[c8 * 8 + j];
+                    *row_ptr(a0, c8) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
                 }
-                *row_ptr(a0, c8) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+            } else {
+                for (int c8 = 0; c8 < K0P / 8; ++c8) *row_ptr(a0, c8) = make_uint4(0, 0, 0, 0);
             }
+            __syncwarp();
+            reinterpret_cast<__nv_bfloat16 *>(a0)[(c_in >> 3) * (TILE * 8) + tid * 8 + (c_in & 7)] = __float2bfloat16_rn(1.0f);
         }
         publish_smem(); // also: every thread is done reading `stage`
         if (tid == 0) {
@@ -368,16 +385,21 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
                 for (int c16 = 0; c16 < HP / 16; ++c16) {
                     uint32_t v[16];
                     tmem_ld16(tmem + lane_base + (l & 1) * HP + c16 * 16, v);
+                    float bv[16];
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        float4 b4 = *reinterpret_cast<const float4 *>(bl + c16 * 16 + j4 * 4);
+                        bv[j4 * 4] = b4.x; bv[j4 * 4 + 1] = b4.y; bv[j4 * 4 + 2] = b4.z; bv[j4 * 4 + 3] = b4.w;
+                    }
                     tmem_ld_wait();
                     float f[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        f[j] = fmaxf(__uint_as_float(v[j]) + bl[c16 * 16 + j], 0.0f);
-                        if (c16 * 16 + j == ones_col) f[j] = 1.0f;
-                    }
+                    for (int j = 0; j < 16; ++j) f[j] = fmaxf(__uint_as_float(v[j]) + bv[j], 0.0f);
                     *row_ptr(an, c16 * 2) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
                     *row_ptr(an, c16 * 2 + 1) = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
                 }
+                __syncwarp();
+                reinterpret_cast<__nv_bfloat16 *>(an)[(ones_col >> 3) * (TILE * 8) + tid * 8 + (ones_col & 7)] = __float2bfloat16_rn(1.0f);
                 publish_smem();
             } else {
                 uint32_t v[16];
@@ -401,96 +423,92 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
                 }
             }
         } else {
-            float r_ = sigmoid_f(hz[0]), g_ = sigmoid_f(hz[1]), b_ = sigmoid_f(hz[2]);
-            float sg = fmaxf(hz[3], 0.0f);
-            head_s[tid] = make_float4(r_, g_, b_, sg);
-            dist_s[tid] = my_dist;
-            if (tid < rays_here * 3) tgt_s[tid] = my_tgt;
-            if (p.dbg && tid < valid) reinterpret_cast<float4 *>(p.dbg)[row0 + tid] = make_float4(r_, g_, b_, sg);
+            // Compositing with one thread per sample (thread r <-> sample r of the tile): segmented
+            // warp-shuffle scans inside each warp, carries across the 4 warps through shared
+            // memory.  scripts/nerf.py:176-288 and its reverse.
+            const float cr = sigmoid_f(hz[0]), cg = sigmoid_f(hz[1]), cb = sigmoid_f(hz[2]);
+            const float sg = fmaxf(hz[3], 0.0f);
+            if (p.dbg && tid < valid) reinterpret_cast<float4 *>(p.dbg)[row0 + tid] = make_float4(cr, cg, cb, sg);
+            const float e = __expf((0.0f - sg) * my_dist);
+            const float a = 1.0f - e;
+            const float qv = live ? (1.0f - a) + 1e-10f : 1.0f;
+            float pr = qv;                                   // segmented inclusive product
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                float o = __shfl_up_sync(0xffffffffu, pr, d);
+                if (lane >= d && smp >= d) pr *= o;
+            }
+            if (lane == 31) { tailp[warp] = pr; tail_s[warp] = smp; }
+            if (lane == 0) headq[warp] = qv;
+            if (live && smp == 0) {
+                color_s[ray_l * 3] = 0.f; color_s[ray_l * 3 + 1] = 0.f; color_s[ray_l * 3 + 2] = 0.f;
+                tgt_s[ray_l * 3] = tg0; tgt_s[ray_l * 3 + 1] = tg1; tgt_s[ray_l * 3 + 2] = tg2;
+            }
             __syncthreads();
-            // warp w composites rays w, w+4, ... of this tile
-            const int S = p.S;
-            for (int ry = warp; ry < rays_here; ry += 4) {
-                const int base = ry * S;
-                const long long ray = row0 / S + ry;
-                const int nch = (S + 31) >> 5;
-                float cin[4];   // prefix product entering each chunk (S <= 128)
-                float carry = 1.0f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    if (ch < nch) {
-                        const int s = ch * 32 + lane;
-                        const bool ok = s < S;
-                        float4 h = ok ? head_s[base + s] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        float dist = ok ? dist_s[base + s] : 0.0f;
-                        float a = 1.0f - __expf((0.0f - h.w) * dist);
-                        float qv = ok ? (1.0f - a) + 1e-10f : 1.0f;
-                        cin[ch] = carry;
-                        float pr = warp_incl_prod(qv, lane) * carry;
-                        carry = __shfl_sync(0xffffffffu, pr, 31);
-                        float T = (s == 0) ? 1.0f : pr;
-                        float w = a * T;
-                        if (ok) { c0 = fmaf(w, h.x, c0); c1 = fmaf(w, h.y, c1); c2 = fmaf(w, h.z, c2); }
-                    }
+            float carry = 1.0f;                              // product of this ray's samples in earlier warps
+            if (smp > lane) {
+                for (int w2 = warp - 1; w2 >= 0; --w2) {
+                    carry *= tailp[w2];
+                    if (tail_s[w2] < 32) break;              // that warp's last segment started inside it
                 }
+            }
+            const float Cpre = pr * carry;                   // true inclusive product prod_{k<=s} q_k
+            const float T = (smp == 0) ? 1.0f : Cpre;
+            const float wgt = a * T;
+            {   // colour: segmented inclusive sums, one shared-memory atomic per (warp, ray) segment
+                float s0 = live ? wgt * cr : 0.f, s1 = live ? wgt * cg : 0.f, s2 = live ? wgt * cb : 0.f;
 #pragma unroll
-                for (int d = 16; d >= 1; d >>= 1) {
-                    c0 += __shfl_xor_sync(0xffffffffu, c0, d);
-                    c1 += __shfl_xor_sync(0xffffffffu, c1, d);
-                    c2 += __shfl_xor_sync(0xffffffffu, c2, d);
+                for (int d = 1; d < 32; d <<= 1) {
+                    float o0 = __shfl_up_sync(0xffffffffu, s0, d), o1 = __shfl_up_sync(0xffffffffu, s1, d), o2 = __shfl_up_sync(0xffffffffu, s2, d);
+                    if (lane >= d && smp >= d) { s0 += o0; s1 += o1; s2 += o2; }
                 }
-                if (p.color && lane == 0) { p.color[ray * 3] = c0; p.color[ray * 3 + 1] = c1; p.color[ray * 3 + 2] = c2; }
-                if (!p.target) continue;
-                float t0, t1, t2;
-                if (ry < 42) { t0 = tgt_s[ry * 3]; t1 = tgt_s[ry * 3 + 1]; t2 = tgt_s[ry * 3 + 2]; }
-                else { const float *tg = p.target + ray * 3; t0 = __ldg(tg); t1 = __ldg(tg + 1); t2 = __ldg(tg + 2); }
-                const float d0 = c0 - t0, d1 = c1 - t1, d2 = c2 - t2;
-                if (lane == 0) loss_acc += d0 * d0 + d1 * d1 + d2 * d2;
-                if (!p.want_grad) continue;
-                const float dc0 = 2.0f * d0, dc1 = 2.0f * d1, dc2 = 2.0f * d2;
-                float G_next = 0.0f, q_next = 0.0f;
-#pragma unroll
-                for (int ch = 3; ch >= 0; --ch) {
-                    if (ch < nch) {
-                        const int s = ch * 32 + lane;
-                        const bool ok = s < S;
-                        float4 h = ok ? head_s[base + s] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        float dist = ok ? dist_s[base + s] : 0.0f;
-                        const float e = __expf((0.0f - h.w) * dist);
-                        const float a = 1.0f - e;
-                        const float qv = ok ? (1.0f - a) + 1e-10f : 1.0f;
-                        const float Cpre = warp_incl_prod(qv, lane) * cin[ch];
-                        const float T = (s == 0) ? 1.0f : Cpre;
-                        const float w = a * T;
-                        const float d_w = h.x * dc0 + h.y * dc1 + h.z * dc2;
-                        const float dT = (s == 0 || !ok) ? 0.0f : d_w * a;
-                        float qn = __shfl_down_sync(0xffffffffu, qv, 1);
-                        if (lane == 31) qn = q_next;
-                        float Aa = dT, Bb = (ok && s + 1 < S) ? qn : 0.0f;
-#pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) {
-                            float A2 = __shfl_down_sync(0xffffffffu, Aa, d);
-                            float B2 = __shfl_down_sync(0xffffffffu, Bb, d);
-                            if (lane + d < 32) { Aa = fmaf(Bb, A2, Aa); Bb = Bb * B2; }
-                        }
-                        const float Gv = fmaf(Bb, G_next, Aa);
-                        float Cm1 = __shfl_up_sync(0xffffffffu, Cpre, 1);
-                        if (lane == 0) Cm1 = cin[ch];
-                        const float d_alpha = d_w * T - Cm1 * Gv;
-                        if (ok)
-                            dzh_s[base + s] = make_float4((w * dc0) * (h.x * (1.0f - h.x)), (w * dc1) * (h.y * (1.0f - h.y)),
-                                                          (w * dc2) * (h.z * (1.0f - h.z)), h.w > 0.0f ? d_alpha * e * dist : 0.0f);
-                        G_next = __shfl_sync(0xffffffffu, Gv, 0);
-                        q_next = __shfl_sync(0xffffffffu, qv, 0);
-                    }
+                if (live && (lane == 31 || smp == S - 1)) {
+                    atomicAdd(color_s + ray_l * 3, s0); atomicAdd(color_s + ray_l * 3 + 1, s1); atomicAdd(color_s + ray_l * 3 + 2, s2);
                 }
             }
             __syncthreads();
-            if (p.want_grad && p.target && tid < rays_here * S) {
-                float4 d4 = dzh_s[tid];
-                dz[0] = d4.x; dz[1] = d4.y; dz[2] = d4.z; dz[3] = d4.w;
+            float dc0 = 0.f, dc1 = 0.f, dc2 = 0.f;
+            if (live) {
+                const float c0 = color_s[ray_l * 3], c1 = color_s[ray_l * 3 + 1], c2 = color_s[ray_l * 3 + 2];
+                if (smp == 0 && p.color) {
+                    float *co = p.color + (row0 / S + ray_l) * 3;
+                    co[0] = c0; co[1] = c1; co[2] = c2;
+                }
+                if (p.target) {
+                    const float d0 = c0 - tgt_s[ray_l * 3], d1 = c1 - tgt_s[ray_l * 3 + 1], d2 = c2 - tgt_s[ray_l * 3 + 2];
+                    if (smp == 0) loss_acc += d0 * d0 + d1 * d1 + d2 * d2;
+                    dc0 = 2.0f * d0; dc1 = 2.0f * d1; dc2 = 2.0f * d2;
+                }
             }
-            __syncthreads(); // the scratch aliases dZ_0: everyone has read it before anyone moves on
+            if (p.want_grad && p.target) {
+                // G_s = dT_s + q_{s+1} G_{s+1}: suffix scan of affine maps; B = 0 at a ray's last sample
+                const float d_w = cr * dc0 + cg * dc1 + cb * dc2;
+                const float dT = (smp == 0 || !live) ? 0.0f : d_w * a;
+                float qn = __shfl_down_sync(0xffffffffu, qv, 1);
+                if (lane == 31) qn = warp < 3 ? headq[warp + 1] : 0.0f;
+                float Aa = dT, Bb = (live && smp + 1 < S) ? qn : 0.0f;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    float A2 = __shfl_down_sync(0xffffffffu, Aa, d);
+                    float B2 = __shfl_down_sync(0xffffffffu, Bb, d);
+                    if (lane + d < 32) { Aa = fmaf(Bb, A2, Aa); Bb = Bb * B2; }
+                }
+                if (lane == 0) { headA[warp] = Aa; headB[warp] = Bb; }
+                __syncthreads();
+                float Gn = 0.0f;                             // G at lane 0 of the next warp
+                for (int w2 = 3; w2 > warp; --w2) Gn = fmaf(headB[w2], Gn, headA[w2]);
+                const float Gv = fmaf(Bb, Gn, Aa);
+                float Cm1 = __shfl_up_sync(0xffffffffu, Cpre, 1);
+                if (lane == 0) Cm1 = carry;
+                if (smp == 0) Cm1 = 1.0f;
+                const float d_alpha = d_w * T - Cm1 * Gv;
+                if (live) {
+                    dz[0] = (wgt * dc0) * (cr * (1.0f - cr));
+                    dz[1] = (wgt * dc1) * (cg * (1.0f - cg));
+                    dz[2] = (wgt * dc2) * (cb * (1.0f - cb));
+                    dz[3] = sg > 0.0f ? d_alpha * e * my_dist : 0.0f;
+                }
+            }
         }
         if (!p.want_grad) continue;
         // ---- backward.  dZ_{L-1}: 4 live features, the rest of the 16 stay zero
@@ -508,18 +526,17 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
             for (int c16 = 0; c16 < HP / 16; ++c16) {
                 uint32_t v[16];
                 tmem_ld16(tmem + lane_base + (l & 1) * HP + c16 * 16, v);
-                tmem_ld_wait();
                 uint4 h0 = *row_ptr(al, c16 * 2), h1 = *row_ptr(al, c16 * 2 + 1);
                 uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-                float f[16];
+                tmem_ld_wait();
+                uint32_t o[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    // bf16 post-ReLU values are >= 0: positive <=> non-zero bits
-                    f[2 * j] = (hw[j] & 0xFFFFu) ? __uint_as_float(v[2 * j]) : 0.0f;
-                    f[2 * j + 1] = (hw[j] >> 16) ? __uint_as_float(v[2 * j + 1]) : 0.0f;
+                    // ReLU mask: bf16 post-ReLU values are >= 0, so positive <=> non-zero halfword
+                    o[j] = pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])) & __vcmpne2(hw[j], 0u);
                 }
-                *row_ptr(dzn, c16 * 2) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-                *row_ptr(dzn, c16 * 2 + 1) = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
+                *row_ptr(dzn, c16 * 2) = make_uint4(o[0], o[1], o[2], o[3]);
+                *row_ptr(dzn, c16 * 2 + 1) = make_uint4(o[4], o[5], o[6], o[7]);
             }
             publish_smem();
         }
@@ -659,8 +676,11 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     int grid = ctx->sm_count * per_sm;
     if (grid > p.n_tiles) grid = p.n_tiles;
     if (grid < 1) grid = 1;
-    LNB_TRY(lnb_arena_reserve(ctx, (size_t)grid * p.part_stride * sizeof(float) + 4096));
+    const int wimg_bytes = HP == 16 ? TcLayout<16>::wimg_bytes(L, K0P) : (HP == 32 ? TcLayout<32>::wimg_bytes(L, K0P) : TcLayout<64>::wimg_bytes(L, K0P));
+    LNB_TRY(lnb_arena_reserve(ctx, (size_t)grid * p.part_stride * sizeof(float) + wimg_bytes + 8192));
     p.part = (float *)lnb_arena_take(ctx, (size_t)grid * p.part_stride * sizeof(float));
+    uint8_t *wimg = (uint8_t *)lnb_arena_take(ctx, wimg_bytes);
+    p.wimg = wimg;
     float *loss = a->loss ? a->loss : (float *)lnb_arena_take(ctx, 16);
     if (N > 0) {
 #define LNB_TC(HPV)                                                                              \
@@ -668,6 +688,10 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
         LNB_CUDA(cudaFuncSetAttribute(fused_tc_kernel<HPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         fused_tc_kernel<HPV><<<grid, TILE, smem, ctx->stream>>>(p);                              \
     } while (0)
+        if (HP == 16) tc_prep_kernel<16><<<1, 256, 0, ctx->stream>>>(p, wimg);
+        else if (HP == 32) tc_prep_kernel<32><<<1, 256, 0, ctx->stream>>>(p, wimg);
+        else tc_prep_kernel<64><<<1, 256, 0, ctx->stream>>>(p, wimg);
+        LNB_CHECK_LAUNCH();
         lnb_prof_begin(ctx, "fused_tc_kernel");
         if (HP == 16) LNB_TC(16);
         else if (HP == 32) LNB_TC(32);
