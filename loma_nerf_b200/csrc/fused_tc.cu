@@ -27,6 +27,9 @@
 // which is what lets H_l serve as A for the forward MMA and as A^T for the dW MMA, and W_l as B
 // for forward and B^T for backward, without any transposed copy.
 #include <cuda_bf16.h>
+#include <stdio.h>
+
+#include <vector>
 
 #include "lnb_internal.h"
 
@@ -127,7 +130,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&h);
 }
-__device__ __forceinline__ float sigmoid_f(float z) { return 1.0f / (1.0f + __expf(0.0f - z)); }
+__device__ __forceinline__ float sigmoid_f(float z) { return __fdividef(1.0f, 1.0f + __expf(0.0f - z)); }
 
 __device__ __forceinline__ float warp_incl_prod(float p, int lane)
 {
@@ -150,9 +153,14 @@ __device__ __forceinline__ float warp_incl_prod(float p, int lane)
 //   | weight image: W_0 .. W_{L-1} (bf16 slabs), biases (fp32)      <- one TMA per CTA
 //   | stage: fp32 features of the next tile                          <- one TMA per tile
 //   | compositing scratch | mbarriers
-// TMEM (128 columns when HP <= 32): R0 [0,HP) and R1 [HP,2HP) ping-pong layer outputs / dH;
-// dW accumulators (M=64: 16 lanes per 32-lane subpartition) pair up two per column range using
-// lane offsets 0 and 16: dW_l at columns 2HP + (l/2)*HP, lanes + 16*(l&1).
+// TMEM (128 columns for 3 layers of width <= 31): [0,HP) holds each layer's output / dH in turn
+// (its epilogue drains it before the next MMA is issued); [HP, HP+ndw) holds ONE concatenated
+// weight-gradient accumulator: all A_l buffers are contiguous in shared memory and so are all
+// dZ_l buffers, so a single M=128 x N=ndw MMA per 16-sample K-step computes
+// [A_0|A_1|..]^T [dZ_0|dZ_1|..]; the blocks (A_l, dZ_l) on its diagonal are the dW_l (the
+// off-diagonal blocks are never read).  8 MMAs per tile instead of 8 per layer.
+// Every MMA's operands are tile-invariant, so the descriptors are computed once per CTA into a
+// shared-memory "MMA program"; issuing a stage is a loop of (load 32 B record, tcgen05.mma).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
@@ -167,9 +175,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 template <int HP>
 struct TcLayout {
     static constexpr int HSL = HP / 8;
-    static constexpr int DW_GROUPS = (MAXL + 1) / 2;
-    static constexpr int TMEM_NEED = 2 * HP + DW_GROUPS * HP;
-    static constexpr uint32_t TMEM_COLS = TMEM_NEED <= 32 ? 32 : (TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512)));
+    // TMEM columns: [0,HP) the layer output / dH region (drained by its epilogue before the next
+    // MMA is issued), [HP, HP + ndw) the concatenated dW accumulator (see issue of the dW stage)
+    __host__ __device__ static int ndw(int L) { return (L - 1) * HP + 16; }
+    __host__ __device__ static uint32_t tmem_cols(int L)
+    {
+        const int need = HP + ndw(L);
+        return need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512)));
+    }
+    static constexpr int MAX_STAGES = 2 * MAXL + 1; // records of the per-CTA MMA program
     __host__ __device__ static int a_off(int l, int K0P) { return l == 0 ? 0 : (K0P / 8 + (l - 1) * HSL) * SLAB; }
     __host__ __device__ static int dz_off(int l, int L, int K0P) { return (K0P / 8 + (L - 1) * HSL + l * HSL) * SLAB; }
     __host__ __device__ static int act_bytes(int L, int K0P) { return (K0P / 8 + 2 * (L - 1) * HSL + 2) * SLAB; }
@@ -185,10 +199,13 @@ struct TcLayout {
     // tc_prep_kernel in global memory
     __host__ __device__ static int wimg_bytes(int L, int K0P) { return w_off(L, L, K0P) + MAXL * HP * 4; }
     __host__ __device__ static int stage_bytes(int c_in, int K0P) { return (TILE * c_in * 4 + 32 + K0P * 4 + 15) / 16 * 16; }
-    static constexpr int SCRATCH_FLOATS = 2 * TILE * 3 + 40; // colour + target per ray, scan carries, loss
+    static constexpr int SCRATCH_FLOATS = 48; // colour + target per ray, scan carries, loss
     __host__ __device__ static size_t total(int L, int K0P, int c_in)
     {
-        return (size_t)act_bytes(L, K0P) + wimg_bytes(L, K0P) + stage_bytes(c_in, K0P) + SCRATCH_FLOATS * 4 + 48;
+        // the concatenated dW MMA reads 16 slabs (M = 128 features) from the start of shared
+        // memory whatever the real feature count: keep that inside the allocation
+        const size_t t = (size_t)act_bytes(L, K0P) + wimg_bytes(L, K0P) + stage_bytes(c_in, K0P) + SCRATCH_FLOATS * 4 + 64 + MAX_STAGES * 48;
+        return t < 16 * SLAB ? 16 * SLAB : t;
     }
 };
 
@@ -220,23 +237,32 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
 {
     using LY = TcLayout<HP>;
     extern __shared__ __align__(1024) uint8_t smem[];
+#ifdef LNB_TC_CLK
+    const long long clk_start = clock64();
+#endif
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = p.L, K0P = p.K0P, c_in = p.dims[0], S = p.S;
     const int act_bytes = LY::act_bytes(L, K0P);
     uint8_t *const Wbase = smem + act_bytes;
     const float *const bias_s = reinterpret_cast<const float *>(Wbase + LY::w_off(L, L, K0P));
     float *const stage = reinterpret_cast<float *>(Wbase + LY::wimg_bytes(L, K0P));
-    float *const color_s = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(stage) + LY::stage_bytes(c_in, K0P));
+    // per-ray colour / target scratch aliases dZ_0: it is dead from the top of a tile (the previous
+    // tile's dW MMAs have been awaited) until the last backward epilogue writes it
+    float *const color_s = reinterpret_cast<float *>(smem + LY::dz_off(0, L, K0P));
     float *const tgt_s = color_s + TILE * 3;
-    float *const tailp = tgt_s + TILE * 3;                   // [4] inclusive product at lane 31 of each warp
+    float *const tailp = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(stage) + LY::stage_bytes(c_in, K0P)); // [4] inclusive product at lane 31
     int *const tail_s = reinterpret_cast<int *>(tailp + 4);  // [4] sample index at lane 31
     float *const headq = tailp + 8;                          // [5] q at lane 0 of each warp
     float *const headA = tailp + 13;                         // [5]
     float *const headB = tailp + 18;                         // [5]
     float *const red_s = tailp + 24;                         // [8]
-    uint64_t *const bar_p = reinterpret_cast<uint64_t *>(tailp + 40);
-    uint32_t *const tmem_slot = reinterpret_cast<uint32_t *>(bar_p + 3);
-    const uint32_t bar_mma = smem_u32(bar_p), bar_x = smem_u32(bar_p + 1), bar_w = smem_u32(bar_p + 2);
+    uint64_t *const bar_p = reinterpret_cast<uint64_t *>(tailp + 48);
+    uint32_t *const tmem_slot = reinterpret_cast<uint32_t *>(bar_p + 4);
+    const uint32_t bar_mma = smem_u32(bar_p), bar_x = smem_u32(bar_p + 1), bar_w = smem_u32(bar_p + 2), bar_dw = smem_u32(bar_p + 3);
+    // MMA program: one record per stage; the MMAs of a stage differ only by constant increments of
+    // the descriptors' start-address fields (the K-steps)
+    struct StageRec { uint64_t a, b; uint32_t inc_a, inc_b, idesc, dcol; uint32_t count, first_acc, pad0, pad1; };
+    StageRec *const prog = reinterpret_cast<StageRec *>(reinterpret_cast<uint8_t *>(bar_p) + 64);
 
     // TMA source of a tile's features (16 B aligned start, `lead` floats in front of the tile)
     auto x_src = [&](int tile, int &lead, uint32_t &bytes) -> const void * {
@@ -252,15 +278,34 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
 
     // ---- one-time setup: zero activations and stage, then TMA the weight image and the first tile
     for (uint8_t *z = smem + tid * 16; z < smem + act_bytes; z += TILE * 16) *reinterpret_cast<uint4 *>(z) = make_uint4(0, 0, 0, 0);
-    for (uint8_t *z = reinterpret_cast<uint8_t *>(stage) + tid * 16; z < reinterpret_cast<uint8_t *>(color_s); z += TILE * 16)
+    for (uint8_t *z = reinterpret_cast<uint8_t *>(stage) + tid * 16; z < reinterpret_cast<uint8_t *>(tailp); z += TILE * 16)
         *reinterpret_cast<uint4 *>(z) = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         mbar_init(bar_mma, 1);
         mbar_init(bar_x, 1);
         mbar_init(bar_w, 1);
+        mbar_init(bar_dw, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // ---- build the MMA program.  Stages: fwd l (0..L-1), dH l (L+l, l = 1..L-1), dW (2L)
+        for (int l = 0; l < L; ++l) {          // D[128 x Np] = A_l[128 x Kp] * W_l   (A, B K-major)
+            const int Np = LY::np(l, L), Kp = LY::kp(l, K0P);
+            const uint32_t a0 = smem_u32(smem + LY::a_off(l, K0P)), b0 = smem_u32(Wbase + LY::w_off(l, L, K0P));
+            prog[l] = StageRec{smem_desc(a0, SLAB, 128), smem_desc(b0, Np * 16, 128), (uint32_t)(2 * SLAB) >> 4, (uint32_t)(2 * Np * 16) >> 4,
+                               instr_desc(128, Np, 0, 0), 0u, (uint32_t)(Kp / 16), 0u, 0u, 0u};
+        }
+        for (int l = 1; l < L; ++l) {          // dH_l[128 x Kp] = dZ_l[128 x Np] * W_l^T (same W bytes, MN-major)
+            const int Np = LY::np(l, L), Kp = LY::kp(l, K0P);
+            const uint32_t a0 = smem_u32(smem + LY::dz_off(l, L, K0P)), b0 = smem_u32(Wbase + LY::w_off(l, L, K0P));
+            prog[L + l] = StageRec{smem_desc(a0, SLAB, 128), smem_desc(b0, 128, Np * 16), (uint32_t)(2 * SLAB) >> 4, 256u >> 4,
+                                   instr_desc(128, Kp, 0, 1), 0u, (uint32_t)(Np / 16), 0u, 0u, 0u};
+        }
+        {                                      // dW: [all A]^T [all dZ], K = 128 samples, both MN-major
+            const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + LY::dz_off(0, L, K0P));
+            prog[2 * L] = StageRec{smem_desc(a0, 128, SLAB), smem_desc(b0, 128, SLAB), 256u >> 4, 256u >> 4,
+                                   instr_desc(128, LY::ndw(L), 1, 1), (uint32_t)HP, (uint32_t)(TILE / 16), 2u, 0u, 0u};
+        }
     }
-    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), LY::TMEM_COLS);
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), LY::tmem_cols(L));
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -278,37 +323,26 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     uint32_t phase = 0, xphase = 0;
     float loss_acc = 0.0f;
-    bool dw_started = false;
+    bool dw_started = false, dw_pending = false;
+    uint32_t dwphase = 0;
     mbar_wait(bar_w, 0); // weights + biases have landed
 
     auto a_buf = [&](int l) { return smem + LY::a_off(l, K0P); };
     auto dz_buf = [&](int l) { return smem + LY::dz_off(l, L, K0P); };
     auto row_ptr = [&](uint8_t *buf, int slab) { return reinterpret_cast<uint4 *>(buf + slab * SLAB + tid * 16); };
-    auto dw_taddr = [&](int l) { return tmem + (uint32_t)(2 * HP + (l >> 1) * HP) + ((uint32_t)(16 * (l & 1)) << 16); };
-    // D[128 x Np] = A_l[128 x Kp] * W_l            (A, B K-major)
-    auto issue_fwd = [&](int l, int reg) {
-        const int Np = LY::np(l, L), Kp = LY::kp(l, K0P);
-        const uint32_t idesc = instr_desc(128, Np, 0, 0);
-        const uint32_t a0 = smem_u32(a_buf(l)), b0 = smem_u32(Wbase + LY::w_off(l, L, K0P));
-        for (int k = 0; k < Kp / 16; ++k)
-            umma_bf16(tmem + reg * HP, smem_desc(a0 + k * 2 * SLAB, SLAB, 128), smem_desc(b0 + k * 2 * (Np * 16), Np * 16, 128), idesc, k > 0);
-    };
-    // dH_l[128 x Kp] = dZ_l[128 x Np] * W_l^T      (B^T = the same bytes read MN-major)
-    auto issue_dh = [&](int l, int reg) {
-        const int Np = LY::np(l, L), Kp = LY::kp(l, K0P);
-        const uint32_t idesc = instr_desc(128, Kp, 0, 1);
-        const uint32_t a0 = smem_u32(dz_buf(l)), b0 = smem_u32(Wbase + LY::w_off(l, L, K0P));
-        for (int k = 0; k < Np / 16; ++k)
-            umma_bf16(tmem + reg * HP, smem_desc(a0 + k * 2 * SLAB, SLAB, 128), smem_desc(b0 + k * 2 * 128, 128, Np * 16), idesc, k > 0);
-    };
-    // dW_l[64 x Np] += A_l^T[64 feats x 128 samples] * dZ_l[128 samples x Np]   (both MN-major)
-    auto issue_dw = [&](int l) {
-        const int Np = LY::np(l, L);
-        const uint32_t idesc = instr_desc(64, Np, 1, 1);
-        const uint32_t a0 = smem_u32(a_buf(l)), b0 = smem_u32(dz_buf(l));
-        const uint32_t d = dw_taddr(l);
-        for (int k = 0; k < TILE / 16; ++k)
-            umma_bf16(d, smem_desc(a0 + k * 256, 128, SLAB), smem_desc(b0 + k * 256, 128, SLAB), idesc, (dw_started || k > 0) ? 1u : 0u);
+    // issue one stage of the MMA program (thread 0 only)
+    auto issue_stage = [&](int stage_id) {
+        const uint4 r0 = *reinterpret_cast<const uint4 *>(prog + stage_id);
+        const uint4 r1 = *(reinterpret_cast<const uint4 *>(prog + stage_id) + 1);
+        const uint4 r2 = *(reinterpret_cast<const uint4 *>(prog + stage_id) + 2);
+        uint32_t alo = r0.x, blo = r0.z;
+        const uint32_t ahi = r0.y, bhi = r0.w;
+        uint32_t acc = r2.y == 2u ? (dw_started ? 1u : 0u) : r2.y;
+        const uint32_t d = tmem + r1.w;
+        for (uint32_t k = 0; k < r2.x; ++k) {
+            umma_bf16(d, ((uint64_t)ahi << 32) | alo, ((uint64_t)bhi << 32) | blo, r1.z, acc);
+            alo += r1.x; blo += r1.y; acc = 1u;
+        }
     };
     auto commit_and_wait = [&]() {
         if (tid == 0) umma_commit(bar_mma);
@@ -323,11 +357,19 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
         tc_fence_after();
     };
 
+#ifdef LNB_TC_CLK
+    long long clk_acc[16] = {0}, clk_t = clock64();
+    clk_acc[14] = clk_t - clk_start;
+#define CLK(i) do { long long t_ = clock64(); clk_acc[i] += t_ - clk_t; clk_t = t_; } while (0)
+#else
+#define CLK(i)
+#endif
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const long long row0 = (long long)tile * p.rows_per_tile;
         long long rem = p.N - row0;
         const int valid = rem < p.rows_per_tile ? (int)rem : p.rows_per_tile;
         const int rays_here = valid / S;
+        CLK(15);
         const int smp = tid % S, ray_l = tid / S;        // this thread's sample within its ray
         const bool live = tid < rays_here * S;
         // early, latency-tolerant loads for this tile (consumed after the MLP forward)
@@ -347,6 +389,9 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
             (void)x_src(tile, lead, bytes);
             mbar_wait(bar_x, xphase);
             xphase ^= 1;
+            CLK(0);
+            if (dw_pending) { mbar_wait(bar_dw, dwphase); dwphase ^= 1; dw_pending = false; tc_fence_after(); }
+            CLK(12);
             uint8_t *a0 = a_buf(0);
             const float *xr = stage + lead + tid * c_in;
             if (tid < valid) {
@@ -363,6 +408,7 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
             reinterpret_cast<__nv_bfloat16 *>(a0)[(c_in >> 3) * (TILE * 8) + tid * 8 + (c_in & 7)] = __float2bfloat16_rn(1.0f);
         }
         publish_smem(); // also: every thread is done reading `stage`
+        CLK(1);
         if (tid == 0) {
             const int nt = tile + gridDim.x;
             if (nt < p.n_tiles) {
@@ -375,8 +421,10 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
         // ---- forward
         float hz[4];
         for (int l = 0; l < L; ++l) {
-            if (tid == 0) issue_fwd(l, l & 1);
+            if (tid == 0) issue_stage(l);
+            CLK(2);
             commit_and_wait();
+            CLK(3);
             const float *bl = bias_s + l * HP;
             if (l < L - 1) {
                 const int ones_col = p.dims[l + 1];
@@ -384,7 +432,7 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
 #pragma unroll
                 for (int c16 = 0; c16 < HP / 16; ++c16) {
                     uint32_t v[16];
-                    tmem_ld16(tmem + lane_base + (l & 1) * HP + c16 * 16, v);
+                    tmem_ld16(tmem + lane_base + c16 * 16, v);
                     float bv[16];
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
@@ -400,10 +448,12 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
                 }
                 __syncwarp();
                 reinterpret_cast<__nv_bfloat16 *>(an)[(ones_col >> 3) * (TILE * 8) + tid * 8 + (ones_col & 7)] = __float2bfloat16_rn(1.0f);
+                CLK(4);
                 publish_smem();
+                CLK(5);
             } else {
                 uint32_t v[16];
-                tmem_ld16(tmem + lane_base + (l & 1) * HP, v);
+                tmem_ld16(tmem + lane_base, v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 4; ++j) hz[j] = __uint_as_float(v[j]) + bl[j];
@@ -428,7 +478,6 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
             // memory.  scripts/nerf.py:176-288 and its reverse.
             const float cr = sigmoid_f(hz[0]), cg = sigmoid_f(hz[1]), cb = sigmoid_f(hz[2]);
             const float sg = fmaxf(hz[3], 0.0f);
-            if (p.dbg && tid < valid) reinterpret_cast<float4 *>(p.dbg)[row0 + tid] = make_float4(cr, cg, cb, sg);
             const float e = __expf((0.0f - sg) * my_dist);
             const float a = 1.0f - e;
             const float qv = live ? (1.0f - a) + 1e-10f : 1.0f;
@@ -510,22 +559,22 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
                 }
             }
         }
+        CLK(6);
         if (!p.want_grad) continue;
         // ---- backward.  dZ_{L-1}: 4 live features, the rest of the 16 stay zero
         *row_ptr(dz_buf(L - 1), 0) = make_uint4(pack_bf16(dz[0], dz[1]), pack_bf16(dz[2], dz[3]), 0u, 0u);
         publish_smem();
-        for (int l = L - 1; l >= 0; --l) {
-            if (tid == 0) {
-                issue_dw(l);
-                if (l > 0) issue_dh(l, l & 1);
-            }
-            commit_and_wait(); // also orders the dW reads of A_l / dZ_l before they are overwritten
-            if (l == 0) break;
+        CLK(7);
+        for (int l = L - 1; l >= 1; --l) {
+            if (tid == 0) issue_stage(L + l);
+            CLK(8);
+            commit_and_wait();
+            CLK(9);
             uint8_t *al = a_buf(l), *dzn = dz_buf(l - 1);
 #pragma unroll
             for (int c16 = 0; c16 < HP / 16; ++c16) {
                 uint32_t v[16];
-                tmem_ld16(tmem + lane_base + (l & 1) * HP + c16 * 16, v);
+                tmem_ld16(tmem + lane_base + c16 * 16, v);
                 uint4 h0 = *row_ptr(al, c16 * 2), h1 = *row_ptr(al, c16 * 2 + 1);
                 uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
                 tmem_ld_wait();
@@ -538,12 +587,20 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
                 *row_ptr(dzn, c16 * 2) = make_uint4(o[0], o[1], o[2], o[3]);
                 *row_ptr(dzn, c16 * 2 + 1) = make_uint4(o[4], o[5], o[6], o[7]);
             }
+            CLK(10);
             publish_smem();
+            CLK(11);
         }
+        // all dZ_l are in shared memory: the weight-gradient MMAs run in the background; their
+        // completion is awaited only before A_0 is overwritten by the next tile (or at the end)
+        if (tid == 0) { issue_stage(2 * L); umma_commit(bar_dw); }
+        dw_pending = true;
+        CLK(13);
         dw_started = true;
     }
 
     // ---- epilogue: this CTA's partials.  loss, then per layer the valid (in_l+1) x out_l block.
+    if (dw_pending) { mbar_wait(bar_dw, dwphase); dwphase ^= 1; }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -554,19 +611,21 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
     __syncthreads();
     if (tid == 0) part[0] = red_s[0] + red_s[1] + red_s[2] + red_s[3];
     if (p.want_grad) {
+        // accumulator row (TMEM lane) = feature index over the concatenated A buffers; thread tid
+        // owns row tid: find the layer whose feature range contains it
         for (int l = 0; l < L; ++l) {
-            // M=64 accumulator l sits in lanes [16*(l&1), 16*(l&1)+16) of every 32-lane subpartition
-            const int sub = lane - 16 * (l & 1);
-            const int row = warp * 16 + sub;
+            const int rowbase = LY::a_off(l, K0P) / SLAB * 8;
             const int in_l = p.dims[l], out_l = p.dims[l + 1], Np = LY::np(l, L);
+            const int row = tid - rowbase;
+            const int colbase = HP + l * HP;
             float *o = part + p.part_off[l];
 #pragma unroll
             for (int c16 = 0; c16 < HP / 16; ++c16) {
                 if (c16 * 16 >= Np) break;
                 uint32_t v[16];
-                tmem_ld16(tmem + lane_base + (uint32_t)(2 * HP + (l >> 1) * HP + c16 * 16), v);
+                tmem_ld16(tmem + lane_base + (uint32_t)(colbase + c16 * 16), v);
                 tmem_ld_wait();
-                if (sub >= 0 && sub < 16 && row <= in_l) {
+                if (row >= 0 && row <= in_l) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         int col = c16 * 16 + j;
@@ -578,7 +637,11 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, LY::TMEM_COLS);
+    if (warp == 0) tmem_dealloc(tmem, LY::tmem_cols(L));
+#ifdef LNB_TC_CLK
+    clk_acc[13] += clock64() - clk_t; // (issue dW slot reused: epilogue after the last tile)
+    if (p.dbg && tid == 0) for (int i = 0; i < 16; ++i) p.dbg[blockIdx.x * 16 + i] = (float)clk_acc[i];
+#endif
 }
 
 // reduce the per-CTA partials in a fixed order; apply the seed; accumulate into the caller's buffers
@@ -667,7 +730,9 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
 
     const int c_in = mlp->dims[0];
     size_t smem = (HP == 16 ? TcLayout<16>::total(L, K0P, c_in) : (HP == 32 ? TcLayout<32>::total(L, K0P, c_in) : TcLayout<64>::total(L, K0P, c_in)));
-    const int tmem_cols = (int)(HP == 16 ? TcLayout<16>::TMEM_COLS : (HP == 32 ? TcLayout<32>::TMEM_COLS : TcLayout<64>::TMEM_COLS));
+    const int tmem_cols = (int)(HP == 16 ? TcLayout<16>::tmem_cols(L) : (HP == 32 ? TcLayout<32>::tmem_cols(L) : TcLayout<64>::tmem_cols(L)));
+    if (K0P / 8 + (L - 1) * (HP / 8) > 16) return unsupported("input + hidden widths exceed 128 features in total");
+    if ((L - 1) * HP + 16 > 256) return unsupported("hidden widths exceed 256 gradient columns");
     if ((reinterpret_cast<uintptr_t>(a->X) & 3) != 0) return unsupported("X must be 4-byte aligned");
     int per_sm = 512 / tmem_cols;
     int by_smem = (int)((227 * 1024) / (smem + 1024));
@@ -682,6 +747,12 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     uint8_t *wimg = (uint8_t *)lnb_arena_take(ctx, wimg_bytes);
     p.wimg = wimg;
     float *loss = a->loss ? a->loss : (float *)lnb_arena_take(ctx, 16);
+#ifdef LNB_TC_CLK
+    float *dbg_dev = nullptr;
+    cudaMalloc(&dbg_dev, (size_t)grid * 16 * sizeof(float));
+    cudaMemset(dbg_dev, 0, (size_t)grid * 16 * sizeof(float));
+    p.dbg = dbg_dev;
+#endif
     if (N > 0) {
 #define LNB_TC(HPV)                                                                              \
     do {                                                                                         \
@@ -702,6 +773,24 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     } else {
         grid = 0;
     }
+#ifdef LNB_TC_CLK
+    {
+        cudaStreamSynchronize(ctx->stream);
+        std::vector<float> h((size_t)grid * 16);
+        cudaMemcpy(h.data(), dbg_dev, h.size() * sizeof(float), cudaMemcpyDeviceToHost);
+        cudaFree(dbg_dev);
+        static int calls = 0;
+        if (++calls == 20) {
+            double acc[16] = {0};
+            for (int b = 0; b < grid; ++b) for (int i = 0; i < 16; ++i) acc[i] += h[(size_t)b * 16 + i];
+            const char *nm[16] = {"wait X", "convert+publish", "issue fwd", "wait fwd mma", "fwd epilogue", "fwd publish", "head+composite", "dz publish",
+                                  "issue bwd", "wait bwd mma", "bwd epilogue", "bwd publish", "wait dW", "issue dW + final epilogue", "prologue", "loop top"};
+            double tot = 0; for (int i = 0; i < 16; ++i) tot += acc[i];
+            fprintf(stderr, "[tc clk] grid %d tiles %d: cycles per tile (thread 0), total %.0f\n", grid, p.n_tiles, tot / p.n_tiles);
+            for (int i = 0; i < 16; ++i) if (acc[i] > 0) fprintf(stderr, "   %-18s %8.0f\n", nm[i], acc[i] / p.n_tiles);
+        }
+    }
+#endif
     const int n_el = p.part_stride - 1;
     const int seed_is_loss = a->seed_mode == LNB_SEED_LOSS;
     const float seed_val = seed_is_loss ? 1.0f : a->seed;
