@@ -34,7 +34,7 @@ extern "C" {
 #define LNB_API
 #endif
 
-#define LNB_ABI_VERSION 1
+#define LNB_ABI_VERSION 2
 #define LNB_MAX_LAYERS 16
 
 /* ------------------------------------------------------------------------------------------
@@ -107,6 +107,7 @@ typedef struct lnb_ctx lnb_ctx; /* device, stream, workspace; one per (thread, G
 enum { LNB_OK = 0, LNB_ERR_CUDA = 1, LNB_ERR_ARG = 2, LNB_ERR_UNSUPPORTED = 3 };
 enum { LNB_HEAD_NERF = 0,     /* sigmoid on channels 0-2, ReLU on channel 3: nerf.py:147-167 */
        LNB_HEAD_SIGMOID = 1 };/* sigmoid on every channel:                  mlp_fit.py:121-132 */
+enum { LNB_RAY_F64 = 0, LNB_RAY_F32 = 1 };
 enum { LNB_SEED_VALUE = 0,    /* backward seed _dreturn = args->seed                        */
        LNB_SEED_LOSS = 1 };   /* backward seed = this step's loss (train_nerf.py:477)       */
 enum { LNB_PATH_F32 = 0,      /* fp32 CUDA-core kernels, <=1e-5 of the reference: the fused  */
@@ -158,11 +159,19 @@ typedef struct {
     float *d_color;           /* += [R][3] or NULL  (d_accumulated_color)                       */
     float *d_inter;           /* += [n_layers][inter_rows][inter_ld] dZ_l, or NULL              */
     int path;                 /* LNB_PATH_*                                                     */
+    /* RAYS MODE (nerf only; selected when X == NULL): the features are computed on the device  */
+    /* from rays and sample depths exactly as the reference host does it: pts = o + d*t          */
+    /* (train_nerf.py:289-299), X = positional_encoding_3d(pts, pe_bands) (pos_encoding.py:38-70),*/
+    /* dists = [t[s+1]-t[s] ..., 1e8] (train_nerf.py:306-311).  `dists` is then ignored.         */
+    const void *rays_o, *rays_d; /* [R][3]                                                      */
+    const void *t;            /* [R][S] sample depths along each ray                            */
+    int ray_dtype;            /* LNB_RAY_F64 (the reference's get_rays/linspace dtype) or F32   */
+    int pe_bands;             /* E; dims[0] must equal 3 + 6E                                   */
 } lnb_step_args;
 
 LNB_API int lnb_abi_version(void);
 /* Fills out[0..n) with {sizeof(lnb_mlp), sizeof(lnb_step_args), offsetof(lnb_step_args, X),
- * inter, rgba, loss, want_grad, d_ws, path}; returns how many values exist.  Lets a foreign-
+ * inter, rgba, loss, want_grad, d_ws, path, rays_o, pe_bands}; returns how many values exist.  Lets a foreign-
  * language binding verify its struct mirror without a GPU. */
 LNB_API int lnb_struct_layout(int *out, int n);
 LNB_API int lnb_device_count(void);

@@ -15,6 +15,7 @@ LNB_OK, LNB_ERR_CUDA, LNB_ERR_ARG, LNB_ERR_UNSUPPORTED = 0, 1, 2, 3
 HEAD_NERF, HEAD_SIGMOID = 0, 1
 SEED_VALUE, SEED_LOSS = 0, 1
 PATH_F32, PATH_TC, PATH_F32_LAYERWISE = 0, 1, 2
+RAY_F64, RAY_F32 = 0, 1
 
 c_float_p = POINTER(c_float)
 
@@ -40,6 +41,8 @@ class LnbStepArgs(Structure):
         ("d_ws", c_void_p), ("d_bs", c_void_p), ("d_X", c_void_p), ("d_target", c_void_p),
         ("d_dists", c_void_p), ("d_color", c_void_p), ("d_inter", c_void_p),
         ("path", c_int),
+        ("rays_o", c_void_p), ("rays_d", c_void_p), ("t", c_void_p), ("ray_dtype", c_int),
+        ("pe_bands", c_int),
     ]
 
 

@@ -50,7 +50,7 @@ def _ptr(x):
     if x is None:
         return None
     if torch is not None and isinstance(x, torch.Tensor):
-        assert x.is_contiguous() and x.dtype in (torch.float32, torch.float64)
+        assert x.is_contiguous() and x.dtype in (torch.float32, torch.float64), (x.dtype, x.is_contiguous())
         return x.data_ptr()
     assert x.flags.c_contiguous
     return x.ctypes.data
@@ -122,17 +122,24 @@ class Context:
 
     # -------------------------------------------------------------------------------------------
     def _step(self, nerf, dims, X, ws, bs, target, dists, R, S, grad, seed, outputs, out, rows,
-              path, inter_accumulate, color_accumulate, head):
-        dev = _is_cuda(X)
+              path, inter_accumulate, color_accumulate, head, rays=None, pe_bands=0):
+        dev = _is_cuda(ws)
         mlp = make_mlp(dims, ws.shape, head)
         Ln, mi, mo = mlp.n_layers, mlp.max_in, mlp.max_out
-        N = int(X.shape[0])
+        N = int(X.shape[0]) if X is not None else int(R) * int(S)
         M = max(int(rows or 0), N)
         Wt = int(target.shape[1]) if target is not None else 3
         a = L.LnbStepArgs()
         a.R, a.S, a.n_rows, a.rows, a.target_w = int(R), int(S), N, M, Wt
         a.X, a.ws, a.bs = _ptr(X), _ptr(ws), _ptr(bs)
         a.target, a.dists = _ptr(target), _ptr(dists)
+        if rays is not None:
+            ro, rd, tv = rays
+            f64 = str(ro.dtype).endswith("float64")
+            assert str(rd.dtype) == str(ro.dtype) == str(tv.dtype), "rays_o, rays_d, t must share one dtype"
+            assert tuple(ro.shape) == (R, 3) and tuple(rd.shape) == (R, 3) and tuple(tv.shape) == (R, S)
+            a.rays_o, a.rays_d, a.t = _ptr(ro), _ptr(rd), _ptr(tv)
+            a.ray_dtype, a.pe_bands = (L.RAY_F64 if f64 else L.RAY_F32), int(pe_bands)
         a.inter_rows, a.inter_ld = M, mo
         a.inter_accumulate, a.color_accumulate = int(inter_accumulate), int(color_accumulate)
         a.want_grad = int(bool(grad))
@@ -144,7 +151,7 @@ class Context:
         a.path = PATHS[path]
         shapes = dict(inter=(Ln, M, mo), rgba=(R, S, 4), alpha=(R, S), cumprod=(R, S),
                       weights=(R, S), color=(R, 3), loss=(1,), d_ws=(Ln, mi, mo), d_bs=(Ln, mo),
-                      d_X=(N, int(X.shape[1])), d_target=(R, Wt), d_dists=(R, S),
+                      d_X=(N, int(dims[0])), d_target=(R, Wt), d_dists=(R, S),
                       d_color=(R, Wt), d_inter=(Ln, M, mo))
         res = {}
         out = out or {}
@@ -159,7 +166,7 @@ class Context:
             buf = out.get(k)
             if buf is None:
                 if dev:
-                    buf = torch.zeros(shapes[k], dtype=torch.float32, device=X.device)
+                    buf = torch.zeros(shapes[k], dtype=torch.float32, device=ws.device)
                 else:
                     buf = np.zeros(shapes[k], np.float32)
             else:
@@ -181,6 +188,16 @@ class Context:
         S = int(dists.shape[1]) if S is None else S
         return self._step(True, dims, X, ws, bs, target, dists, R, S, grad, seed, outputs, out,
                           rows, path, inter_accumulate, color_accumulate, L.HEAD_NERF)
+
+    def nerf_step_rays(self, dims, rays_o, rays_d, t, pe_bands, ws, bs, target=None, grad=False, seed=1.0,
+                       outputs=("color", "loss"), out=None, path="f32"):
+        """The same step starting from rays: the sample positions o + d*t, their positional encoding
+        and the dists are computed on the device (train_nerf.py:289-311, pos_encoding.py:38-70) --
+        fused into the first layer on the tensor-core path.  rays_o, rays_d [R][3], t [R][S], all
+        float64 (the reference's dtype) or all float32."""
+        R, S = int(t.shape[0]), int(t.shape[1])
+        return self._step(True, dims, None, ws, bs, target, None, R, S, grad, seed, outputs, out, None, path,
+                          False, False, L.HEAD_NERF, rays=(rays_o, rays_d, t), pe_bands=pe_bands)
 
     def fit_step(self, dims, X, ws, bs, target, grad=False, seed=1.0, outputs=("loss",), out=None,
                  rows=None, path="f32", inter_accumulate=False):

@@ -82,7 +82,8 @@ extern "C" int lnb_struct_layout(int *out, int n)
                      (int)offsetof(lnb_step_args, X), (int)offsetof(lnb_step_args, inter),
                      (int)offsetof(lnb_step_args, rgba), (int)offsetof(lnb_step_args, loss),
                      (int)offsetof(lnb_step_args, want_grad), (int)offsetof(lnb_step_args, d_ws),
-                     (int)offsetof(lnb_step_args, path)};
+                     (int)offsetof(lnb_step_args, path), (int)offsetof(lnb_step_args, rays_o),
+                     (int)offsetof(lnb_step_args, pe_bands)};
     const int k = (int)(sizeof(v) / sizeof(v[0]));
     for (int i = 0; i < k && i < n; ++i) out[i] = v[i];
     return k;
@@ -255,10 +256,18 @@ int validate(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, bool nerf
     d->M = a->rows > d->N ? a->rows : d->N;
     d->Wt = a->target_w > 0 ? a->target_w : 3;
     d->out_last = mlp->dims[mlp->n_layers];
-    LNB_ARG((a->X || d->N == 0) && a->ws && a->bs, "X, ws, bs are required");
+    const bool rays = !a->X && a->rays_o;
+    LNB_ARG((a->X || d->N == 0 || rays) && a->ws && a->bs, "X (or rays), ws, bs are required");
+    if (rays) {
+        LNB_ARG(nerf, "rays mode is a nerf-path feature");
+        LNB_ARG(a->rays_d && a->t, "rays mode needs rays_o, rays_d and t");
+        LNB_ARG(a->pe_bands >= 0 && d->c_in == 3 + 6 * a->pe_bands, "rays mode: dims[0] != 3 + 6*pe_bands");
+        LNB_ARG(a->ray_dtype == LNB_RAY_F64 || a->ray_dtype == LNB_RAY_F32, "ray_dtype");
+        LNB_ARG(!a->d_X, "d_X is not available in rays mode");
+    }
     if (nerf) {
         LNB_ARG(d->out_last >= 4, "nerf head needs >= 4 output channels");
-        LNB_ARG(a->dists || d->R == 0, "dists is required");
+        LNB_ARG(a->dists || d->R == 0 || rays, "dists is required");
         LNB_ARG(d->N >= d->R * d->S, "n_rows < R*S");
         LNB_ARG(d->Wt == 3, "nerf target must have 3 columns");
     } else {
@@ -289,8 +298,10 @@ int step_layerwise(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, boo
     if (n_chunks < 1) n_chunks = 1;
 
     // ---- arena plan
+    const bool rays = !a->X && a->rays_o;
     size_t need = 4096;
     auto add = [&](size_t floats) { need += align_up(floats * sizeof(float), 256) + 256; };
+    if (rays) { add((size_t)N * d.c_in); add((size_t)R * S); }
     if (!a->inter)
         for (int l = 0; l < L; ++l) add((size_t)M * mlp->dims[l + 1]);
     add((size_t)R + 1);      // ray_sse
@@ -306,6 +317,13 @@ int step_layerwise(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, boo
     LNB_TRY(lnb_arena_reserve(ctx, need));
     auto takef = [&](size_t floats) { return (float *)lnb_arena_take(ctx, floats * sizeof(float)); };
 
+    // ---- rays mode: sample generation + positional encoding on the device (float64 like the reference)
+    const float *X = a->X, *dists = a->dists;
+    if (rays) {
+        float *Xe = takef((size_t)N * d.c_in), *de = takef((size_t)R * S);
+        LNB_TRY(lnb_launch_sample_encode(ctx, a->rays_o, a->rays_d, a->t, a->ray_dtype == LNB_RAY_F64, R, S, a->pe_bands, Xe, de));
+        X = Xe; dists = de;
+    }
     // ---- forward
     std::vector<float *> Y(L);
     std::vector<int> ldy(L);
@@ -326,7 +344,7 @@ int step_layerwise(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, boo
 
     for (int l = 0; l < L; ++l) {
         lnb_gemm_args g{};
-        g.A = l == 0 ? a->X : Y[l - 1];
+        g.A = l == 0 ? X : Y[l - 1];
         g.lda = l == 0 ? d.c_in : ldy[l - 1];
         g.a_rows = l == 0 ? N : M;
         g.B = a->ws + (size_t)l * mlp->max_in * mlp->max_out;
@@ -345,7 +363,7 @@ int step_layerwise(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, boo
     const float *head = Y[L - 1];
     const int ldh = ldy[L - 1];
     if (nerf) {
-        LNB_TRY(lnb_launch_composite_fwd(ctx, head, ldh, a->dists, a->target, R, S, a->rgba,
+        LNB_TRY(lnb_launch_composite_fwd(ctx, head, ldh, dists, a->target, R, S, a->rgba,
                                          a->alpha, a->cumprod, a->weights, color, color_acc,
                                          ray_sse));
     } else if (a->target) {
@@ -364,7 +382,7 @@ int step_layerwise(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, boo
     const int n_bwd = nerf ? R * S : R; // rows that carry a non-zero adjoint
     int ldz = d.out_last;
     if (nerf) {
-        LNB_TRY(lnb_launch_composite_bwd(ctx, head, ldh, a->dists, a->target, color, R, S, dZa, ldz,
+        LNB_TRY(lnb_launch_composite_bwd(ctx, head, ldh, dists, a->target, color, R, S, dZa, ldz,
                                          d.out_last, a->d_dists ? d_dists_u : nullptr, d_color_u));
         if (a->d_dists)
             LNB_TRY(lnb_launch_axpy2d(ctx, a->d_dists, S, d_dists_u, S, R, S, 1.0f, seed_val, seed_dev));
@@ -379,7 +397,7 @@ int step_layerwise(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, boo
     float *dZ = dZa, *dZn = dZb;
     for (int l = L - 1; l >= 0; --l) {
         const int in_l = mlp->dims[l], out_l = mlp->dims[l + 1];
-        const float *H = l == 0 ? a->X : Y[l - 1];
+        const float *H = l == 0 ? X : Y[l - 1];
         const int ldhh = l == 0 ? d.c_in : ldy[l - 1];
         LNB_TRY(lnb_launch_dw_partials(ctx, H, ldhh, dZ, ldz, partial, in_l, out_l, n_bwd, n_chunks));
         LNB_TRY(lnb_launch_dw_reduce(ctx, partial, n_chunks, in_l, out_l,
@@ -480,10 +498,16 @@ int step_host(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, bool ner
 #define OUT_(field, n) if (a->field) reg(nullptr, a->field, (n), BUF_OUT, (void **)&dev.field)
 #define ACC_(field, n) if (a->field) reg(nullptr, a->field, (n), BUF_OUT_ACC, (void **)&dev.field)
     IN_(X, N * d.c_in);
+    if (!a->X && a->rays_o) {
+        const size_t w = a->ray_dtype == LNB_RAY_F64 ? 2 : 1; // floats per element
+        reg(a->rays_o, nullptr, R * 3 * w, BUF_IN, (void **)&dev.rays_o);
+        reg(a->rays_d, nullptr, R * 3 * w, BUF_IN, (void **)&dev.rays_d);
+        reg(a->t, nullptr, R * S * w, BUF_IN, (void **)&dev.t);
+    }
     IN_(ws, nW);
     IN_(bs, nB);
     IN_(target, R * d.Wt);
-    if (nerf) IN_(dists, R * S);
+    if (nerf && !(!a->X && a->rays_o)) IN_(dists, R * S);
     if (a->inter) reg(a->inter, a->inter, nInter, a->inter_accumulate ? BUF_INOUT : BUF_OUT, (void **)&dev.inter);
     if (nerf) {
         OUT_(rgba, R * S * 4);
@@ -587,7 +611,7 @@ extern "C" int lnb_sample_encode(lnb_ctx *ctx, const double *rays_o, const doubl
     if (!ctx) return LNB_ERR_ARG;
     LNB_ARG(rays_o && rays_d && t && X && R >= 0 && S >= 1 && E >= 0, "sample_encode arguments");
     if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
-    return lnb_launch_sample_encode(ctx, rays_o, rays_d, t, R, S, E, X, dists);
+    return lnb_launch_sample_encode(ctx, rays_o, rays_d, t, 1, R, S, E, X, dists);
 }
 
 extern "C" int lnb_mult_a_b(lnb_ctx *ctx, const float *a, int a_h, int a_w, const float *b, int b_w,

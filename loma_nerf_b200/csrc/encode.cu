@@ -29,8 +29,9 @@ __global__ void pos_encoding_kernel(const double *__restrict__ x, long long n, i
     }
 }
 
-__global__ void sample_encode_kernel(const double *__restrict__ o, const double *__restrict__ d,
-                                     const double *__restrict__ t, int R, int S, int E,
+template <typename T>
+__global__ void sample_encode_kernel(const T *__restrict__ o, const T *__restrict__ d,
+                                     const T *__restrict__ t, int R, int S, int E,
                                      float *__restrict__ X, float *__restrict__ dists)
 {
     long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -39,8 +40,8 @@ __global__ void sample_encode_kernel(const double *__restrict__ o, const double 
     int f = (int)(e % 3);
     int r = (int)(smp / S), s = (int)(smp % S);
     const int C = 3 * (1 + 2 * E);
-    double tt = t[smp];
-    double v = o[r * 3 + f] + d[r * 3 + f] * tt;
+    double tt = (double)t[smp];
+    double v = (double)o[r * 3 + f] + (double)d[r * 3 + f] * tt;
     float *x = X + smp * C;
     x[f] = (float)v;
     double freq = 1.0;
@@ -51,7 +52,7 @@ __global__ void sample_encode_kernel(const double *__restrict__ o, const double 
         x[(2 * i + 2) * 3 + f] = (float)cs;
         freq *= 2.0;
     }
-    if (f == 0 && dists) dists[smp] = (s + 1 < S) ? (float)(t[smp + 1] - tt) : (float)1e8;
+    if (f == 0 && dists) dists[smp] = (s + 1 < S) ? (float)((double)t[smp + 1] - tt) : (float)1e8;
 }
 
 } // namespace
@@ -65,13 +66,16 @@ int lnb_launch_pos_encoding(lnb_ctx *ctx, const double *x, long long n, int F, i
     return LNB_OK;
 }
 
-int lnb_launch_sample_encode(lnb_ctx *ctx, const double *o, const double *d, const double *t,
+int lnb_launch_sample_encode(lnb_ctx *ctx, const void *o, const void *d, const void *t, int f64,
                              int R, int S, int E, float *X, float *dists)
 {
     long long tot = (long long)R * S * 3;
     if (tot <= 0) return LNB_OK;
-    sample_encode_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(o, d, t, R, S, E,
-                                                                                X, dists);
+    const unsigned blocks = (unsigned)((tot + 255) / 256);
+    if (f64)
+        sample_encode_kernel<double><<<blocks, 256, 0, ctx->stream>>>((const double *)o, (const double *)d, (const double *)t, R, S, E, X, dists);
+    else
+        sample_encode_kernel<float><<<blocks, 256, 0, ctx->stream>>>((const float *)o, (const float *)d, (const float *)t, R, S, E, X, dists);
     LNB_CHECK_LAUNCH();
     return LNB_OK;
 }

@@ -28,6 +28,7 @@
 // for forward and B^T for backward, without any transposed copy.
 #include <cuda_bf16.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -45,6 +46,9 @@ struct TcParams {
     float *part;       // [grid][part_stride]
     float *dbg;        // optional [N][4] head outputs (debug)
     const void *wimg;  // weight image built by tc_prep_kernel (TcLayout::wimg_bytes)
+    // rays mode (X == NULL): features are computed in the kernel from rays and sample depths
+    const void *rays_o, *rays_d, *tvals; // [R][3], [R][3], [R][S]; float64 when ray_f64 else float32
+    int ray_f64, pe_bands;
     long long N;       // samples (rows of X)
     int R, S, G, rows_per_tile, n_tiles;
     int L, dims[MAXL + 1], max_in, max_out;
@@ -200,8 +204,12 @@ struct TcLayout {
     __host__ __device__ static int wimg_bytes(int L, int K0P) { return w_off(L, L, K0P) + MAXL * HP * 4; }
     __host__ __device__ static int stage_bytes(int c_in, int K0P) { return (TILE * c_in * 4 + 32 + K0P * 4 + 15) / 16 * 16; }
     static constexpr int SCRATCH_FLOATS = 48; // colour + target per ray, scan carries, loss
-    __host__ __device__ static size_t total(int L, int K0P, int c_in)
+    __host__ __device__ static size_t total(int L, int K0P, int c_in, bool rays = false)
     {
+        if (rays) {
+            const size_t t = (size_t)act_bytes(L, K0P) + wimg_bytes(L, K0P) + SCRATCH_FLOATS * 4 + 64 + MAX_STAGES * 48;
+            return t < 16 * SLAB ? 16 * SLAB : t;
+        }
         // the concatenated dW MMA reads 16 slabs (M = 128 features) from the start of shared
         // memory whatever the real feature count: keep that inside the allocation
         const size_t t = (size_t)act_bytes(L, K0P) + wimg_bytes(L, K0P) + stage_bytes(c_in, K0P) + SCRATCH_FLOATS * 4 + 64 + MAX_STAGES * 48;
@@ -232,7 +240,10 @@ __global__ void tc_prep_kernel(const TcParams p, uint8_t *__restrict__ img)
     }
 }
 
-template <int HP>
+// fp32 sin/cos of the positional encoding (pos_encoding.py:38-70): one accurate sincosf per
+// coordinate, higher bands by angle doubling (sin 2a = 2 s c, cos 2a = 1 - 2 s^2).  The doubling
+// amplifies the base error by 2^(E-1): ~1e-6 at E = 5, far below the bf16 operand rounding.
+template <bool RAYS, int HP>
 __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
 {
     using LY = TcLayout<HP>;
@@ -246,11 +257,12 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
     uint8_t *const Wbase = smem + act_bytes;
     const float *const bias_s = reinterpret_cast<const float *>(Wbase + LY::w_off(L, L, K0P));
     float *const stage = reinterpret_cast<float *>(Wbase + LY::wimg_bytes(L, K0P));
+    const int stage_sz = RAYS ? 0 : LY::stage_bytes(c_in, K0P);
     // per-ray colour / target scratch aliases dZ_0: it is dead from the top of a tile (the previous
     // tile's dW MMAs have been awaited) until the last backward epilogue writes it
     float *const color_s = reinterpret_cast<float *>(smem + LY::dz_off(0, L, K0P));
     float *const tgt_s = color_s + TILE * 3;
-    float *const tailp = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(stage) + LY::stage_bytes(c_in, K0P)); // [4] inclusive product at lane 31
+    float *const tailp = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(stage) + stage_sz); // [4] inclusive product at lane 31
     int *const tail_s = reinterpret_cast<int *>(tailp + 4);  // [4] sample index at lane 31
     float *const headq = tailp + 8;                          // [5] q at lane 0 of each warp
     float *const headA = tailp + 13;                         // [5]
@@ -314,10 +326,12 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
         const uint32_t wb = (uint32_t)LY::wimg_bytes(L, K0P);
         mbar_expect_tx(bar_w, wb);
         bulk_g2s(smem_u32(Wbase), p.wimg, wb, bar_w);
-        int lead; uint32_t bytes;
-        const void *src = x_src(blockIdx.x, lead, bytes);
-        mbar_expect_tx(bar_x, bytes);
-        bulk_g2s(smem_u32(stage), src, bytes, bar_x);
+        if (!RAYS) {
+            int lead; uint32_t bytes;
+            const void *src = x_src(blockIdx.x, lead, bytes);
+            mbar_expect_tx(bar_x, bytes);
+            bulk_g2s(smem_u32(stage), src, bytes, bar_x);
+        }
     }
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
@@ -375,16 +389,60 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
         // early, latency-tolerant loads for this tile (consumed after the MLP forward)
         float my_dist = 0.0f, tg0 = 0.0f, tg1 = 0.0f, tg2 = 0.0f;
         if (p.head == LNB_HEAD_NERF && live) {
-            my_dist = __ldg(p.dists + row0 + tid);
+            if (!RAYS) my_dist = __ldg(p.dists + row0 + tid);
             if (p.target && smp == 0) {
                 const float *tg = p.target + (row0 / S + ray_l) * 3;
                 tg0 = __ldg(tg); tg1 = __ldg(tg + 1); tg2 = __ldg(tg + 2);
             }
         }
-        // ---- features: wait for the TMA, convert this thread's row to bf16 slabs.  Columns beyond
-        // c_in read the following floats of `stage` (finite: next row / zeroed slack) and meet zero
-        // weights; column c_in is then patched to 1 (the bias-gradient feature).
-        {
+        if (RAYS) {
+            // ---- features from rays: pts = o + d t (train_nerf.py:289-299), PE (pos_encoding.py:38-70),
+            // dist = t[s+1] - t[s], last 1e8 (train_nerf.py:306-311); written straight into A_0
+            float x[3] = {0.f, 0.f, 0.f};
+            if (live) {
+                const long long ray = row0 / S + ray_l, smpl = row0 + tid;
+                if (p.ray_f64) {
+                    const double *o = reinterpret_cast<const double *>(p.rays_o) + ray * 3;
+                    const double *d = reinterpret_cast<const double *>(p.rays_d) + ray * 3;
+                    const double *tv = reinterpret_cast<const double *>(p.tvals) + smpl;
+                    const double tt = __ldg(tv);
+                    my_dist = smp + 1 < S ? (float)(__ldg(tv + 1) - tt) : 1e8f;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) x[c] = (float)(__ldg(o + c) + __ldg(d + c) * tt);
+                } else {
+                    const float *o = reinterpret_cast<const float *>(p.rays_o) + ray * 3;
+                    const float *d = reinterpret_cast<const float *>(p.rays_d) + ray * 3;
+                    const float *tv = reinterpret_cast<const float *>(p.tvals) + smpl;
+                    const float tt = __ldg(tv);
+                    my_dist = smp + 1 < S ? __ldg(tv + 1) - tt : 1e8f;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) x[c] = fmaf(__ldg(d + c), tt, __ldg(o + c));
+                }
+            }
+            if (dw_pending) { mbar_wait(bar_dw, dwphase); dwphase ^= 1; dw_pending = false; tc_fence_after(); }
+            CLK(12);
+            __nv_bfloat16 *a0 = reinterpret_cast<__nv_bfloat16 *>(a_buf(0));
+            auto put = [&](int f, float v) { a0[(f >> 3) * (TILE * 8) + tid * 8 + (f & 7)] = __float2bfloat16_rn(v); };
+            float sn[3], cs[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                put(c, x[c]);
+                sincosf(x[c], &sn[c], &cs[c]);
+            }
+            for (int i = 0; i < p.pe_bands; ++i) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    put((2 * i + 1) * 3 + c, sn[c]);
+                    put((2 * i + 2) * 3 + c, cs[c]);
+                    const float s2 = 2.0f * sn[c] * cs[c], c2 = fmaf(-2.0f * sn[c], sn[c], 1.0f);
+                    sn[c] = s2; cs[c] = c2;
+                }
+            }
+            put(c_in, 1.0f); // the bias-gradient feature
+        } else {
+            // ---- features: wait for the TMA, convert this thread's row to bf16 slabs.  Columns beyond
+            // c_in read the following floats of `stage` (finite: next row / zeroed slack) and meet zero
+            // weights; column c_in is then patched to 1 (the bias-gradient feature).
             int lead; uint32_t bytes;
             (void)x_src(tile, lead, bytes);
             mbar_wait(bar_x, xphase);
@@ -409,7 +467,7 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
         }
         publish_smem(); // also: every thread is done reading `stage`
         CLK(1);
-        if (tid == 0) {
+        if (!RAYS && tid == 0) {
             const int nt = tile + gridDim.x;
             if (nt < p.n_tiles) {
                 int lead; uint32_t bytes;
@@ -706,6 +764,9 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     const int R = a->R, S = nerf ? a->S : 1;
     const long long N = a->n_rows > 0 ? a->n_rows : (long long)R * S;
     if (nerf && (S > TILE || N != (long long)R * S)) return unsupported("needs S <= 128 and n_rows == R*S");
+    const bool rays = a->X == nullptr && a->rays_o != nullptr;
+    if (rays && (!nerf || !a->rays_d || !a->t || mlp->dims[0] != 3 + 6 * a->pe_bands))
+        return unsupported("rays mode needs rays_o, rays_d, t and dims[0] == 3 + 6 * pe_bands");
     if (!nerf && N != R) return unsupported("needs n_rows == R");
     if (a->rows > N) return unsupported("rows > n_rows");
     if (!nerf && (a->target_w > 4)) return unsupported("target wider than 4");
@@ -714,6 +775,7 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
 
     TcParams p{};
     p.X = a->X; p.dists = a->dists; p.target = a->target; p.ws = a->ws; p.bs = a->bs;
+    p.rays_o = a->rays_o; p.rays_d = a->rays_d; p.tvals = a->t; p.ray_f64 = a->ray_dtype == LNB_RAY_F64; p.pe_bands = a->pe_bands;
     p.color = nerf ? a->color : nullptr;
     p.N = N; p.R = R; p.S = S;
     p.G = nerf ? TILE / S : TILE;
@@ -729,15 +791,16 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     p.part_stride = off;
 
     const int c_in = mlp->dims[0];
-    size_t smem = (HP == 16 ? TcLayout<16>::total(L, K0P, c_in) : (HP == 32 ? TcLayout<32>::total(L, K0P, c_in) : TcLayout<64>::total(L, K0P, c_in)));
+    size_t smem = (HP == 16 ? TcLayout<16>::total(L, K0P, c_in, rays) : (HP == 32 ? TcLayout<32>::total(L, K0P, c_in, rays) : TcLayout<64>::total(L, K0P, c_in, rays)));
     const int tmem_cols = (int)(HP == 16 ? TcLayout<16>::tmem_cols(L) : (HP == 32 ? TcLayout<32>::tmem_cols(L) : TcLayout<64>::tmem_cols(L)));
     if (K0P / 8 + (L - 1) * (HP / 8) > 16) return unsupported("input + hidden widths exceed 128 features in total");
     if ((L - 1) * HP + 16 > 256) return unsupported("hidden widths exceed 256 gradient columns");
-    if ((reinterpret_cast<uintptr_t>(a->X) & 3) != 0) return unsupported("X must be 4-byte aligned");
+    if (!rays && (reinterpret_cast<uintptr_t>(a->X) & 3) != 0) return unsupported("X must be 4-byte aligned");
     int per_sm = 512 / tmem_cols;
     int by_smem = (int)((227 * 1024) / (smem + 1024));
     if (by_smem < per_sm) per_sm = by_smem;
     if (per_sm < 1) return unsupported("shared memory");
+    if (const char *e = getenv("LNB_TC_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
     int grid = ctx->sm_count * per_sm;
     if (grid > p.n_tiles) grid = p.n_tiles;
     if (grid < 1) grid = 1;
@@ -756,14 +819,19 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     if (N > 0) {
 #define LNB_TC(HPV)                                                                              \
     do {                                                                                         \
-        LNB_CUDA(cudaFuncSetAttribute(fused_tc_kernel<HPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        fused_tc_kernel<HPV><<<grid, TILE, smem, ctx->stream>>>(p);                              \
+        if (rays) {                                                                              \
+            LNB_CUDA(cudaFuncSetAttribute(fused_tc_kernel<true, HPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            fused_tc_kernel<true, HPV><<<grid, TILE, smem, ctx->stream>>>(p);                    \
+        } else {                                                                                 \
+            LNB_CUDA(cudaFuncSetAttribute(fused_tc_kernel<false, HPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            fused_tc_kernel<false, HPV><<<grid, TILE, smem, ctx->stream>>>(p);                   \
+        }                                                                                        \
     } while (0)
         if (HP == 16) tc_prep_kernel<16><<<1, 256, 0, ctx->stream>>>(p, wimg);
         else if (HP == 32) tc_prep_kernel<32><<<1, 256, 0, ctx->stream>>>(p, wimg);
         else tc_prep_kernel<64><<<1, 256, 0, ctx->stream>>>(p, wimg);
         LNB_CHECK_LAUNCH();
-        lnb_prof_begin(ctx, "fused_tc_kernel");
+        lnb_prof_begin(ctx, rays ? "fused_tc_kernel<rays>" : "fused_tc_kernel<features>");
         if (HP == 16) LNB_TC(16);
         else if (HP == 32) LNB_TC(32);
         else LNB_TC(64);

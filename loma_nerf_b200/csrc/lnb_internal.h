@@ -141,7 +141,7 @@ int lnb_launch_axpy2d(lnb_ctx *ctx, float *dst, long long ldd, const float *src,
 
 // ---- encode.cu / optim.cu ---------------------------------------------------------------------
 int lnb_launch_pos_encoding(lnb_ctx *ctx, const double *x, long long n, int F, int E, float *out);
-int lnb_launch_sample_encode(lnb_ctx *ctx, const double *o, const double *d, const double *t,
+int lnb_launch_sample_encode(lnb_ctx *ctx, const void *o, const void *d, const void *t, int f64,
                              int R, int S, int E, float *X, float *dists);
 int lnb_launch_adam(lnb_ctx *ctx, float *p, const float *g, float *m, float *v, long long n, int t,
                     double lr, double b1, double b2, double eps);

@@ -9,15 +9,18 @@ R, S = 4096, 64
 cases = []
 for i in range(6):
     c = O.make_nerf_case(100 + i, R, S)
-    cases.append({k: torch.as_tensor(np.ascontiguousarray(c[k], np.float32)).cuda() for k in ("X", "dists", "target")})
+    cases.append({k: torch.as_tensor(np.ascontiguousarray(c[k], np.float32)).cuda() for k in ("X", "dists", "target", "rays_o", "rays_d", "t")})
 c0 = O.make_nerf_case(1, 4, 64)
 dims = [int(v) for v in c0["dims"]]
 ws = torch.as_tensor(c0["ws"]).cuda(); bs = torch.as_tensor(c0["bs"]).cuda()
 out = dict(d_ws=torch.zeros_like(ws), d_bs=torch.zeros_like(bs), loss=torch.zeros(1, device=dev))
 def call(i, path):
     b = cases[i % 6]
+    if path == "tc_rays":
+        ctx.nerf_step_rays(dims, b["rays_o"], b["rays_d"], b["t"], 5, ws, bs, b["target"], grad=True, seed=1.0, outputs=("loss",), out=out, path="tc")
+        return
     ctx.nerf_step(dims, b["X"], ws, bs, b["dists"], b["target"], R=R, S=S, grad=True, seed=1.0, outputs=("loss",), out=out, path=path)
-for path in ("tc", "f32"):
+for path in ("tc", "tc_rays"):
     for i in range(5): call(i, path)
     torch.cuda.synchronize()
     for rep in range(2):

@@ -43,10 +43,11 @@ def test_struct_mirror_matches_c_layout(lib):
     n = lib.lnb_struct_layout(out, 16)
     A = L.LnbStepArgs
     mine = [ctypes.sizeof(L.LnbMlp), ctypes.sizeof(A), A.X.offset, A.inter.offset, A.rgba.offset,
-            A.loss.offset, A.want_grad.offset, A.d_ws.offset, A.path.offset]
+            A.loss.offset, A.want_grad.offset, A.d_ws.offset, A.path.offset, A.rays_o.offset,
+            A.pe_bands.offset]
     assert n == len(mine)
     assert list(out[:n]) == mine
-    assert lib.lnb_abi_version() == 1
+    assert lib.lnb_abi_version() == 2
 
 
 def test_compile_shim_binds_reference_argtypes(lib):

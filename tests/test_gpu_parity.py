@@ -316,6 +316,31 @@ def test_linearity_additivity_and_accumulation(ctx, torch_cuda, path):
     assert rel_err(host(bufs["d_ws"]), 2 * a["d_ws"]) <= 1e-6
 
 
+@pytest.mark.parametrize("device", [True, False])
+@pytest.mark.parametrize("gpath", [p for p in NERF_GOLDEN if "c5" not in p], ids=os.path.basename)
+def test_rays_mode_exact_path_matches_reference_golden(ctx, torch_cuda, gpath, device):
+    """Rays in (float64, as get_rays / linspace make them): the device builds pts, the positional
+    encoding and dists in float64 (encode.cu) and then runs the exact fp32 kernels."""
+    torch = torch_cuda
+    gd = load_golden(gpath)
+    R, S, E = int(gd["R"]), int(gd["S"]), int(gd["E"])
+    if device:
+        cv = lambda a, dt=torch.float32: dev(torch, a, dt)  # noqa: E731
+        rays = [cv(gd[k], torch.float64) for k in ("rays_o", "rays_d", "t")]
+    else:
+        cv = lambda a, dt=None: np.ascontiguousarray(a, np.float32)  # noqa: E731
+        rays = [np.ascontiguousarray(gd[k], np.float64) for k in ("rays_o", "rays_d", "t")]
+    out = ctx.nerf_step_rays([int(v) for v in gd["dims"]], rays[0], rays[1], rays[2], E, cv(gd["ws"]), cv(gd["bs"]),
+                             cv(gd["target"]), grad=True, seed="loss",
+                             outputs=("color", "loss", "d_ws", "d_bs", "d_dists", "d_target"), path="f32")
+    if device:
+        ctx.synchronize()
+    o = {k: host(v) for k, v in out.items()}
+    assert rel_err(o["loss"][0], gd["loss"]) <= TOL
+    for k in ["color", "d_ws", "d_bs", "d_dists", "d_target"]:
+        assert rel_err(o[k], gd[k]) <= TOL, k
+
+
 def test_render_only_and_edge_shapes(ctx, torch_cuda):
     torch = torch_cuda
     case = O.make_nerf_case(55, 64, 64)

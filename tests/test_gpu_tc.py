@@ -101,3 +101,26 @@ def test_tc_render_only_and_unsupported_requests(ctx, torch_cuda):
     with pytest.raises(api.LnbError):
         ctx.nerf_step(dims, dev(torch, case["X"]), dev(torch, case["ws"]), dev(torch, case["bs"]),
                       dev(torch, case["dists"]), dev(torch, case["target"]), grad=True, outputs=("d_X",), path="tc")
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("R,S,E", [(4096, 64, 5), (333, 30, 5), (200, 128, 5), (64, 64, 10), (100, 7, 2)])
+def test_tc_rays_mode_fused_positional_encoding(ctx, torch_cuda, R, S, E, dtype):
+    """Rays mode: sample positions, positional encoding and dists computed inside the fused kernel
+    (train_nerf.py:289-311 + pos_encoding.py:38-70), checked against the float64 restatement fed
+    with the host-built features."""
+    torch = torch_cuda
+    width = 30
+    case = O.make_nerf_case(700 + S + E, R, S, E=E, width=width)
+    tdt = getattr(torch, dtype)
+    cvr = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(tdt).cuda().contiguous()  # noqa: E731
+    out = ctx.nerf_step_rays([int(v) for v in case["dims"]], cvr(case["rays_o"]), cvr(case["rays_d"]), cvr(case["t"]), E,
+                             dev(torch, case["ws"]), dev(torch, case["bs"]), dev(torch, case["target"]), grad=True,
+                             seed=1.0, outputs=("color", "loss"), path="tc")
+    ctx.synchronize()
+    o = {k: host(v) for k, v in out.items()}
+    f = O.nerf_f64(case["X"], case["ws"], case["bs"], case["dims"], case["target"], case["dists"], R, S, g=1.0)
+    errs = dict(loss=rel_err(o["loss"][0], f["loss"]), color=rel_err(o["color"], f["color"]),
+                d_ws=rel_err(o["d_ws"], f["d_ws"]), d_bs=rel_err(o["d_bs"], f["d_bs"]))
+    log("rays %s R=%d S=%d E=%d %s" % (dtype, R, S, E, errs))
+    assert max(errs.values()) <= TC_TOL, errs
