@@ -231,6 +231,29 @@ LNB_API int lnb_adam_step_dev(lnb_ctx *ctx, float *param, const float *grad, flo
                       int *t_dev, double lr, double beta1, double beta2, double eps);
 LNB_API int lnb_sgd_step(lnb_ctx *ctx, float *param, const float *grad, long long n, double lr);
 
+/* ------------------------------------------------------------------------------------------
+ * Device-resident training state (the hosts' per-chunk "grad call, then optimiser on the padded
+ * arrays" loop, train_nerf.py:395-499 / fit_img.py:468-513, without leaving the GPU).
+ * A batch is an lnb_step_args with DEVICE pointers; its ws, bs, d_*, loss and by-product fields are
+ * ignored (the trainer supplies them).  lnb_trainer_step = gradient + optimiser update (two kernel
+ * launches on the tensor-core path).  For data-parallel training split it:
+ * lnb_trainer_grad -> all-reduce lnb_trainer_grad_buffer ([d_ws | d_bs | loss], written, not
+ * accumulated) over the ranks -> lnb_trainer_apply.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct lnb_trainer lnb_trainer;
+enum { LNB_OPT_ADAM = 0,  /* AdamOptimizer.update, train_nerf.py:133-161 (double bias correction) */
+       LNB_OPT_SGD = 1 }; /* p -= lr * g, fit_img.py:512-513                                      */
+LNB_API int lnb_trainer_create(lnb_ctx *ctx, const lnb_mlp *mlp, const float *ws_host, const float *bs_host,
+                       int optimizer, double lr, double beta1, double beta2, double eps, lnb_trainer **out);
+LNB_API void lnb_trainer_destroy(lnb_trainer *t);
+LNB_API int lnb_trainer_step(lnb_trainer *t, const lnb_step_args *batch, int nerf);
+LNB_API int lnb_trainer_grad(lnb_trainer *t, const lnb_step_args *batch, int nerf);
+LNB_API int lnb_trainer_apply(lnb_trainer *t);
+LNB_API float *lnb_trainer_grad_buffer(lnb_trainer *t, long long *n_floats);
+LNB_API float *lnb_trainer_params(lnb_trainer *t, long long *n_w, long long *n_b);
+/* synchronises; any pointer may be NULL */
+LNB_API int lnb_trainer_read(lnb_trainer *t, float *ws_host, float *bs_host, float *loss_host);
+
 /* Process-wide default context used by the compat symbols (created lazily on first call,
  * device from LOMA_NERF_B200_DEVICE or 0). Returns NULL when no CUDA device is usable. */
 LNB_API lnb_ctx *lnb_default_ctx(void);

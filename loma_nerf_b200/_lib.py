@@ -16,6 +16,7 @@ HEAD_NERF, HEAD_SIGMOID = 0, 1
 SEED_VALUE, SEED_LOSS = 0, 1
 PATH_F32, PATH_TC, PATH_F32_LAYERWISE = 0, 1, 2
 RAY_F64, RAY_F32 = 0, 1
+OPT_ADAM, OPT_SGD = 0, 1
 
 c_float_p = POINTER(c_float)
 
@@ -95,6 +96,18 @@ def load():
     lib.lnb_adam_step_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
                                       c_void_p, c_double, c_double, c_double, c_double]
     lib.lnb_sgd_step.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_double]
+    lib.lnb_trainer_create.argtypes = [c_void_p, P(LnbMlp), c_void_p, c_void_p, c_int, c_double, c_double,
+                                       c_double, c_double, P(c_void_p)]
+    lib.lnb_trainer_destroy.argtypes = [c_void_p]
+    lib.lnb_trainer_destroy.restype = None
+    for name in ("lnb_trainer_step", "lnb_trainer_grad"):
+        getattr(lib, name).argtypes = [c_void_p, P(LnbStepArgs), c_int]
+    lib.lnb_trainer_apply.argtypes = [c_void_p]
+    lib.lnb_trainer_grad_buffer.argtypes = [c_void_p, P(c_longlong)]
+    lib.lnb_trainer_grad_buffer.restype = c_void_p
+    lib.lnb_trainer_params.argtypes = [c_void_p, P(c_longlong), P(c_longlong)]
+    lib.lnb_trainer_params.restype = c_void_p
+    lib.lnb_trainer_read.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
     lib.lnb_default_ctx.restype = c_void_p
     lib.lnb_struct_layout.argtypes = [P(c_int), c_int]
     lib.lnb_struct_layout.restype = c_int

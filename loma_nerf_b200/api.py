@@ -244,3 +244,90 @@ class Context:
     def sgd_step(self, param, grad, lr):
         """ws -= lr * d_ws (fit_img.py:512-513), in place."""
         self._check(self.lib.lnb_sgd_step(self.h, param.data_ptr(), grad.data_ptr(), param.numel(), lr))
+
+
+class Trainer:
+    """Device-resident weights + optimiser state (lnb_trainer): the reference hosts' per-chunk
+    "grad call, then Adam / SGD on the padded arrays" loop (train_nerf.py:395-499,
+    fit_img.py:468-513) without host round trips.  Batches are torch CUDA tensors."""
+
+    def __init__(self, ctx, dims, ws, bs, head=L.HEAD_NERF, optimizer="adam", lr=5e-4, beta1=0.9, beta2=0.999,
+                 eps=1e-8):
+        self.ctx, self.lib = ctx, ctx.lib
+        ws = np.ascontiguousarray(ws, np.float32)
+        bs = np.ascontiguousarray(bs, np.float32)
+        self.dims, self.ws_shape, self.bs_shape = [int(d) for d in dims], ws.shape, bs.shape
+        self.mlp = make_mlp(dims, ws.shape, head)
+        self.head = head
+        h = ctypes.c_void_p()
+        opt = {"adam": L.OPT_ADAM, "sgd": L.OPT_SGD}[optimizer]
+        ctx._check(self.lib.lnb_trainer_create(ctx.h, ctypes.byref(self.mlp), ws.ctypes.data, bs.ctypes.data, opt,
+                                               lr, beta1, beta2, eps, ctypes.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lnb_trainer_destroy(self.h)
+            self.h = None
+
+    def _batch(self, X=None, dists=None, target=None, rays=None, pe_bands=0, R=None, S=None, path="tc", seed=1.0):
+        a = L.LnbStepArgs()
+        nerf = self.head == L.HEAD_NERF
+        if rays is not None:
+            ro, rd, tv = rays
+            R, S = int(tv.shape[0]), int(tv.shape[1])
+            a.rays_o, a.rays_d, a.t = _ptr(ro), _ptr(rd), _ptr(tv)
+            a.ray_dtype = L.RAY_F64 if str(ro.dtype).endswith("float64") else L.RAY_F32
+            a.pe_bands = int(pe_bands)
+        else:
+            a.X = _ptr(X)
+            if nerf:
+                R = int(dists.shape[0]) if R is None else R
+                S = int(dists.shape[1]) if S is None else S
+                a.dists = _ptr(dists)
+            else:
+                R, S = int(target.shape[0]), 1
+        a.R, a.S, a.target_w = R, S, int(target.shape[1])
+        a.n_rows = R * S
+        a.target = _ptr(target)
+        a.path = PATHS[path]
+        if isinstance(seed, str):
+            a.seed_mode, a.seed = L.SEED_LOSS, 1.0
+        else:
+            a.seed_mode, a.seed = L.SEED_VALUE, float(seed)
+        return a, int(nerf)
+
+    def step(self, **batch):
+        """forward + backward + optimiser update on one batch."""
+        a, nerf = self._batch(**batch)
+        self.ctx._check(self.lib.lnb_trainer_step(self.h, ctypes.byref(a), nerf))
+
+    def grad(self, **batch):
+        """forward + backward only: gradients (and loss) land in grad_buffer()."""
+        a, nerf = self._batch(**batch)
+        self.ctx._check(self.lib.lnb_trainer_grad(self.h, ctypes.byref(a), nerf))
+
+    def apply(self):
+        self.ctx._check(self.lib.lnb_trainer_apply(self.h))
+
+    def grad_buffer(self):
+        """torch view of the flat [d_ws | d_bs | loss] device buffer (for dist.all_reduce)."""
+        n = ctypes.c_longlong()
+        ptr = self.lib.lnb_trainer_grad_buffer(self.h, ctypes.byref(n))
+        return _torch_view(ptr, n.value, self.ctx.device)
+
+    def read(self):
+        """(ws, bs, loss) as numpy; synchronises."""
+        ws = np.empty(self.ws_shape, np.float32)
+        bs = np.empty(self.bs_shape, np.float32)
+        loss = np.empty(1, np.float32)
+        self.ctx._check(self.lib.lnb_trainer_read(self.h, ws.ctypes.data, bs.ctypes.data, loss.ctypes.data))
+        return ws, bs, float(loss[0])
+
+
+def _torch_view(ptr, n_floats, device):
+    """float32 torch tensor aliasing n_floats of device memory at ptr (no copy, no ownership)."""
+    class _Arr:
+        __cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (int(ptr), False), "version": 3,
+                                    "strides": None}
+    return torch.as_tensor(_Arr(), device=torch.device("cuda", device))

@@ -426,10 +426,8 @@ int step_layerwise(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, boo
 
 } // namespace
 
-// fused tensor-core step (fused_tc.cu); LNB_ERR_UNSUPPORTED when the problem does not fit it
-int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, bool nerf);
 
-static int step_dispatch(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, bool nerf)
+static int step_dispatch(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, bool nerf, const lnb_tc_extra *ex = nullptr)
 {
     if (!ctx) return LNB_ERR_ARG;
     LNB_ARG(a, "null args");
@@ -437,10 +435,15 @@ static int step_dispatch(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *
     if (a->path == LNB_PATH_TC) {
         StepDims d;
         LNB_TRY(validate(ctx, mlp, a, nerf, &d));
-        return lnb_fused_tc_step(ctx, mlp, a, nerf); // never silently changes arithmetic
+        return lnb_fused_tc_step(ctx, mlp, a, nerf, ex); // never silently changes arithmetic
     }
     LNB_ARG(false, "unknown path");
     return LNB_ERR_ARG;
+}
+
+int lnb_step_ex(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, bool nerf, const lnb_tc_extra *ex)
+{
+    return step_dispatch(ctx, mlp, a, nerf, ex);
 }
 
 extern "C" int lnb_nerf_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *args)

@@ -49,6 +49,7 @@ struct TcParams {
     // rays mode (X == NULL): features are computed in the kernel from rays and sample depths
     const void *rays_o, *rays_d, *tvals; // [R][3], [R][3], [R][S]; float64 when ray_f64 else float32
     int ray_f64, pe_bands;
+    int *t_dev;        // optimiser step counter, incremented once per launch (or NULL)
     long long N;       // samples (rows of X)
     int R, S, G, rows_per_tile, n_tiles;
     int L, dims[MAXL + 1], max_in, max_out;
@@ -668,6 +669,7 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
     if (lane == 0) red_s[warp] = loss_acc;
     __syncthreads();
     if (tid == 0) part[0] = red_s[0] + red_s[1] + red_s[2] + red_s[3];
+    if (tid == 0 && blockIdx.x == 0 && p.t_dev) p.t_dev[0] += 1; // read by the kernels that follow in the stream
     if (p.want_grad) {
         // accumulator row (TMEM lane) = feature index over the concatenated A buffers; thread tid
         // owns row tid: find the layer whose feature range contains it
@@ -702,10 +704,54 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
 #endif
 }
 
-// reduce the per-CTA partials in a fixed order; apply the seed; accumulate into the caller's buffers
+// image offset (bytes) of weight (l, k, j) / the fp32 bias region, mirroring tc_prep_kernel
+struct ImgMap {
+    int L, HP, K0P;
+    __device__ int np(int l) const { return l < L - 1 ? HP : 16; }
+    __device__ int kp(int l) const { return l == 0 ? K0P : HP; }
+    __device__ int w_off(int l) const { int o = 0; for (int i = 0; i < l; ++i) o += np(i) * kp(i) * 2; return o; }
+    __device__ void put_w(uint8_t *img, int l, int k, int j, float v) const
+    {
+        reinterpret_cast<__nv_bfloat16 *>(img + w_off(l))[(k >> 3) * (np(l) * 8) + j * 8 + (k & 7)] = __float2bfloat16_rn(v);
+    }
+    __device__ void put_b(uint8_t *img, int l, int j, float v) const { reinterpret_cast<float *>(img + w_off(L))[l * HP + j] = v; }
+};
+
+struct AdamArgs {
+    float *param, *m, *v;
+    const int *t_dev;
+    double lr, b1, b2, eps;
+    uint8_t *wimg;
+    long long n_w; // floats in the padded ws block (biases follow)
+    int sgd;       // 1: param -= lr * g (fit_img.py:512-513) instead of Adam
+};
+
+// the reference's AdamOptimizer.update (train_nerf.py:133-161, double bias correction kept) on
+// one parameter; python-float scalars meet float32 arrays exactly as in optim.cu
+__device__ __forceinline__ float adam_one(const AdamArgs &a, long long i, float g)
+{
+    if (a.sgd) {
+        const float pn = a.param[i] - (float)a.lr * g;
+        a.param[i] = pn;
+        return pn;
+    }
+    const int t = a.t_dev[0];
+    const double c1 = 1.0 - pow(a.b1, (double)t), c2 = 1.0 - pow(a.b2, (double)t);
+    const float lr_t = (float)(a.lr * (sqrt(c2) / c1));
+    const float mi = (float)a.b1 * a.m[i] + (float)(1.0 - a.b1) * g;
+    const float vi = (float)a.b2 * a.v[i] + (float)(1.0 - a.b2) * (g * g);
+    a.m[i] = mi;
+    a.v[i] = vi;
+    const float pnew = a.param[i] - lr_t * (mi / (float)c1) / (sqrtf(vi / (float)c2) + (float)a.eps);
+    a.param[i] = pnew;
+    return pnew;
+}
+
+// reduce the per-CTA partials in a fixed order; apply the seed; accumulate into (or overwrite) the
+// caller's buffers; optionally apply Adam to the parameter and refresh the bf16 weight image
 __global__ void tc_reduce_kernel(const float *__restrict__ part, int n_part, int part_stride, TcParams p,
                                  float *__restrict__ d_ws, float *__restrict__ d_bs, float *__restrict__ loss,
-                                 float seed_value, int seed_is_loss)
+                                 float seed_value, int seed_is_loss, int overwrite, int fuse_adam, AdamArgs ad, ImgMap im)
 {
     __shared__ float sloss;
     // every block sums the loss partials itself (same order everywhere) so the seed needs no second pass
@@ -734,15 +780,102 @@ __global__ void tc_reduce_kernel(const float *__restrict__ part, int n_part, int
         while (l + 1 < p.L && e >= p.part_off[l + 1]) ++l;
         e -= p.part_off[l];
         const int out_l = p.dims[l + 1], k = e / out_l, j = e % out_l;
-        if (k < p.dims[l]) d_ws[((size_t)l * p.max_in + k) * p.max_out + j] += scale * s;
-        else d_bs[(size_t)l * p.max_out + j] += scale * s;
+        const bool is_w = k < p.dims[l];
+        float *dst = is_w ? d_ws + ((size_t)l * p.max_in + k) * p.max_out + j : d_bs + (size_t)l * p.max_out + j;
+        const float g = overwrite ? scale * s : *dst + scale * s;
+        *dst = g;
+        if (fuse_adam) {
+            const long long pi = is_w ? ((long long)l * p.max_in + k) * p.max_out + j : ad.n_w + (long long)l * p.max_out + j;
+            const float pn = adam_one(ad, pi, g);
+            if (ad.wimg) { if (is_w) im.put_w(ad.wimg, l, k, j, pn); else im.put_b(ad.wimg, l, j, pn); }
+        }
     }
+}
+
+// stand-alone Adam + image refresh over the live (non-padding) parameters, one thread each
+__global__ void tc_adam_img_kernel(TcParams p, const float *__restrict__ grad, AdamArgs ad, ImgMap im, int n_el)
+{
+    const int e0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e0 >= n_el) return;
+    int e = e0 + 1, l = 0;
+    while (l + 1 < p.L && e >= p.part_off[l + 1]) ++l;
+    e -= p.part_off[l];
+    const int out_l = p.dims[l + 1], k = e / out_l, j = e % out_l;
+    const bool is_w = k < p.dims[l];
+    const long long pi = is_w ? ((long long)l * p.max_in + k) * p.max_out + j : ad.n_w + (long long)l * p.max_out + j;
+    const float pn = adam_one(ad, pi, grad[pi]);
+    if (ad.wimg) { if (is_w) im.put_w(ad.wimg, l, k, j, pn); else im.put_b(ad.wimg, l, j, pn); }
+}
+
+int tc_pick(const lnb_mlp *mlp, int *HP, int *K0P)
+{
+    const int L = mlp->n_layers;
+    if (L < 2 || L > MAXL) return 0;
+    int hw = 0;
+    for (int l = 1; l < L; ++l) hw = mlp->dims[l] > hw ? mlp->dims[l] : hw;
+    *HP = hw + 1 <= 16 ? 16 : (hw + 1 <= 32 ? 32 : (hw + 1 <= 64 ? 64 : 0));
+    *K0P = (mlp->dims[0] + 1 + 15) / 16 * 16;
+    if (!*HP || *K0P > 64 || mlp->dims[L] > 16) return 0;
+    if (*K0P / 8 + (L - 1) * (*HP / 8) > 16 || (L - 1) * *HP + 16 > 256) return 0;
+    return 1;
+}
+
+void fill_layout(TcParams &p, const lnb_mlp *mlp, int K0P)
+{
+    const int L = mlp->n_layers;
+    p.L = L;
+    for (int l = 0; l <= L; ++l) p.dims[l] = mlp->dims[l];
+    p.max_in = mlp->max_in; p.max_out = mlp->max_out;
+    p.K0P = K0P;
+    int off = 1;
+    for (int l = 0; l < L; ++l) { p.part_off[l] = off; off += (mlp->dims[l] + 1) * mlp->dims[l + 1]; }
+    p.part_stride = off;
 }
 
 } // namespace
 
 // Returns LNB_ERR_UNSUPPORTED when the problem does not fit the fused tensor-core kernel.
-int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, bool nerf)
+int lnb_tc_layout(const lnb_mlp *mlp, int *HP, int *K0P, int *wimg_bytes)
+{
+    int hp = 0, k0p = 0;
+    if (!tc_pick(mlp, &hp, &k0p)) return 0;
+    const int L = mlp->n_layers;
+    if (HP) *HP = hp;
+    if (K0P) *K0P = k0p;
+    if (wimg_bytes) *wimg_bytes = hp == 16 ? TcLayout<16>::wimg_bytes(L, k0p) : (hp == 32 ? TcLayout<32>::wimg_bytes(L, k0p) : TcLayout<64>::wimg_bytes(L, k0p));
+    return 1;
+}
+
+int lnb_tc_prep(lnb_ctx *ctx, const lnb_mlp *mlp, const float *ws, const float *bs, void *wimg)
+{
+    int HP = 0, K0P = 0;
+    if (!tc_pick(mlp, &HP, &K0P)) { ctx->err = "fused tensor-core path: MLP shape not supported"; return LNB_ERR_UNSUPPORTED; }
+    TcParams p{};
+    fill_layout(p, mlp, K0P);
+    p.ws = ws; p.bs = bs;
+    if (HP == 16) tc_prep_kernel<16><<<1, 256, 0, ctx->stream>>>(p, (uint8_t *)wimg);
+    else if (HP == 32) tc_prep_kernel<32><<<1, 256, 0, ctx->stream>>>(p, (uint8_t *)wimg);
+    else tc_prep_kernel<64><<<1, 256, 0, ctx->stream>>>(p, (uint8_t *)wimg);
+    LNB_CHECK_LAUNCH();
+    return LNB_OK;
+}
+
+int lnb_tc_adam_img(lnb_ctx *ctx, const lnb_mlp *mlp, float *param, const float *grad, float *m, float *v,
+                    const int *t_dev, double lr, double b1, double b2, double eps, void *wimg)
+{
+    int HP = 0, K0P = 0;
+    if (!tc_pick(mlp, &HP, &K0P)) { ctx->err = "fused tensor-core path: MLP shape not supported"; return LNB_ERR_UNSUPPORTED; }
+    TcParams p{};
+    fill_layout(p, mlp, K0P);
+    AdamArgs ad{param, m, v, t_dev, lr, b1, b2, eps, (uint8_t *)wimg, (long long)mlp->n_layers * mlp->max_in * mlp->max_out, m == nullptr};
+    ImgMap im{mlp->n_layers, HP, K0P};
+    const int n_el = p.part_stride - 1;
+    tc_adam_img_kernel<<<(n_el + 255) / 256, 256, 0, ctx->stream>>>(p, grad, ad, im, n_el);
+    LNB_CHECK_LAUNCH();
+    return LNB_OK;
+}
+
+int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, bool nerf, const lnb_tc_extra *ex)
 {
     const int L = mlp->n_layers;
     auto unsupported = [&](const char *why) {
@@ -808,7 +941,8 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     LNB_TRY(lnb_arena_reserve(ctx, (size_t)grid * p.part_stride * sizeof(float) + wimg_bytes + 8192));
     p.part = (float *)lnb_arena_take(ctx, (size_t)grid * p.part_stride * sizeof(float));
     uint8_t *wimg = (uint8_t *)lnb_arena_take(ctx, wimg_bytes);
-    p.wimg = wimg;
+    p.wimg = (ex && ex->wimg) ? ex->wimg : wimg;
+    p.t_dev = ex ? ex->t_dev : nullptr;
     float *loss = a->loss ? a->loss : (float *)lnb_arena_take(ctx, 16);
 #ifdef LNB_TC_CLK
     float *dbg_dev = nullptr;
@@ -827,10 +961,12 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
             fused_tc_kernel<false, HPV><<<grid, TILE, smem, ctx->stream>>>(p);                   \
         }                                                                                        \
     } while (0)
-        if (HP == 16) tc_prep_kernel<16><<<1, 256, 0, ctx->stream>>>(p, wimg);
-        else if (HP == 32) tc_prep_kernel<32><<<1, 256, 0, ctx->stream>>>(p, wimg);
-        else tc_prep_kernel<64><<<1, 256, 0, ctx->stream>>>(p, wimg);
-        LNB_CHECK_LAUNCH();
+        if (!(ex && ex->wimg)) {
+            if (HP == 16) tc_prep_kernel<16><<<1, 256, 0, ctx->stream>>>(p, wimg);
+            else if (HP == 32) tc_prep_kernel<32><<<1, 256, 0, ctx->stream>>>(p, wimg);
+            else tc_prep_kernel<64><<<1, 256, 0, ctx->stream>>>(p, wimg);
+            LNB_CHECK_LAUNCH();
+        }
         lnb_prof_begin(ctx, rays ? "fused_tc_kernel<rays>" : "fused_tc_kernel<features>");
         if (HP == 16) LNB_TC(16);
         else if (HP == 32) LNB_TC(32);
@@ -863,8 +999,14 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     const int seed_is_loss = a->seed_mode == LNB_SEED_LOSS;
     const float seed_val = seed_is_loss ? 1.0f : a->seed;
     int blocks = a->want_grad ? (n_el * 32 + 255) / 256 : 1;
+    AdamArgs ad{};
+    ImgMap im{L, HP, K0P};
+    const int fuse = ex && ex->fuse_adam && a->want_grad;
+    if (fuse) ad = AdamArgs{ex->param, ex->m, ex->v, ex->t_dev, ex->lr, ex->b1, ex->b2, ex->eps, (uint8_t *)ex->wimg_out,
+                            (long long)L * mlp->max_in * mlp->max_out, ex->m == nullptr};
     tc_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(p.part, grid, p.part_stride, p, a->want_grad ? a->d_ws : nullptr,
-                                                      a->want_grad ? a->d_bs : nullptr, loss, seed_val, seed_is_loss);
+                                                      a->want_grad ? a->d_bs : nullptr, loss, seed_val, seed_is_loss,
+                                                      ex ? ex->overwrite_grads : 0, fuse, ad, im);
     LNB_CHECK_LAUNCH();
     return LNB_OK;
 }

@@ -139,6 +139,34 @@ int lnb_launch_axpy2d(lnb_ctx *ctx, float *dst, long long ldd, const float *src,
                       long long rows, int cols, float sign, float seed_value,
                       const float *seed_dev);
 
+// ---- fused_tc.cu ---------------------------------------------------------------------------
+// Optional extras of the fused tensor-core step, used by the trainer (trainer.cu):
+//   wimg            : a valid weight image (skips the per-step prep kernel)
+//   overwrite_grads : d_ws / d_bs are written (=) instead of accumulated (+=)
+//   fuse_adam       : the reduce kernel applies the reference's Adam update to (param, m, v) with
+//                     the device step counter and refreshes `wimg_out` (the next step's image)
+struct lnb_tc_extra {
+    const void *wimg = nullptr;
+    int overwrite_grads = 0;
+    int fuse_adam = 0;
+    float *param = nullptr, *m = nullptr, *v = nullptr; // flat [ws | bs] padded layout
+    int *t_dev = nullptr;                               // incremented by the fused kernel
+    double lr = 0, b1 = 0, b2 = 0, eps = 0;
+    void *wimg_out = nullptr;
+};
+int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, bool nerf,
+                      const lnb_tc_extra *ex);
+// validated dispatch of one step with tensor-core extras (api_flat.cu)
+int lnb_step_ex(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, bool nerf, const lnb_tc_extra *ex);
+// padded widths of the fused kernel for this MLP, 0 when unsupported; bytes of its weight image
+int lnb_tc_layout(const lnb_mlp *mlp, int *HP, int *K0P, int *wimg_bytes);
+// build the weight image from fp32 padded weights (one small kernel)
+int lnb_tc_prep(lnb_ctx *ctx, const lnb_mlp *mlp, const float *ws, const float *bs, void *wimg);
+// Adam on the flat padded params with a device step counter (*t_dev already incremented), then
+// refresh of the weight image (when wimg != NULL)
+int lnb_tc_adam_img(lnb_ctx *ctx, const lnb_mlp *mlp, float *param, const float *grad, float *m, float *v,
+                    const int *t_dev, double lr, double b1, double b2, double eps, void *wimg);
+
 // ---- encode.cu / optim.cu ---------------------------------------------------------------------
 int lnb_launch_pos_encoding(lnb_ctx *ctx, const double *x, long long n, int F, int E, float *out);
 int lnb_launch_sample_encode(lnb_ctx *ctx, const void *o, const void *d, const void *t, int f64,
@@ -147,4 +175,7 @@ int lnb_launch_adam(lnb_ctx *ctx, float *p, const float *g, float *m, float *v, 
                     double lr, double b1, double b2, double eps);
 int lnb_launch_adam_dev(lnb_ctx *ctx, float *p, const float *g, float *m, float *v, long long n,
                         int *t_dev, double lr, double b1, double b2, double eps);
+int lnb_launch_incr(lnb_ctx *ctx, int *t_dev);
+int lnb_launch_adam_at(lnb_ctx *ctx, float *p, const float *g, float *m, float *v, long long n,
+                       const int *t_dev, double lr, double b1, double b2, double eps);
 int lnb_launch_sgd(lnb_ctx *ctx, float *p, const float *g, long long n, double lr);

@@ -1,0 +1,164 @@
+// trainer.cu -- device-resident training state for the hot path.
+//
+// The reference keeps the padded weights in numpy and, per chunk, calls the grad function and
+// then applies AdamOptimizer.update (train_nerf.py:395-499) or SGD (fit_img.py:512-513) on the
+// host.  A trainer keeps weights, optimiser state, the gradient buffer and (tensor-core path) the
+// bf16 weight image on the GPU, so one train step is two kernel launches and no host traffic:
+//     fused forward+backward kernel  ->  reduce partials + optimiser update + weight-image refresh
+// For multi-GPU data parallelism the step splits at the gradient buffer:
+//     lnb_trainer_grad -> (caller: NCCL all-reduce of lnb_trainer_grad_buffer) -> lnb_trainer_apply
+#include <string.h>
+
+#include "lnb_internal.h"
+
+struct lnb_trainer {
+    lnb_ctx *ctx = nullptr;
+    lnb_mlp mlp{};
+    int opt = LNB_OPT_ADAM;
+    double lr = 5e-4, b1 = 0.9, b2 = 0.999, eps = 1e-8;
+    long long n_w = 0, n_b = 0;
+    float *params = nullptr; // [ws | bs]
+    float *grads = nullptr;  // [d_ws | d_bs | loss]
+    float *m = nullptr, *v = nullptr;
+    int *t_dev = nullptr;
+    void *wimg = nullptr;    // tensor-core weight image, kept in sync with params
+    bool tc_ok = false;
+    bool t_bumped = false;   // the last lnb_trainer_grad already incremented *t_dev
+};
+
+extern "C" int lnb_trainer_create(lnb_ctx *ctx, const lnb_mlp *mlp, const float *ws_host, const float *bs_host,
+                                  int optimizer, double lr, double beta1, double beta2, double eps, lnb_trainer **out)
+{
+    if (!ctx || !out) return LNB_ERR_ARG;
+    *out = nullptr;
+    LNB_ARG(mlp && ws_host && bs_host, "trainer: mlp, ws, bs required");
+    LNB_ARG(mlp->n_layers >= 1 && mlp->n_layers <= LNB_MAX_LAYERS, "trainer: n_layers");
+    LNB_ARG(optimizer == LNB_OPT_ADAM || optimizer == LNB_OPT_SGD, "trainer: optimizer");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
+    lnb_trainer *t = new lnb_trainer();
+    t->ctx = ctx; t->mlp = *mlp; t->opt = optimizer;
+    t->lr = lr; t->b1 = beta1; t->b2 = beta2; t->eps = eps;
+    t->n_w = (long long)mlp->n_layers * mlp->max_in * mlp->max_out;
+    t->n_b = (long long)mlp->n_layers * mlp->max_out;
+    const size_t np = (size_t)(t->n_w + t->n_b);
+    int wimg_bytes = 0;
+    t->tc_ok = lnb_tc_layout(mlp, nullptr, nullptr, &wimg_bytes) != 0;
+    bool ok = cudaMalloc((void **)&t->params, np * 4) == cudaSuccess && cudaMalloc((void **)&t->grads, (np + 1) * 4) == cudaSuccess &&
+              cudaMalloc((void **)&t->m, np * 4) == cudaSuccess && cudaMalloc((void **)&t->v, np * 4) == cudaSuccess &&
+              cudaMalloc((void **)&t->t_dev, 16) == cudaSuccess;
+    if (ok && t->tc_ok) ok = cudaMalloc(&t->wimg, (size_t)wimg_bytes) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(t->params, ws_host, (size_t)t->n_w * 4, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
+         cudaMemcpyAsync(t->params + t->n_w, bs_host, (size_t)t->n_b * 4, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
+         cudaMemsetAsync(t->grads, 0, (np + 1) * 4, ctx->stream) == cudaSuccess && cudaMemsetAsync(t->m, 0, np * 4, ctx->stream) == cudaSuccess &&
+         cudaMemsetAsync(t->v, 0, np * 4, ctx->stream) == cudaSuccess && cudaMemsetAsync(t->t_dev, 0, 16, ctx->stream) == cudaSuccess;
+    if (ok && t->tc_ok) ok = lnb_tc_prep(ctx, mlp, t->params, t->params + t->n_w, t->wimg) == LNB_OK;
+    ok = ok && cudaStreamSynchronize(ctx->stream) == cudaSuccess; // the host buffers may go away
+    if (!ok) {
+        ctx->err = std::string("trainer: allocation or upload failed: ") + cudaGetErrorString(cudaGetLastError());
+        lnb_trainer_destroy(t);
+        return LNB_ERR_CUDA;
+    }
+    *out = t;
+    return LNB_OK;
+}
+
+extern "C" void lnb_trainer_destroy(lnb_trainer *t)
+{
+    if (!t) return;
+    cudaSetDevice(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+    cudaFree(t->params); cudaFree(t->grads); cudaFree(t->m); cudaFree(t->v); cudaFree(t->t_dev);
+    if (t->wimg) cudaFree(t->wimg);
+    delete t;
+}
+
+static int trainer_run(lnb_trainer *t, const lnb_step_args *batch, int nerf, bool fuse_update)
+{
+    lnb_ctx *ctx = t->ctx;
+    LNB_ARG(batch, "trainer: null batch");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
+    lnb_step_args a = *batch;
+    a.ws = t->params; a.bs = t->params + t->n_w;
+    a.want_grad = 1;
+    a.d_ws = t->grads; a.d_bs = t->grads + t->n_w; a.loss = t->grads + t->n_w + t->n_b;
+    a.d_X = a.d_target = a.d_dists = a.d_color = a.d_inter = nullptr;
+    a.inter = a.rgba = a.alpha = a.cumprod = a.weights = nullptr;
+    if (a.path == LNB_PATH_TC) {
+        LNB_ARG(t->tc_ok, "trainer: this MLP does not fit the tensor-core path");
+        lnb_tc_extra ex;
+        ex.wimg = t->wimg; ex.overwrite_grads = 1; ex.t_dev = t->t_dev;
+        if (fuse_update) {
+            ex.fuse_adam = 1; ex.param = t->params; ex.m = t->opt == LNB_OPT_ADAM ? t->m : nullptr; ex.v = t->v;
+            ex.lr = t->lr; ex.b1 = t->b1; ex.b2 = t->b2; ex.eps = t->eps; ex.wimg_out = t->wimg;
+        }
+        LNB_TRY(lnb_step_ex(ctx, &t->mlp, &a, nerf != 0, &ex));
+        t->t_bumped = !fuse_update;
+        return LNB_OK;
+    }
+    // exact fp32 path: zero the gradient buffer (its kernels accumulate), step, optional update
+    LNB_CUDA(cudaMemsetAsync(t->grads, 0, (size_t)(t->n_w + t->n_b + 1) * 4, ctx->stream));
+    LNB_TRY(nerf ? lnb_nerf_step(ctx, &t->mlp, &a) : lnb_fit_step(ctx, &t->mlp, &a));
+    t->t_bumped = false;
+    if (fuse_update) return lnb_trainer_apply(t);
+    return LNB_OK;
+}
+
+extern "C" int lnb_trainer_grad(lnb_trainer *t, const lnb_step_args *batch, int nerf)
+{
+    if (!t) return LNB_ERR_ARG;
+    return trainer_run(t, batch, nerf, false);
+}
+
+extern "C" int lnb_trainer_step(lnb_trainer *t, const lnb_step_args *batch, int nerf)
+{
+    if (!t) return LNB_ERR_ARG;
+    return trainer_run(t, batch, nerf, true);
+}
+
+extern "C" int lnb_trainer_apply(lnb_trainer *t)
+{
+    if (!t) return LNB_ERR_ARG;
+    lnb_ctx *ctx = t->ctx;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
+    const long long np = t->n_w + t->n_b;
+    if (t->tc_ok) {
+        // keeps the bf16 weight image in step with the fp32 parameters
+        if (!t->t_bumped && t->opt == LNB_OPT_ADAM) LNB_TRY(lnb_launch_incr(ctx, t->t_dev));
+        t->t_bumped = false;
+        return lnb_tc_adam_img(ctx, &t->mlp, t->params, t->grads, t->opt == LNB_OPT_ADAM ? t->m : nullptr, t->v, t->t_dev,
+                               t->lr, t->b1, t->b2, t->eps, t->wimg);
+    }
+    if (t->opt == LNB_OPT_SGD) return lnb_launch_sgd(ctx, t->params, t->grads, np, t->lr);
+    if (t->t_bumped) { // counter already advanced: use the host-free variant that reads it as is
+        t->t_bumped = false;
+        return lnb_launch_adam_at(ctx, t->params, t->grads, t->m, t->v, np, t->t_dev, t->lr, t->b1, t->b2, t->eps);
+    }
+    return lnb_launch_adam_dev(ctx, t->params, t->grads, t->m, t->v, np, t->t_dev, t->lr, t->b1, t->b2, t->eps);
+}
+
+extern "C" float *lnb_trainer_grad_buffer(lnb_trainer *t, long long *n_floats)
+{
+    if (!t) return nullptr;
+    if (n_floats) *n_floats = t->n_w + t->n_b + 1;
+    return t->grads;
+}
+
+extern "C" float *lnb_trainer_params(lnb_trainer *t, long long *n_w, long long *n_b)
+{
+    if (!t) return nullptr;
+    if (n_w) *n_w = t->n_w;
+    if (n_b) *n_b = t->n_b;
+    return t->params;
+}
+
+extern "C" int lnb_trainer_read(lnb_trainer *t, float *ws_host, float *bs_host, float *loss_host)
+{
+    if (!t) return LNB_ERR_ARG;
+    lnb_ctx *ctx = t->ctx;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
+    if (ws_host) LNB_CUDA(cudaMemcpyAsync(ws_host, t->params, (size_t)t->n_w * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (bs_host) LNB_CUDA(cudaMemcpyAsync(bs_host, t->params + t->n_w, (size_t)t->n_b * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (loss_host) LNB_CUDA(cudaMemcpyAsync(loss_host, t->grads + t->n_w + t->n_b, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    LNB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LNB_OK;
+}

@@ -124,3 +124,59 @@ def test_tc_rays_mode_fused_positional_encoding(ctx, torch_cuda, R, S, E, dtype)
                 d_ws=rel_err(o["d_ws"], f["d_ws"]), d_bs=rel_err(o["d_bs"], f["d_bs"]))
     log("rays %s R=%d S=%d E=%d %s" % (dtype, R, S, E, errs))
     assert max(errs.values()) <= TC_TOL, errs
+
+
+@pytest.mark.parametrize("path,tol", [("f32", 2e-5), ("tc", 5e-2)])
+def test_trainer_follows_the_reference_host_loop(ctx, torch_cuda, path, tol):
+    """lnb_trainer (weights, Adam state and gradients resident on the device) against the reference
+    host loop restated with the float64 oracle gradients and numpy Adam (train_nerf.py:133-161,
+    :395-499): 5 steps on different ray batches, features in and rays in."""
+    torch = torch_cuda
+    from loma_nerf_b200 import api
+    R, S, E = 256, 64, 5
+    cases = [O.make_nerf_case(900 + i, R, S) for i in range(5)]
+    ws0, bs0 = cases[0]["ws"].copy(), cases[0]["bs"].copy()
+    dims = [int(v) for v in cases[0]["dims"]]
+    lr, b1, b2, eps = 5e-4, 0.9, 0.999, 1e-8
+    ws, bs = ws0.astype(np.float64), bs0.astype(np.float64)
+    m = [np.zeros_like(ws), np.zeros_like(bs)]; v = [np.zeros_like(ws), np.zeros_like(bs)]
+    losses = []
+    for t, c in enumerate(cases, start=1):
+        f = O.nerf_f64(c["X"], ws.astype(np.float32), bs.astype(np.float32), c["dims"], c["target"], c["dists"], R, S, g=1.0)
+        losses.append(f["loss"])
+        lr_t = lr * (np.sqrt(1 - b2 ** t) / (1 - b1 ** t))
+        for i, (p_, g_) in enumerate(((ws, f["d_ws"]), (bs, f["d_bs"]))):
+            m[i] = b1 * m[i] + (1 - b1) * g_
+            v[i] = b2 * v[i] + (1 - b2) * g_ ** 2
+            p_ -= lr_t * (m[i] / (1 - b1 ** t)) / (np.sqrt(v[i] / (1 - b2 ** t)) + eps)
+    for mode in ("features", "rays"):
+        tr = api.Trainer(ctx, dims, ws0, bs0, optimizer="adam", lr=lr, beta1=b1, beta2=b2, eps=eps)
+        got_losses = []
+        for i, c in enumerate(cases):
+            tg = dev(torch, c["target"])
+            if mode == "features":
+                batch = dict(X=dev(torch, c["X"]), dists=dev(torch, c["dists"]), target=tg, path=path)
+            else:
+                rays = tuple(torch.as_tensor(np.ascontiguousarray(c[k])).cuda() for k in ("rays_o", "rays_d", "t"))
+                batch = dict(rays=rays, pe_bands=E, target=tg, path=path)
+            if i % 2 == 0:
+                tr.step(**batch)
+            else:                      # the split form used for data-parallel training
+                tr.grad(**batch)
+                g = tr.grad_buffer()
+                assert g.numel() == ws0.size + bs0.size + 1
+                tr.apply()
+            got_losses.append(tr.read()[2])
+        w, b, _ = tr.read()
+        tr.close()
+        errs = dict(ws=rel_err(w, ws), bs=rel_err(b, bs), loss=rel_err(got_losses, losses))
+        log("trainer %s %s %s" % (path, mode, errs))
+        # Adam normalises every step to ~lr * sign(g): where a gradient entry is below the bf16 noise
+        # its sign (hence the whole update of that entry) is arbitrary, so the tensor-core path is
+        # held to an L2 bound on the update vector; the exact path to a max-norm one
+        du, dr = (w - ws0).ravel().astype(np.float64), (ws - ws0).ravel()
+        upd_l2 = float(np.linalg.norm(du - dr) / np.linalg.norm(dr))
+        upd_max = rel_err(du, dr)
+        log("trainer %s %s update error: l2 %.3g max %.3g" % (path, mode, upd_l2, upd_max))
+        assert errs["loss"] <= tol, errs
+        assert (upd_l2 <= 0.15) if path == "tc" else (upd_max <= 1e-3), (upd_l2, upd_max)
