@@ -152,6 +152,7 @@ def run_ours(args):
     dims = synthetic.mlp_dims(c_in, w["width"], w["layers"], 4)
     N = R * S
     path = args.path
+    use_rays = args.input == "rays"
 
     ctx = api.Context(local)
     stream = torch.cuda.current_stream(device)
@@ -159,38 +160,43 @@ def run_ours(args):
 
     # ---- synthetic inputs: a pool of batches larger than L2 (126 MB), rotated every step
     rng = np.random.default_rng(215 + 1000 * rank)          # the reference seeds numpy with 215
-    bytes_per_batch = N * c_in * 4 + N * 4 + R * 12
+    if use_rays:
+        bytes_per_batch = R * 3 * 8 * 2 + N * 8 + R * 12
+    else:
+        bytes_per_batch = N * c_in * 4 + N * 4 + R * 12
     n_pool = max(2, int(np.ceil(160e6 / bytes_per_batch)) + 1)
-    batches = []
-    for _ in range(n_pool):
+    batches, host_batches = [], []
+    for b in range(n_pool):
         o, d = synthetic.random_rays(rng, R)
         t = synthetic.stratified_t(rng, R, S)
-        X, dists = ctx.sample_encode(torch.as_tensor(o, device=device), torch.as_tensor(d, device=device),
-                                     torch.as_tensor(t, device=device), E)
-        target = torch.as_tensor(rng.uniform(0, 1, (R, 3)).astype(np.float32), device=device)
-        batches.append((X, dists, target))
+        target = rng.uniform(0, 1, (R, 3)).astype(np.float32)
+        od, dd, td = (torch.as_tensor(v, device=device) for v in (o, d, t))
+        tgd = torch.as_tensor(target, device=device)
+        if use_rays:
+            batches.append(dict(rays=(od, dd, td), pe_bands=E, target=tgd, path=path))
+        else:
+            X, dists = ctx.sample_encode(od, dd, td, E)
+            batches.append(dict(X=X, dists=dists, target=tgd, path=path))
+        if b < 2:   # host copies (pinned) for the end-to-end legs
+            X, dists = ctx.sample_encode(od, dd, td, E)
+            host_batches.append(dict(
+                features=dict(X=X.cpu().pin_memory(), dists=dists.cpu().pin_memory(), target=tgd.cpu().pin_memory(), path=path),
+                rays=dict(rays=tuple(torch.as_tensor(v).pin_memory() for v in (o, d, t)), pe_bands=E,
+                          target=tgd.cpu().pin_memory(), path=path)))
     ws_np, bs_np = synthetic.init_mlp(np.random.default_rng(216), dims)   # same weights on every rank
-    nW, nB = ws_np.size, bs_np.size
-    params = torch.empty(nW + nB, dtype=torch.float32, device=device)
-    params[:nW] = torch.as_tensor(ws_np.ravel(), device=device)
-    params[nW:] = torch.as_tensor(bs_np.ravel(), device=device)
-    ws, bs = params[:nW].view(ws_np.shape), params[nW:].view(bs_np.shape)
-    grads = torch.zeros(nW + nB + 1, dtype=torch.float32, device=device)   # [d_ws, d_bs, loss]
-    out = {"d_ws": grads[:nW].view(ws_np.shape), "d_bs": grads[nW:nW + nB].view(bs_np.shape),
-           "loss": grads[nW + nB:]}
-    adam_m, adam_v = torch.zeros_like(params), torch.zeros_like(params)
-    t_dev = torch.zeros(1, dtype=torch.int32, device=device)
+    nP = ws_np.size + bs_np.size
+    trainer = api.Trainer(ctx, dims, ws_np, bs_np, optimizer="adam", lr=5e-4)
+    grads = trainer.grad_buffer()                           # [d_ws | d_bs | loss] on the device
 
     def step_body(b):
-        X, dists, target = batches[b]
-        grads.zero_()
-        ctx.nerf_step(dims, X, ws, bs, dists, target, R=R, S=S, grad=True, seed=1.0, outputs=("loss",),
-                      out=out, path=path)
-        if world > 1:
-            dist.all_reduce(grads)                      # NCCL sum over NVLink: gradients + loss
-        ctx.adam_step_dev(params, grads[:nW + nB], adam_m, adam_v, t_dev, lr=5e-4)
+        if world == 1:
+            trainer.step(**batches[b])                      # fused fwd+bwd kernel, then reduce + Adam
+        else:
+            trainer.grad(**batches[b])
+            dist.all_reduce(grads)                          # NCCL sum over NVLink: gradients + loss
+            trainer.apply()
 
-    # one CUDA graph per input batch (zero -> step kernels -> [all-reduce] -> Adam): one launch per step
+    # one CUDA graph per input batch: one launch per step
     graphs, launch_mode = [], "cuda-graph per step"
     if not args.eager:
         try:
@@ -210,7 +216,6 @@ def run_ours(args):
             torch.cuda.synchronize(device)
     else:
         launch_mode = "eager"
-    kernels_per_step = [0]
 
     def step(i):
         if graphs:
@@ -236,7 +241,8 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for i in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for i in range(warm):
         step(i)
     barrier()
     clocks = ClockSampler(local)
@@ -249,43 +255,33 @@ def run_ours(args):
     barrier()
     ms = timed(step, args.steps)
     launches = per_step * args.steps
-    loss_now = float(grads[nW + nB].item())
+    loss_now = float(grads[nP].item())
     value = world * N * args.steps / (ms * 1e-3)
 
     # ---- dominant-kernel roofline: CUDA events around that kernel alone, same inputs
     prof = ctx.profile_dominant(lambda: [step_body(i % n_pool) for i in range(args.steps)])
 
-    # ---- e2e: the host-pointer C-ABI call, pinned host buffers, copies inside the timed region
-    hb = []
-    for b in range(2):
-        Xh, dh, th = (t.cpu().pin_memory() for t in batches[b])
-        hb.append((Xh, dh, th))
-    ws_h, bs_h = ws.cpu().pin_memory(), bs.cpu().pin_memory()
-    g_ws = torch.zeros(ws_np.shape).pin_memory()
-    g_bs = torch.zeros(bs_np.shape).pin_memory()
-    loss_h = torch.zeros(1).pin_memory()
-    hout = {"d_ws": g_ws.numpy(), "d_bs": g_bs.numpy(), "loss": loss_h.numpy()}
+    # ---- e2e: the host-buffer C-ABI step (lnb_trainer_step_host): batch copied from pinned host
+    # memory, step, loss copied back, every step inside the timed region
+    def e2e(kind):
+        hb = [host_batches[0][kind], host_batches[1][kind]]
+        for i in range(3):
+            trainer.step_host(**hb[i % 2])
+        barrier()
+        n = max(3, min(args.steps, 20))
+        t0 = time.perf_counter()
+        for i in range(n):
+            trainer.step_host(**hb[i % 2])
+        torch.cuda.synchronize(device)
+        sec = torch.tensor([time.perf_counter() - t0], device=device)
+        if world > 1:
+            dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+        return world * N * n / float(sec.item()), n
 
-    def e2e_step(i):
-        Xh, dh, th = hb[i % 2]
-        g_ws.zero_(); g_bs.zero_()
-        ctx.nerf_step(dims, Xh.numpy(), ws_h.numpy(), bs_h.numpy(), dh.numpy(), th.numpy(), R=R, S=S, grad=True,
-                      seed=1.0, outputs=("loss",), out=hout, path=path)
-
-    e2e_steps = max(3, min(args.steps, 20))
-    for i in range(3):
-        e2e_step(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        e2e_step(i)
-    torch.cuda.synchronize(device)
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=device)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * N * e2e_steps / float(e2e_s.item())
-    h2d = (N * c_in + N + R * 3 + nW + nB) * 4
-    d2h = (nW + nB + 1) * 4
+    e2e_feat, e2e_n = e2e("features")
+    e2e_rays, _ = e2e("rays")
+    h2d_feat = (N * c_in + N + R * 3) * 4
+    h2d_rays = R * 3 * 8 * 2 + N * 8 + R * 12
     clk = clocks.stop() if rank == 0 else None
 
     if rank == 0:
@@ -295,35 +291,47 @@ def run_ours(args):
         except Exception:
             pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if path != "tc" else "bf16",
+                "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if path != "tc" else "bf16 operands, f32 accumulate (tcgen05)",
                 "data": "synthetic",
                 "config": workload_config(args.workload, world, {
-                    "path": path, "l2": "inputs rotate over %d batches (%.0f MB) > 126 MB L2" % (n_pool, n_pool * bytes_per_batch / 1e6),
+                    "path": path, "input": "rays + sample depths (PE fused in the kernel)" if use_rays else "pre-encoded features (the reference .so's layout)",
+                    "l2": "inputs rotate over %d batches (%.0f MB) > 126 MB L2" % (n_pool, n_pool * bytes_per_batch / 1e6),
                     "optimizer": "Adam (train_nerf.py:133-161) inside the step", "launch": launch_mode,
                     "loss_last_step": loss_now}),
                 "clocks": clk, "gpu_launches": launches,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": e2e_steps, "api": "lnb_nerf_step_host (pinned host buffers)"}}
+                "e2e": {"value": e2e_feat, "unit": UNIT, "h2d_bytes_per_step": h2d_feat, "d2h_bytes_per_step": 4,
+                        "steps": e2e_n, "api": "lnb_trainer_step_host, pre-encoded features from pinned host memory"},
+                "e2e_rays": {"value": e2e_rays, "unit": UNIT, "h2d_bytes_per_step": h2d_rays, "d2h_bytes_per_step": 4,
+                             "steps": e2e_n, "api": "lnb_trainer_step_host, rays mode: float64 rays + depths from pinned host "
+                                                    "memory, sample positions and positional encoding on the device"}}
         fl = flops_per_sample(dims)
+        alg_bytes = (N * 8 + R * 60) if use_rays else (N * (c_in * 4 + 4) + R * 12)
         if prof:
-            # the fused kernel reads pre-encoded features: HBM-bound by SURVEY.md 8d's per-unit bytes
-            peak = peaks.get("hbm_gbs", 6650.0)
-            alg_bytes = N * (c_in * 4 + 4) + R * 12          # features + dist per sample, target per ray
             sec = prof["ms_per_launch"] * 1e-3
-            ach = alg_bytes / sec / 1e9
-            line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                                "traffic": None, "kernel": prof["kernel"], "us_per_launch": prof["ms_per_launch"] * 1e3,
-                                "launches_timed": prof["launches"], "algorithmic_bytes_per_launch": alg_bytes,
-                                "algorithmic_tflops": N * fl / sec / 1e12,
-                                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"}
+            if use_rays:
+                peak = peaks.get("bf16_tflops", 1590.0)
+                ach = N * fl / sec / 1e12
+                line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                                    "traffic": None, "kernel": prof["kernel"], "us_per_launch": sec * 1e6,
+                                    "launches_timed": prof["launches"], "algorithmic_flops_per_launch": N * fl,
+                                    "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1590 TFLOP/s"}
+            else:
+                # the fused kernel reads pre-encoded features: HBM-bound by SURVEY.md 8d's per-unit bytes
+                peak = peaks.get("hbm_gbs", 6650.0)
+                ach = alg_bytes / sec / 1e9
+                line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                    "traffic": None, "kernel": prof["kernel"], "us_per_launch": sec * 1e6,
+                                    "launches_timed": prof["launches"], "algorithmic_bytes_per_launch": alg_bytes,
+                                    "algorithmic_tflops": N * fl / sec / 1e12,
+                                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"}
         else:
             # no single dominant kernel on the layerwise path: report the whole step against HBM
             peak = peaks.get("hbm_gbs", 6650.0)
-            alg_bytes = N * (c_in * 4 + 4) + R * 12
             ach = alg_bytes / (ms / args.steps * 1e-3) / 1e9
             line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                                "traffic": None, "kernel": "whole step (layerwise kernels)",
+                                "traffic": None, "kernel": "whole step (layerwise fp32 kernels)",
                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import cpu_bench
@@ -333,6 +341,7 @@ def run_ours(args):
                                     "sample": "%d cores x 40 chunks x 256 samples (4 rays x 64), forward + grad call per chunk, "
                                               "time inside the C calls only" % cores}
         print(json.dumps(line))
+    trainer.close()
     if world > 1:
         dist.destroy_process_group()
     ctx.close()
@@ -346,7 +355,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--path", default="f32", choices=["f32", "tc", "f32_layerwise"])
+    ap.add_argument("--path", default="tc", choices=["tc", "f32"],
+                    help="tc: fused tcgen05 kernel (bf16 operands); f32: exact fp32 CUDA-core kernels")
+    ap.add_argument("--input", default="features", choices=["features", "rays"],
+                    help="device-resident batch format: pre-encoded features, or rays (PE fused in the kernel)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()

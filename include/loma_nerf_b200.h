@@ -247,6 +247,9 @@ LNB_API int lnb_trainer_create(lnb_ctx *ctx, const lnb_mlp *mlp, const float *ws
                        int optimizer, double lr, double beta1, double beta2, double eps, lnb_trainer **out);
 LNB_API void lnb_trainer_destroy(lnb_trainer *t);
 LNB_API int lnb_trainer_step(lnb_trainer *t, const lnb_step_args *batch, int nerf);
+/* the same step with the batch in HOST memory (pinned buffers are copied from directly): stages
+ * host->device, steps, returns the loss through *loss_out; synchronous */
+LNB_API int lnb_trainer_step_host(lnb_trainer *t, const lnb_step_args *batch, int nerf, float *loss_out);
 LNB_API int lnb_trainer_grad(lnb_trainer *t, const lnb_step_args *batch, int nerf);
 LNB_API int lnb_trainer_apply(lnb_trainer *t);
 LNB_API float *lnb_trainer_grad_buffer(lnb_trainer *t, long long *n_floats);

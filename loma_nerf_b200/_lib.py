@@ -102,6 +102,7 @@ def load():
     lib.lnb_trainer_destroy.restype = None
     for name in ("lnb_trainer_step", "lnb_trainer_grad"):
         getattr(lib, name).argtypes = [c_void_p, P(LnbStepArgs), c_int]
+    lib.lnb_trainer_step_host.argtypes = [c_void_p, P(LnbStepArgs), c_int, P(c_float)]
     lib.lnb_trainer_apply.argtypes = [c_void_p]
     lib.lnb_trainer_grad_buffer.argtypes = [c_void_p, P(c_longlong)]
     lib.lnb_trainer_grad_buffer.restype = c_void_p

@@ -302,6 +302,14 @@ class Trainer:
         a, nerf = self._batch(**batch)
         self.ctx._check(self.lib.lnb_trainer_step(self.h, ctypes.byref(a), nerf))
 
+    def step_host(self, **batch):
+        """step() with the batch in host memory (numpy arrays / pinned CPU tensors): the C library
+        stages it to the device, steps, and returns the loss.  Synchronous."""
+        a, nerf = self._batch(**batch)
+        loss = ctypes.c_float()
+        self.ctx._check(self.lib.lnb_trainer_step_host(self.h, ctypes.byref(a), nerf, ctypes.byref(loss)))
+        return float(loss.value)
+
     def grad(self, **batch):
         """forward + backward only: gradients (and loss) land in grad_buffer()."""
         a, nerf = self._batch(**batch)

@@ -136,6 +136,71 @@ extern "C" int lnb_trainer_apply(lnb_trainer *t)
     return lnb_launch_adam_dev(ctx, t->params, t->grads, t->m, t->v, np, t->t_dev, t->lr, t->b1, t->b2, t->eps);
 }
 
+// Host-buffer step: stages the batch (pinned buffers are copied directly, pageable ones bounce
+// through the context's pinned block), runs lnb_trainer_step, returns the loss.  Synchronous.
+extern "C" int lnb_trainer_step_host(lnb_trainer *t, const lnb_step_args *batch, int nerf, float *loss_out)
+{
+    if (!t) return LNB_ERR_ARG;
+    lnb_ctx *ctx = t->ctx;
+    LNB_ARG(batch, "trainer: null batch");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
+    lnb_step_args a = *batch;
+    const size_t R = (size_t)a.R, S = nerf ? (size_t)a.S : 1, N = a.n_rows > 0 ? (size_t)a.n_rows : R * S;
+    const size_t c_in = (size_t)t->mlp.dims[0], Wt = a.target_w > 0 ? (size_t)a.target_w : 3;
+    const bool rays = !a.X && a.rays_o;
+    const size_t rw = a.ray_dtype == LNB_RAY_F64 ? 8 : 4;
+    struct In { const void **slot; size_t bytes; };
+    In ins[6];
+    int n_in = 0;
+    if (rays) {
+        ins[n_in++] = In{&a.rays_o, R * 3 * rw};
+        ins[n_in++] = In{&a.rays_d, R * 3 * rw};
+        ins[n_in++] = In{&a.t, R * S * rw};
+    } else {
+        LNB_ARG(a.X, "trainer: X or rays required");
+        ins[n_in++] = In{(const void **)&a.X, N * c_in * 4};
+        if (nerf) { LNB_ARG(a.dists, "trainer: dists required"); ins[n_in++] = In{(const void **)&a.dists, R * S * 4}; }
+    }
+    LNB_ARG(a.target, "trainer: target required");
+    ins[n_in++] = In{(const void **)&a.target, R * Wt * 4};
+    size_t dtotal = 0, ptotal = 0;
+    bool direct[6];
+    for (int i = 0; i < n_in; ++i) {
+        cudaPointerAttributes at;
+        direct[i] = cudaPointerGetAttributes(&at, *ins[i].slot) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        if (!direct[i]) { cudaGetLastError(); ptotal += (ins[i].bytes + 255) / 256 * 256 + 256; }
+        dtotal += (ins[i].bytes + 255) / 256 * 256;
+    }
+    if (dtotal + 256 > ctx->dstage_cap) {
+        LNB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->dstage) LNB_CUDA(cudaFree(ctx->dstage));
+        ctx->dstage = nullptr; ctx->dstage_cap = 0;
+        const size_t cap = (dtotal + dtotal / 4 + (1 << 20)) / (1 << 20) * (1 << 20);
+        LNB_CUDA(cudaMalloc((void **)&ctx->dstage, cap));
+        ctx->dstage_cap = cap;
+    }
+    LNB_TRY(lnb_pinned_reserve(ctx, ptotal + 256));
+    size_t off = 0;
+    for (int i = 0; i < n_in; ++i) {
+        const void *src = *ins[i].slot;
+        if (!direct[i]) {
+            void *pin = lnb_pinned_take(ctx, ins[i].bytes);
+            memcpy(pin, src, ins[i].bytes);
+            src = pin;
+        }
+        LNB_CUDA(cudaMemcpyAsync(ctx->dstage + off, src, ins[i].bytes, cudaMemcpyHostToDevice, ctx->stream));
+        *ins[i].slot = ctx->dstage + off;
+        off += (ins[i].bytes + 255) / 256 * 256;
+    }
+    LNB_TRY(trainer_run(t, &a, nerf, true));
+    float *pl = (float *)lnb_pinned_take(ctx, 16);
+    if (!pl) { LNB_TRY(lnb_pinned_reserve(ctx, 4096)); pl = (float *)lnb_pinned_take(ctx, 16); }
+    LNB_CUDA(cudaMemcpyAsync(pl, t->grads + t->n_w + t->n_b, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    LNB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (loss_out) *loss_out = *pl;
+    return LNB_OK;
+}
+
 extern "C" float *lnb_trainer_grad_buffer(lnb_trainer *t, long long *n_floats)
 {
     if (!t) return nullptr;
