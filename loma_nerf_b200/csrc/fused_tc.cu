@@ -749,7 +749,7 @@ __device__ __forceinline__ float adam_one(const AdamArgs &a, long long i, float 
 
 // reduce the per-CTA partials in a fixed order; apply the seed; accumulate into (or overwrite) the
 // caller's buffers; optionally apply Adam to the parameter and refresh the bf16 weight image
-__global__ void tc_reduce_kernel(const float *__restrict__ part, int n_part, int part_stride, TcParams p,
+__global__ void __launch_bounds__(1024) tc_reduce_kernel(const float *__restrict__ part, int n_part, int part_stride, TcParams p,
                                  float *__restrict__ d_ws, float *__restrict__ d_bs, float *__restrict__ loss,
                                  float seed_value, int seed_is_loss, int overwrite, int fuse_adam, AdamArgs ad, ImgMap im)
 {
@@ -768,15 +768,25 @@ __global__ void tc_reduce_kernel(const float *__restrict__ part, int n_part, int
     __syncthreads();
     if (!d_ws) return;
     const float scale = seed_is_loss ? sloss * seed_value : seed_value;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    // 32 consecutive elements per block (one coalesced 128 B line per partial), 32 warps stride over
+    // the partials with all their loads in flight, fixed-order combine through shared memory
+    __shared__ float acc[32][33];
+    const int el = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int n_el = part_stride - 1;
-    if (warp >= n_el) return;
+    const int e_glob = blockIdx.x * 32 + el;
     float s = 0.0f;
-    for (int i = lane; i < n_part; i += 32) s += part[(size_t)i * part_stride + 1 + warp];
+    if (e_glob < n_el) {
+        const float *src = part + 1 + e_glob;
+#pragma unroll 8
+        for (int i = grp; i < n_part; i += 32) s += src[(size_t)i * part_stride];
+    }
+    acc[grp][el] = s;
+    __syncthreads();
+    if (grp == 0 && e_glob < n_el) {
+        s = 0.0f;
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-    if (lane == 0) {
-        int e = warp + 1, l = 0;
+        for (int w2 = 0; w2 < 32; ++w2) s += acc[w2][el];
+        int e = e_glob + 1, l = 0;
         while (l + 1 < p.L && e >= p.part_off[l + 1]) ++l;
         e -= p.part_off[l];
         const int out_l = p.dims[l + 1], k = e / out_l, j = e % out_l;
@@ -998,13 +1008,13 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     const int n_el = p.part_stride - 1;
     const int seed_is_loss = a->seed_mode == LNB_SEED_LOSS;
     const float seed_val = seed_is_loss ? 1.0f : a->seed;
-    int blocks = a->want_grad ? (n_el * 32 + 255) / 256 : 1;
+    int blocks = a->want_grad ? (n_el + 31) / 32 : 1;
     AdamArgs ad{};
     ImgMap im{L, HP, K0P};
     const int fuse = ex && ex->fuse_adam && a->want_grad;
     if (fuse) ad = AdamArgs{ex->param, ex->m, ex->v, ex->t_dev, ex->lr, ex->b1, ex->b2, ex->eps, (uint8_t *)ex->wimg_out,
                             (long long)L * mlp->max_in * mlp->max_out, ex->m == nullptr};
-    tc_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(p.part, grid, p.part_stride, p, a->want_grad ? a->d_ws : nullptr,
+    tc_reduce_kernel<<<blocks, 1024, 0, ctx->stream>>>(p.part, grid, p.part_stride, p, a->want_grad ? a->d_ws : nullptr,
                                                       a->want_grad ? a->d_bs : nullptr, loss, seed_val, seed_is_loss,
                                                       ex ? ex->overwrite_grads : 0, fuse, ad, im);
     LNB_CHECK_LAUNCH();
