@@ -128,6 +128,12 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def _dbg(msg):
+    if os.environ.get("BENCH_DEBUG"):
+        sys.stderr.write("[bench rank %s] %s\n" % (os.environ.get("RANK", "0"), msg))
+        sys.stderr.flush()
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -183,6 +189,7 @@ def run_ours(args):
                 features=dict(X=X.cpu().pin_memory(), dists=dists.cpu().pin_memory(), target=tgd.cpu().pin_memory(), path=path),
                 rays=dict(rays=tuple(torch.as_tensor(v).pin_memory() for v in (o, d, t)), pe_bands=E,
                           target=tgd.cpu().pin_memory(), path=path)))
+    _dbg("inputs ready")
     ws_np, bs_np = synthetic.init_mlp(np.random.default_rng(216), dims)   # same weights on every rank
     nP = ws_np.size + bs_np.size
     trainer = api.Trainer(ctx, dims, ws_np, bs_np, optimizer="adam", lr=5e-4)
@@ -196,8 +203,9 @@ def run_ours(args):
             dist.all_reduce(grads)                          # NCCL sum over NVLink: gradients + loss
             trainer.apply()
 
-    # one CUDA graph per input batch: one launch per step
-    graphs, launch_mode = [], "cuda-graph per step"
+    # CUDA graphs: one per input batch (N=1: the whole step; N>1: the gradient half, then an eager
+    # NCCL all-reduce, then one shared graph for the optimiser half -- NCCL stays outside capture)
+    graphs, apply_graph, launch_mode = [], None, "cuda-graph per step"
     if not args.eager:
         try:
             for b in range(2):
@@ -207,19 +215,32 @@ def run_ours(args):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     ctx.set_stream(torch.cuda.current_stream(device))
-                    step_body(b)
+                    if world == 1:
+                        trainer.step(**batches[b])
+                    else:
+                        trainer.grad(**batches[b])
                 graphs.append(g)
+            if world > 1:
+                apply_graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(apply_graph):
+                    ctx.set_stream(torch.cuda.current_stream(device))
+                    trainer.apply()
+                launch_mode = "cuda-graph (gradient) + NCCL all-reduce + cuda-graph (optimiser) per step"
             ctx.set_stream(stream)
         except Exception as e:  # report, never hide: fall back to eager launches
-            graphs, launch_mode = [], "eager (graph capture failed: %s)" % str(e)[:80]
+            graphs, apply_graph, launch_mode = [], None, "eager (graph capture failed: %s)" % str(e)[:80]
             ctx.set_stream(stream)
             torch.cuda.synchronize(device)
     else:
         launch_mode = "eager"
+    _dbg("launch mode: " + launch_mode)
 
     def step(i):
         if graphs:
             graphs[i % n_pool].replay()
+            if world > 1:
+                dist.all_reduce(grads)
+                apply_graph.replay()
         else:
             step_body(i % n_pool)
 
@@ -254,6 +275,7 @@ def run_ours(args):
     per_step = ctx.launches - l0
     barrier()
     ms = timed(step, args.steps)
+    _dbg("timed region done: %.3f ms" % ms)
     launches = per_step * args.steps
     loss_now = float(grads[nP].item())
     value = world * N * args.steps / (ms * 1e-3)
@@ -278,11 +300,13 @@ def run_ours(args):
             dist.all_reduce(sec, op=dist.ReduceOp.MAX)
         return world * N * n / float(sec.item()), n
 
+    _dbg("profile pass done")
     e2e_feat, e2e_n = e2e("features")
     e2e_rays, _ = e2e("rays")
     h2d_feat = (N * c_in + N + R * 3) * 4
     h2d_rays = R * 3 * 8 * 2 + N * 8 + R * 12
     clk = clocks.stop() if rank == 0 else None
+    _dbg("e2e done")
 
     if rank == 0:
         peaks = {}
