@@ -130,6 +130,7 @@ extern "C" void lnb_destroy(lnb_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->dstage) cudaFree(ctx->dstage);
+    if (ctx->tc_counter) cudaFree(ctx->tc_counter);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);

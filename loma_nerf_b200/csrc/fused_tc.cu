@@ -50,6 +50,7 @@ struct TcParams {
     const void *rays_o, *rays_d, *tvals; // [R][3], [R][3], [R][S]; float64 when ray_f64 else float32
     int ray_f64, pe_bands;
     int *t_dev;        // optimiser step counter, incremented once per launch (or NULL)
+    int *tile_counter; // dynamic tile scheduler: tiles beyond the first are claimed with atomicAdd
     long long N;       // samples (rows of X)
     int R, S, G, rows_per_tile, n_tiles;
     int L, dims[MAXL + 1], max_in, max_out;
@@ -251,6 +252,8 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
     extern __shared__ __align__(1024) uint8_t smem[];
 #ifdef LNB_TC_CLK
     const long long clk_start = clock64();
+    unsigned long long gt_start;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_start));
 #endif
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = p.L, K0P = p.K0P, c_in = p.dims[0], S = p.S;
@@ -290,7 +293,11 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
     };
 
     // ---- one-time setup: zero activations and stage, then TMA the weight image and the first tile
-    for (uint8_t *z = smem + tid * 16; z < smem + act_bytes; z += TILE * 16) *reinterpret_cast<uint4 *>(z) = make_uint4(0, 0, 0, 0);
+    // (every activation / adjoint buffer is fully rewritten each tile before it is read, except
+    // the upper 8 features of dZ_{L-1}, which must stay zero)
+    for (uint8_t *z = smem + LY::dz_off(L - 1, L, K0P) + tid * 16; z < smem + act_bytes; z += TILE * 16) *reinterpret_cast<uint4 *>(z) = make_uint4(0, 0, 0, 0);
+    if (RAYS) // the fused prologue writes only the live features of A_0: its padding columns must be zero
+        for (uint8_t *z = smem + tid * 16; z < smem + LY::a_off(1, K0P); z += TILE * 16) *reinterpret_cast<uint4 *>(z) = make_uint4(0, 0, 0, 0);
     for (uint8_t *z = reinterpret_cast<uint8_t *>(stage) + tid * 16; z < reinterpret_cast<uint8_t *>(tailp); z += TILE * 16)
         *reinterpret_cast<uint4 *>(z) = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
@@ -373,13 +380,14 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
     };
 
 #ifdef LNB_TC_CLK
-    long long clk_acc[16] = {0}, clk_t = clock64();
+    long long clk_acc[24] = {0}, clk_t = clock64();
     clk_acc[14] = clk_t - clk_start;
 #define CLK(i) do { long long t_ = clock64(); clk_acc[i] += t_ - clk_t; clk_t = t_; } while (0)
 #else
 #define CLK(i)
 #endif
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    int *const next_tile_s = reinterpret_cast<int *>(tailp + 32);
+    for (int tile = blockIdx.x; tile < p.n_tiles;) {
         const long long row0 = (long long)tile * p.rows_per_tile;
         long long rem = p.N - row0;
         const int valid = rem < p.rows_per_tile ? (int)rem : p.rows_per_tile;
@@ -468,9 +476,12 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
         }
         publish_smem(); // also: every thread is done reading `stage`
         CLK(1);
-        if (!RAYS && tid == 0) {
-            const int nt = tile + gridDim.x;
-            if (nt < p.n_tiles) {
+        if (tid == 0) {
+            // claim the next tile now (so its features can be prefetched); CTAs that started late or
+            // run slow simply claim fewer tiles
+            const int nt = atomicAdd(p.tile_counter, 1) + (int)gridDim.x;
+            *next_tile_s = nt;
+            if (!RAYS && nt < p.n_tiles) {
                 int lead; uint32_t bytes;
                 const void *src = x_src(nt, lead, bytes);
                 mbar_expect_tx(bar_x, bytes);
@@ -518,6 +529,7 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
                 for (int j = 0; j < 4; ++j) hz[j] = __uint_as_float(v[j]) + bl[j];
             }
         }
+        CLK(16);
         // ---- head + loss + adjoint of the head's pre-activation (unit seed)
         float dz[4] = {0.f, 0.f, 0.f, 0.f};
         if (p.head == LNB_HEAD_SIGMOID) {
@@ -552,7 +564,9 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
                 color_s[ray_l * 3] = 0.f; color_s[ray_l * 3 + 1] = 0.f; color_s[ray_l * 3 + 2] = 0.f;
                 tgt_s[ray_l * 3] = tg0; tgt_s[ray_l * 3 + 1] = tg1; tgt_s[ray_l * 3 + 2] = tg2;
             }
+            CLK(17);
             __syncthreads();
+            CLK(18);
             float carry = 1.0f;                              // product of this ray's samples in earlier warps
             if (smp > lane) {
                 for (int w2 = warp - 1; w2 >= 0; --w2) {
@@ -574,7 +588,9 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
                     atomicAdd(color_s + ray_l * 3, s0); atomicAdd(color_s + ray_l * 3 + 1, s1); atomicAdd(color_s + ray_l * 3 + 2, s2);
                 }
             }
+            CLK(19);
             __syncthreads();
+            CLK(20);
             float dc0 = 0.f, dc1 = 0.f, dc2 = 0.f;
             if (live) {
                 const float c0 = color_s[ray_l * 3], c1 = color_s[ray_l * 3 + 1], c2 = color_s[ray_l * 3 + 2];
@@ -602,7 +618,9 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
                     if (lane + d < 32) { Aa = fmaf(Bb, A2, Aa); Bb = Bb * B2; }
                 }
                 if (lane == 0) { headA[warp] = Aa; headB[warp] = Bb; }
+                CLK(21);
                 __syncthreads();
+                CLK(22);
                 float Gn = 0.0f;                             // G at lane 0 of the next warp
                 for (int w2 = 3; w2 > warp; --w2) Gn = fmaf(headB[w2], Gn, headA[w2]);
                 const float Gv = fmaf(Bb, Gn, Aa);
@@ -618,8 +636,8 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
                 }
             }
         }
-        CLK(6);
-        if (!p.want_grad) continue;
+        CLK(23);
+        if (!p.want_grad) { __syncthreads(); tile = *next_tile_s; continue; }
         // ---- backward.  dZ_{L-1}: 4 live features, the rest of the 16 stay zero
         *row_ptr(dz_buf(L - 1), 0) = make_uint4(pack_bf16(dz[0], dz[1]), pack_bf16(dz[2], dz[3]), 0u, 0u);
         publish_smem();
@@ -655,6 +673,7 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
         if (tid == 0) { issue_stage(2 * L); umma_commit(bar_dw); }
         dw_pending = true;
         CLK(13);
+        tile = *next_tile_s; // written before this tile's forward; several block barriers ago
         dw_started = true;
     }
 
@@ -700,7 +719,13 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
     if (warp == 0) tmem_dealloc(tmem, LY::tmem_cols(L));
 #ifdef LNB_TC_CLK
     clk_acc[13] += clock64() - clk_t; // (issue dW slot reused: epilogue after the last tile)
-    if (p.dbg && tid == 0) for (int i = 0; i < 16; ++i) p.dbg[blockIdx.x * 16 + i] = (float)clk_acc[i];
+    unsigned long long gt_end;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_end));
+    if (p.dbg && tid == 0) {
+        unsigned long long *tt = reinterpret_cast<unsigned long long *>(p.dbg + (size_t)gridDim.x * 24);
+        tt[blockIdx.x * 2] = gt_start; tt[blockIdx.x * 2 + 1] = gt_end;
+    }
+    if (p.dbg && tid == 0) for (int i = 0; i < 24; ++i) p.dbg[blockIdx.x * 24 + i] = (float)clk_acc[i];
 #endif
 }
 
@@ -763,6 +788,7 @@ __global__ void __launch_bounds__(1024) tc_reduce_kernel(const float *__restrict
         if (threadIdx.x == 0) {
             sloss = s;
             if (blockIdx.x == 0 && loss) loss[0] = s;
+            if (blockIdx.x == 0 && p.tile_counter) p.tile_counter[0] = 0; // ready for the next launch
         }
     }
     __syncthreads();
@@ -953,11 +979,16 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     uint8_t *wimg = (uint8_t *)lnb_arena_take(ctx, wimg_bytes);
     p.wimg = (ex && ex->wimg) ? ex->wimg : wimg;
     p.t_dev = ex ? ex->t_dev : nullptr;
+    if (!ctx->tc_counter) {
+        LNB_CUDA(cudaMalloc((void **)&ctx->tc_counter, 256));
+        LNB_CUDA(cudaMemsetAsync(ctx->tc_counter, 0, 256, ctx->stream));
+    }
+    p.tile_counter = ctx->tc_counter;
     float *loss = a->loss ? a->loss : (float *)lnb_arena_take(ctx, 16);
 #ifdef LNB_TC_CLK
     float *dbg_dev = nullptr;
-    cudaMalloc(&dbg_dev, (size_t)grid * 16 * sizeof(float));
-    cudaMemset(dbg_dev, 0, (size_t)grid * 16 * sizeof(float));
+    cudaMalloc(&dbg_dev, (size_t)grid * 28 * sizeof(float));
+    cudaMemset(dbg_dev, 0, (size_t)grid * 28 * sizeof(float));
     p.dbg = dbg_dev;
 #endif
     if (N > 0) {
@@ -990,18 +1021,29 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
 #ifdef LNB_TC_CLK
     {
         cudaStreamSynchronize(ctx->stream);
-        std::vector<float> h((size_t)grid * 16);
+        std::vector<float> h((size_t)grid * 28);
         cudaMemcpy(h.data(), dbg_dev, h.size() * sizeof(float), cudaMemcpyDeviceToHost);
         cudaFree(dbg_dev);
         static int calls = 0;
-        if (++calls == 20) {
-            double acc[16] = {0};
-            for (int b = 0; b < grid; ++b) for (int i = 0; i < 16; ++i) acc[i] += h[(size_t)b * 16 + i];
-            const char *nm[16] = {"wait X", "convert+publish", "issue fwd", "wait fwd mma", "fwd epilogue", "fwd publish", "head+composite", "dz publish",
-                                  "issue bwd", "wait bwd mma", "bwd epilogue", "bwd publish", "wait dW", "issue dW + final epilogue", "prologue", "loop top"};
-            double tot = 0; for (int i = 0; i < 16; ++i) tot += acc[i];
+        if (++calls % 150 == 20) {
+            double acc[24] = {0};
+            for (int b = 0; b < grid; ++b) for (int i = 0; i < 24; ++i) acc[i] += h[(size_t)b * 24 + i];
+            const char *nm[24] = {"wait X", "convert+publish", "issue fwd", "wait fwd mma", "fwd epilogue", "fwd publish", "head+composite", "dz publish",
+                                  "issue bwd", "wait bwd mma", "bwd epilogue", "bwd publish", "wait dW", "issue dW + final epilogue", "prologue", "loop top",
+                                  "head ld+bias", "comp: act+prodscan", "comp: sync1", "comp: carry+colour", "comp: sync2", "comp: dcol+affine", "comp: sync3", "comp: finish"};
+            double tot = 0; for (int i = 0; i < 24; ++i) tot += acc[i];
             fprintf(stderr, "[tc clk] grid %d tiles %d: cycles per tile (thread 0), total %.0f\n", grid, p.n_tiles, tot / p.n_tiles);
-            for (int i = 0; i < 16; ++i) if (acc[i] > 0) fprintf(stderr, "   %-18s %8.0f\n", nm[i], acc[i] / p.n_tiles);
+            {
+                const unsigned long long *tt = reinterpret_cast<const unsigned long long *>(h.data() + (size_t)grid * 24);
+                unsigned long long s0 = ~0ull, s1 = 0, e0 = ~0ull, e1 = 0;
+                for (int b = 0; b < grid; ++b) {
+                    s0 = tt[2 * b] < s0 ? tt[2 * b] : s0; s1 = tt[2 * b] > s1 ? tt[2 * b] : s1;
+                    e0 = tt[2 * b + 1] < e0 ? tt[2 * b + 1] : e0; e1 = tt[2 * b + 1] > e1 ? tt[2 * b + 1] : e1;
+                }
+                fprintf(stderr, "   CTA start spread %.1f us, first end at %.1f us, last end at %.1f us (from first start)\n",
+                        (s1 - s0) * 1e-3, (e0 - s0) * 1e-3, (e1 - s0) * 1e-3);
+            }
+            for (int i = 0; i < 24; ++i) if (acc[i] > 0) fprintf(stderr, "   %-18s %8.0f\n", nm[i], acc[i] / p.n_tiles);
         }
     }
 #endif

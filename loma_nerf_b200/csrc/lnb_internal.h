@@ -25,6 +25,7 @@ struct lnb_ctx {
     char *dstage = nullptr;
     size_t dstage_cap = 0;
     long long launches = 0;
+    int *tc_counter = nullptr; // tile-scheduler counter of the fused kernel (zero between launches)
     std::string err;
     // optional timing of the dominant (fused) kernel: CUDA-event pairs around each launch
     bool prof_on = false;
