@@ -296,8 +296,8 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
     // (every activation / adjoint buffer is fully rewritten each tile before it is read, except
     // the upper 8 features of dZ_{L-1}, which must stay zero)
     for (uint8_t *z = smem + LY::dz_off(L - 1, L, K0P) + tid * 16; z < smem + act_bytes; z += TILE * 16) *reinterpret_cast<uint4 *>(z) = make_uint4(0, 0, 0, 0);
-    if (RAYS) // the fused prologue writes only the live features of A_0: its padding columns must be zero
-        for (uint8_t *z = smem + tid * 16; z < smem + LY::a_off(1, K0P); z += TILE * 16) *reinterpret_cast<uint4 *>(z) = make_uint4(0, 0, 0, 0);
+    // A_0: only the slabs holding live features are rewritten per tile; its padding must be zero
+    for (uint8_t *z = smem + tid * 16; z < smem + LY::a_off(1, K0P); z += TILE * 16) *reinterpret_cast<uint4 *>(z) = make_uint4(0, 0, 0, 0);
     for (uint8_t *z = reinterpret_cast<uint8_t *>(stage) + tid * 16; z < reinterpret_cast<uint8_t *>(tailp); z += TILE * 16)
         *reinterpret_cast<uint4 *>(z) = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
@@ -461,15 +461,16 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
             CLK(12);
             uint8_t *a0 = a_buf(0);
             const float *xr = stage + lead + tid * c_in;
+            const int live_slabs = (c_in + 8) >> 3; // slabs containing features 0..c_in (incl. the ones column)
             if (tid < valid) {
-                for (int c8 = 0; c8 < K0P / 8; ++c8) {
+                for (int c8 = 0; c8 < live_slabs; ++c8) {
                     float f[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) f[j] = xr[c8 * 8 + j];
                     *row_ptr(a0, c8) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
                 }
             } else {
-                for (int c8 = 0; c8 < K0P / 8; ++c8) *row_ptr(a0, c8) = make_uint4(0, 0, 0, 0);
+                for (int c8 = 0; c8 < live_slabs; ++c8) *row_ptr(a0, c8) = make_uint4(0, 0, 0, 0);
             }
             __syncwarp();
             reinterpret_cast<__nv_bfloat16 *>(a0)[(c_in >> 3) * (TILE * 8) + tid * 8 + (c_in & 7)] = __float2bfloat16_rn(1.0f);
@@ -493,26 +494,31 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
         for (int l = 0; l < L; ++l) {
             if (tid == 0) issue_stage(l);
             CLK(2);
+#ifdef LNB_TC_ISSUE_TWICE
+            if (tid == 0) issue_stage(l);
+            CLK(6);
+#endif
             commit_and_wait();
             CLK(3);
             const float *bl = bias_s + l * HP;
             if (l < L - 1) {
                 const int ones_col = p.dims[l + 1];
                 uint8_t *an = a_buf(l + 1);
+                uint32_t v[HP / 16][16];
+#pragma unroll
+                for (int c16 = 0; c16 < HP / 16; ++c16) tmem_ld16(tmem + lane_base + c16 * 16, v[c16]);
+                tmem_ld_wait();
 #pragma unroll
                 for (int c16 = 0; c16 < HP / 16; ++c16) {
-                    uint32_t v[16];
-                    tmem_ld16(tmem + lane_base + c16 * 16, v);
-                    float bv[16];
-#pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        float4 b4 = *reinterpret_cast<const float4 *>(bl + c16 * 16 + j4 * 4);
-                        bv[j4 * 4] = b4.x; bv[j4 * 4 + 1] = b4.y; bv[j4 * 4 + 2] = b4.z; bv[j4 * 4 + 3] = b4.w;
-                    }
-                    tmem_ld_wait();
                     float f[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) f[j] = fmaxf(__uint_as_float(v[j]) + bv[j], 0.0f);
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 b4 = *reinterpret_cast<const float4 *>(bl + c16 * 16 + j4 * 4);
+                        f[j4 * 4] = fmaxf(__uint_as_float(v[c16][j4 * 4]) + b4.x, 0.0f);
+                        f[j4 * 4 + 1] = fmaxf(__uint_as_float(v[c16][j4 * 4 + 1]) + b4.y, 0.0f);
+                        f[j4 * 4 + 2] = fmaxf(__uint_as_float(v[c16][j4 * 4 + 2]) + b4.z, 0.0f);
+                        f[j4 * 4 + 3] = fmaxf(__uint_as_float(v[c16][j4 * 4 + 3]) + b4.w, 0.0f);
+                    }
                     *row_ptr(an, c16 * 2) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
                     *row_ptr(an, c16 * 2 + 1) = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
                 }
@@ -648,21 +654,24 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
             commit_and_wait();
             CLK(9);
             uint8_t *al = a_buf(l), *dzn = dz_buf(l - 1);
+            uint32_t v[HP / 16][16];
 #pragma unroll
-            for (int c16 = 0; c16 < HP / 16; ++c16) {
-                uint32_t v[16];
-                tmem_ld16(tmem + lane_base + c16 * 16, v);
-                uint4 h0 = *row_ptr(al, c16 * 2), h1 = *row_ptr(al, c16 * 2 + 1);
-                uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-                tmem_ld_wait();
-                uint32_t o[8];
+            for (int c16 = 0; c16 < HP / 16; ++c16) tmem_ld16(tmem + lane_base + c16 * 16, v[c16]);
+            uint4 hm[HP / 8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    // ReLU mask: bf16 post-ReLU values are >= 0, so positive <=> non-zero halfword
-                    o[j] = pack_bf16(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])) & __vcmpne2(hw[j], 0u);
+            for (int c8 = 0; c8 < HP / 8; ++c8) hm[c8] = *row_ptr(al, c8);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c8 = 0; c8 < HP / 8; ++c8) {
+                // ReLU mask: bf16 post-ReLU values are >= 0, so positive <=> non-zero halfword
+                const uint32_t hw[4] = {hm[c8].x, hm[c8].y, hm[c8].z, hm[c8].w};
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int e = (c8 & 1) * 8 + 2 * j;
+                    o[j] = pack_bf16(__uint_as_float(v[c8 >> 1][e]), __uint_as_float(v[c8 >> 1][e + 1])) & __vcmpne2(hw[j], 0u);
                 }
-                *row_ptr(dzn, c16 * 2) = make_uint4(o[0], o[1], o[2], o[3]);
-                *row_ptr(dzn, c16 * 2 + 1) = make_uint4(o[4], o[5], o[6], o[7]);
+                *row_ptr(dzn, c8) = make_uint4(o[0], o[1], o[2], o[3]);
             }
             CLK(10);
             publish_smem();
@@ -670,7 +679,7 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
         }
         // all dZ_l are in shared memory: the weight-gradient MMAs run in the background; their
         // completion is awaited only before A_0 is overwritten by the next tile (or at the end)
-        if (tid == 0) { issue_stage(2 * L); umma_commit(bar_dw); }
+        if (tid == 32) { issue_stage(2 * L); umma_commit(bar_dw); } // warp 1 issues; warp 0 moves on
         dw_pending = true;
         CLK(13);
         tile = *next_tile_s; // written before this tile's forward; several block barriers ago
@@ -1028,7 +1037,7 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
         if (++calls % 150 == 20) {
             double acc[24] = {0};
             for (int b = 0; b < grid; ++b) for (int i = 0; i < 24; ++i) acc[i] += h[(size_t)b * 24 + i];
-            const char *nm[24] = {"wait X", "convert+publish", "issue fwd", "wait fwd mma", "fwd epilogue", "fwd publish", "head+composite", "dz publish",
+            const char *nm[24] = {"wait X", "convert+publish", "issue fwd", "wait fwd mma", "fwd epilogue", "fwd publish", "issue fwd AGAIN (experiment)", "dz publish",
                                   "issue bwd", "wait bwd mma", "bwd epilogue", "bwd publish", "wait dW", "issue dW + final epilogue", "prologue", "loop top",
                                   "head ld+bias", "comp: act+prodscan", "comp: sync1", "comp: carry+colour", "comp: sync2", "comp: dcol+affine", "comp: sync3", "comp: finish"};
             double tot = 0; for (int i = 0; i < 24; ++i) tot += acc[i];
