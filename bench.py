@@ -301,6 +301,34 @@ def run_ours(args):
         return world * N * n / float(sec.item()), n
 
     _dbg("profile pass done")
+    # ---- render (BASELINE config 4 shape): forward-only 800x800 frames, 64 samples per ray, rays mode;
+    # frames are disjoint across ranks (no collective)
+    render = None
+    if not args.no_render:
+        Hh = 800
+        frames = []
+        for _ in range(2):
+            fo, fd = synthetic.frame_rays(rng, Hh, Hh)
+            ft = synthetic.stratified_t(rng, Hh * Hh, S)
+            frames.append(tuple(torch.as_tensor(v, device=device) for v in (fo, fd, ft)))
+        col = torch.zeros((Hh * Hh, 3), dtype=torch.float32, device=device)
+
+        def render_frame(i):
+            fo, fd, ft = frames[i % 2]
+            ctx.nerf_step_rays(dims, fo, fd, ft, E, ws_d, bs_d, target=None, grad=False, outputs=("color",),
+                               out={"color": col}, path=path)
+
+        ws_d, bs_d = (torch.as_tensor(v, device=device) for v in trainer.read()[:2])
+        for i in range(2):
+            render_frame(i)
+        n_fr = 6
+        rms = timed(render_frame, n_fr)
+        render = {"metric": "nerf_render_rays_per_s", "value": world * Hh * Hh * n_fr / (rms * 1e-3), "unit": "rays/s",
+                  "rays_per_frame": Hh * Hh, "samples_per_ray": S, "frames_timed": n_fr, "ms_per_frame": rms / n_fr,
+                  "samples_per_s": world * Hh * Hh * S * n_fr / (rms * 1e-3),
+                  "input": "float64 rays + depths resident in HBM, PE on the device", "frames_across_gpus": world}
+        del frames, col
+    _dbg("render done")
     e2e_feat, e2e_n = e2e("features")
     e2e_rays, _ = e2e("rays")
     h2d_feat = (N * c_in + N + R * 3) * 4
@@ -324,7 +352,7 @@ def run_ours(args):
                     "l2": "inputs rotate over %d batches (%.0f MB) > 126 MB L2" % (n_pool, n_pool * bytes_per_batch / 1e6),
                     "optimizer": "Adam (train_nerf.py:133-161) inside the step", "launch": launch_mode,
                     "loss_last_step": loss_now}),
-                "clocks": clk, "gpu_launches": launches,
+                "clocks": clk, "gpu_launches": launches, "render": render,
                 "e2e": {"value": e2e_feat, "unit": UNIT, "h2d_bytes_per_step": h2d_feat, "d2h_bytes_per_step": 4,
                         "steps": e2e_n, "api": "lnb_trainer_step_host, pre-encoded features from pinned host memory"},
                 "e2e_rays": {"value": e2e_rays, "unit": UNIT, "h2d_bytes_per_step": h2d_rays, "d2h_bytes_per_step": 4,
@@ -384,6 +412,7 @@ def main():
     ap.add_argument("--input", default="features", choices=["features", "rays"],
                     help="device-resident batch format: pre-encoded features, or rays (PE fused in the kernel)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-render", action="store_true", help="skip the forward-only frame-render measurement")
     ap.add_argument("--eager", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -1,0 +1,65 @@
+"""Forward-only full-frame rendering and the hosts' small helpers around it.
+
+The reference's render path is the eval block of train_nerf.py:558-700 (make_nerf_video.py only
+stitches ground-truth PNGs): get_rays for one pose, 4-ray chunks through
+nerf_evaluate_and_march, accumulated_color read back, PSNR against the ground truth.  Here a frame is
+one call: all H*W rays go to the device in rays mode, colours come back.
+"""
+import numpy as np
+
+
+def get_rays(height, width, normalized_K, c2w_pose):
+    """Ray origins / directions of every pixel, exactly as train_nerf.py:23-62 builds them
+    (normalised pixel grid linspace(0,1,width), directions NOT normalised, float64)."""
+    rng = np.linspace(0, 1, width)
+    i, j = np.meshgrid(rng, rng, indexing="xy")
+    i, j = i.flatten(), j.flatten()
+    dirs = np.stack([(i - normalized_K[0, 2]) / normalized_K[0, 0],
+                     -(j - normalized_K[1, 2]) / normalized_K[1, 1], -np.ones_like(i)], axis=-1)
+    R, T = c2w_pose[:3, :3], c2w_pose[:3, 3]
+    return T[None, :].repeat(dirs.shape[0], 0), dirs @ R.T
+
+
+def compute_psnr(img1, img2, max_val=1.0):
+    """train_nerf.py:163-183."""
+    mse = np.mean((np.asarray(img1, np.float64) - np.asarray(img2, np.float64)) ** 2)
+    return 20 * np.log10(max_val / np.sqrt(mse))
+
+
+def render_rays(ctx, dims, ws, bs, rays_o, rays_d, t, pe_bands, path="tc", rays_per_call=1 << 18):
+    """Colours [R][3] (numpy float32) of R rays; rays_o/rays_d [R][3] and t [R][S] numpy (float64 as
+    the reference makes them, or float32).  Host buffers in, host buffer out, chunked so the device
+    staging stays bounded."""
+    R = rays_o.shape[0]
+    out = np.empty((R, 3), np.float32)
+    ws = np.ascontiguousarray(ws, np.float32)
+    bs = np.ascontiguousarray(bs, np.float32)
+    for r0 in range(0, R, rays_per_call):
+        r1 = min(R, r0 + rays_per_call)
+        res = ctx.nerf_step_rays(dims, np.ascontiguousarray(rays_o[r0:r1]), np.ascontiguousarray(rays_d[r0:r1]),
+                                 np.ascontiguousarray(t[r0:r1]), pe_bands, ws, bs, target=None, grad=False,
+                                 outputs=("color",), path=path)
+        out[r0:r1] = res["color"]
+    return out
+
+
+def render_frame(ctx, dims, ws, bs, height, width, normalized_K, c2w_pose, n_samples, pe_bands, near=2.0, far=6.0,
+                 path="tc"):
+    """One H x W frame: t = linspace(near, far, S) for every ray (train_nerf.py:589-605)."""
+    o, d = get_rays(height, width, normalized_K, c2w_pose)
+    t = np.broadcast_to(np.linspace(near, far, n_samples)[None, :], (o.shape[0], n_samples))
+    return render_rays(ctx, dims, ws, bs, o, d, np.ascontiguousarray(t), pe_bands, path=path).reshape(height, width, 3)
+
+
+def save_weights(prefix, ws_padded, bs_padded):
+    """The padded (L,max_in,max_out) / (L,max_out) float32 arrays as models/weights.npy /
+    models/biases.npy hold them (the save the reference has commented out, train_nerf.py:559-564)."""
+    np.save(prefix + "weights.npy", np.ascontiguousarray(ws_padded, np.float32))
+    np.save(prefix + "biases.npy", np.ascontiguousarray(bs_padded, np.float32))
+
+
+def load_weights(prefix):
+    ws, bs = np.load(prefix + "weights.npy"), np.load(prefix + "biases.npy")
+    if ws.ndim != 3 or bs.ndim != 2 or ws.shape[0] != bs.shape[0] or ws.shape[2] != bs.shape[1]:
+        raise ValueError("not a padded (L,max_in,max_out) / (L,max_out) weight pair")
+    return ws.astype(np.float32), bs.astype(np.float32)

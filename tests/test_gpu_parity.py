@@ -366,3 +366,25 @@ def test_render_only_and_edge_shapes(ctx, torch_cuda):
     from loma_nerf_b200 import api
     with pytest.raises(api.LnbError):
         ctx.nerf_step([33, 30, 3], cv(case["X"]), cv(case["ws"]), cv(case["bs"]), cv(case["dists"]), cv(case["target"]))
+
+
+def test_render_frame_matches_reference_per_ray_colours(ctx, torch_cuda):
+    """Forward-only frame render (train_nerf.py:581-661): every pixel's accumulated colour, shared
+    linspace depths, against the C oracle fed with the host-built features."""
+    from loma_nerf_b200 import render
+    rng = np.random.default_rng(77)
+    E, S, H = 5, 30, 24
+    dims = O.mlp_dims(3 + 6 * E, 30, 3, 4)
+    ws, bs = O.init_mlp(rng, dims, 1.0)
+    K = np.array([[1.2, 0, 0.5], [0, 1.2, 0.5], [0, 0, 1.0]])
+    c2w = np.eye(4); c2w[:3, 3] = [0.3, -0.2, 4.0]
+    img = render.render_frame(ctx, dims, ws, bs, H, H, K, c2w, S, E, path="f32")
+    o, d = render.get_rays(H, H, K, c2w)
+    pts, dists = O.sample_points(o, d, np.linspace(2.0, 6.0, S))
+    X = O.positional_encoding(pts, E).reshape(H * H * S, -1)
+    f = O.nerf_f64(X, ws, bs, dims, np.zeros((H * H, 3), np.float32), dists, H * H, S)
+    assert img.shape == (H, H, 3)
+    assert rel_err(img.reshape(-1, 3), f["color"]) <= TOL
+    img_tc = render.render_frame(ctx, dims, ws, bs, H, H, K, c2w, S, E, path="tc")
+    assert rel_err(img_tc.reshape(-1, 3), f["color"]) <= 3e-2
+    assert render.compute_psnr(img_tc, img) > 35.0
