@@ -194,9 +194,19 @@ def run_ours(args):
     nP = ws_np.size + bs_np.size
     trainer = api.Trainer(ctx, dims, ws_np, bs_np, optimizer="adam", lr=5e-4)
     grads = trainer.grad_buffer()                           # [d_ws | d_bs | loss] on the device
+    collective = "none"
+    if world > 1:
+        collective = "nccl"
+        if args.collective == "peer" and path == "tc":
+            try:
+                trainer.enable_peer_allreduce()
+                collective = "peer"
+            except Exception as e:
+                _dbg("peer all-reduce unavailable (%s); using NCCL" % str(e)[:120])
+    fused_step = world == 1 or collective == "peer"
 
     def step_body(b):
-        if world == 1:
+        if fused_step:
             trainer.step(**batches[b])                      # fused fwd+bwd kernel, then reduce + Adam
         else:
             trainer.grad(**batches[b])
@@ -215,12 +225,12 @@ def run_ours(args):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     ctx.set_stream(torch.cuda.current_stream(device))
-                    if world == 1:
+                    if fused_step:
                         trainer.step(**batches[b])
                     else:
                         trainer.grad(**batches[b])
                 graphs.append(g)
-            if world > 1:
+            if not fused_step:
                 apply_graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(apply_graph):
                     ctx.set_stream(torch.cuda.current_stream(device))
@@ -238,7 +248,7 @@ def run_ours(args):
     def step(i):
         if graphs:
             graphs[i % n_pool].replay()
-            if world > 1:
+            if not fused_step:
                 dist.all_reduce(grads)
                 apply_graph.replay()
         else:
@@ -351,6 +361,8 @@ def run_ours(args):
                     "path": path, "input": "rays + sample depths (PE fused in the kernel)" if use_rays else "pre-encoded features (the reference .so's layout)",
                     "l2": "inputs rotate over %d batches (%.0f MB) > 126 MB L2" % (n_pool, n_pool * bytes_per_batch / 1e6),
                     "optimizer": "Adam (train_nerf.py:133-161) inside the step", "launch": launch_mode,
+                    "collective": {"none": "none (1 GPU)", "nccl": "NCCL all-reduce of [d_ws|d_bs|loss] between gradient and optimiser kernels",
+                                   "peer": "one-shot all-reduce over NVLink peer memory fused into the reduction+Adam kernel"}[collective],
                     "loss_last_step": loss_now}),
                 "clocks": clk, "gpu_launches": launches, "render": render,
                 "e2e": {"value": e2e_feat, "unit": UNIT, "h2d_bytes_per_step": h2d_feat, "d2h_bytes_per_step": 4,
@@ -412,6 +424,8 @@ def main():
     ap.add_argument("--input", default="features", choices=["features", "rays"],
                     help="device-resident batch format: pre-encoded features, or rays (PE fused in the kernel)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="N>1: gradient exchange fused into the step over peer memory, or a separate NCCL all-reduce")
     ap.add_argument("--no-render", action="store_true", help="skip the forward-only frame-render measurement")
     ap.add_argument("--eager", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()

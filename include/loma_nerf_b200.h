@@ -254,6 +254,15 @@ LNB_API int lnb_trainer_grad(lnb_trainer *t, const lnb_step_args *batch, int ner
 LNB_API int lnb_trainer_apply(lnb_trainer *t);
 LNB_API float *lnb_trainer_grad_buffer(lnb_trainer *t, long long *n_floats);
 LNB_API float *lnb_trainer_params(lnb_trainer *t, long long *n_w, long long *n_b);
+/* Peer-memory gradient all-reduce for the ranks of one box (one process per GPU), fused into the
+ * tensor-core step's reduction kernel: every rank exports a 64-byte CUDA IPC handle of its exchange
+ * buffer, the host exchanges the handles (any transport), every rank attaches all `world` handles
+ * (rank-major, 64 bytes each).  From then on lnb_trainer_step[_host] sums the gradients (and the
+ * loss) of all ranks over NVLink inside its second kernel -- no separate collective -- and all ranks
+ * must step in lockstep.  lnb_trainer_comm_status: 0 fine, 1 a peer never showed up. */
+LNB_API int lnb_trainer_comm_export(lnb_trainer *t, void *handle64);
+LNB_API int lnb_trainer_comm_attach(lnb_trainer *t, int rank, int world, const void *handles);
+LNB_API int lnb_trainer_comm_status(lnb_trainer *t);
 /* synchronises; any pointer may be NULL */
 LNB_API int lnb_trainer_read(lnb_trainer *t, float *ws_host, float *bs_host, float *loss_host);
 

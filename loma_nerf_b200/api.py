@@ -318,6 +318,25 @@ class Trainer:
     def apply(self):
         self.ctx._check(self.lib.lnb_trainer_apply(self.h))
 
+    def enable_peer_allreduce(self, group=None):
+        """Fuse the gradient all-reduce into the step (tensor-core path, GPUs of one box): exchanges
+        CUDA IPC handles of the per-rank exchange buffers through torch.distributed and attaches
+        them.  Afterwards step()/step_host() sum gradients and loss over all ranks inside the
+        reduction kernel (NVLink peer loads) and every rank must step in lockstep."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        h = ctypes.create_string_buffer(64)
+        self.ctx._check(self.lib.lnb_trainer_comm_export(self.h, h))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(h.raw), group=group)
+        blob = ctypes.create_string_buffer(b"".join(handles), 64 * world)
+        self.ctx._check(self.lib.lnb_trainer_comm_attach(self.h, rank, world, blob))
+        dist.barrier(group)
+        return True
+
+    def comm_status(self):
+        return int(self.lib.lnb_trainer_comm_status(self.h))
+
     def grad_buffer(self):
         """torch view of the flat [d_ws | d_bs | loss] device buffer (for dist.all_reduce)."""
         n = ctypes.c_longlong()

@@ -781,11 +781,25 @@ __device__ __forceinline__ float adam_one(const AdamArgs &a, long long i, float 
     return pnew;
 }
 
+// One-shot all-reduce over NVLink peer memory, fused into the gradient reduction (SURVEY.md 8e:
+// 12 KB per step, latency-bound).  Every rank writes its reduced gradient into its own comm buffer
+// (double-buffered by step parity), publishes the step number with a system-scope release, waits
+// for every peer's flag with system-scope acquires, and sums all ranks' vectors IN RANK ORDER so
+// that every rank computes bit-identical totals; the optimiser update follows in the same kernel.
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // reduce the per-CTA partials in a fixed order; apply the seed; accumulate into (or overwrite) the
 // caller's buffers; optionally apply Adam to the parameter and refresh the bf16 weight image
 __global__ void __launch_bounds__(1024) tc_reduce_kernel(const float *__restrict__ part, int n_part, int part_stride, TcParams p,
                                  float *__restrict__ d_ws, float *__restrict__ d_bs, float *__restrict__ loss,
-                                 float seed_value, int seed_is_loss, int overwrite, int fuse_adam, AdamArgs ad, ImgMap im)
+                                 float seed_value, int seed_is_loss, int overwrite, int fuse_adam, AdamArgs ad, ImgMap im,
+                                 lnb_tc_comm cm)
 {
     __shared__ float sloss;
     // every block sums the loss partials itself (same order everywhere) so the seed needs no second pass
@@ -817,17 +831,60 @@ __global__ void __launch_bounds__(1024) tc_reduce_kernel(const float *__restrict
     }
     acc[grp][el] = s;
     __syncthreads();
-    if (grp == 0 && e_glob < n_el) {
+    float g_local = 0.0f;
+    if (grp == 0) {
         s = 0.0f;
 #pragma unroll
         for (int w2 = 0; w2 < 32; ++w2) s += acc[w2][el];
+        g_local = scale * s;
+    }
+    float loss_total = sloss;
+    if (cm.world > 1) {
+        // ---- exchange: publish my vector, wait for the peers, sum in rank order
+        const unsigned step = (unsigned)ad.t_dev[0], par = step & 1u;
+        if (grp == 0 && e_glob < n_el) cm.my_data[(size_t)par * cm.n_slot + e_glob] = g_local;
+        if (blockIdx.x == 0 && threadIdx.x == 0) cm.my_data[(size_t)par * cm.n_slot + n_el] = sloss;
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (atomicAdd(cm.done_counter, 1u) == gridDim.x - 1) { // last block of this rank: everything is written
+                *cm.done_counter = 0u;
+                __threadfence_system();
+                st_release_sys(cm.my_flags + par, step);
+            }
+            for (int r = 0; r < cm.world; ++r) {
+                if (r == cm.rank) continue;
+                unsigned spins = 0;
+                while ((int)(ld_acquire_sys(cm.peer_flags[r] + par) - step) < 0) {
+                    __nanosleep(64);
+                    if (++spins > (1u << 22)) { *cm.status = 1; break; } // a lost peer must not hang the GPU
+                }
+            }
+        }
+        __syncthreads();
+        if (grp == 0 && e_glob < n_el) {
+            float tot = 0.0f;
+            for (int r = 0; r < cm.world; ++r)
+                tot += r == cm.rank ? g_local : __ldcv(cm.peer_data[r] + (size_t)par * cm.n_slot + e_glob);
+            g_local = tot;
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            float tot = 0.0f;
+            for (int r = 0; r < cm.world; ++r)
+                tot += r == cm.rank ? sloss : __ldcv(cm.peer_data[r] + (size_t)par * cm.n_slot + n_el);
+            loss_total = tot;
+            if (loss) loss[0] = tot;
+        }
+    }
+    (void)loss_total;
+    if (grp == 0 && e_glob < n_el) {
         int e = e_glob + 1, l = 0;
         while (l + 1 < p.L && e >= p.part_off[l + 1]) ++l;
         e -= p.part_off[l];
         const int out_l = p.dims[l + 1], k = e / out_l, j = e % out_l;
         const bool is_w = k < p.dims[l];
         float *dst = is_w ? d_ws + ((size_t)l * p.max_in + k) * p.max_out + j : d_bs + (size_t)l * p.max_out + j;
-        const float g = overwrite ? scale * s : *dst + scale * s;
+        const float g = overwrite ? g_local : *dst + g_local;
         *dst = g;
         if (fuse_adam) {
             const long long pi = is_w ? ((long long)l * p.max_in + k) * p.max_out + j : ad.n_w + (long long)l * p.max_out + j;
@@ -1067,7 +1124,8 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
                             (long long)L * mlp->max_in * mlp->max_out, ex->m == nullptr};
     tc_reduce_kernel<<<blocks, 1024, 0, ctx->stream>>>(p.part, grid, p.part_stride, p, a->want_grad ? a->d_ws : nullptr,
                                                       a->want_grad ? a->d_bs : nullptr, loss, seed_val, seed_is_loss,
-                                                      ex ? ex->overwrite_grads : 0, fuse, ad, im);
+                                                      ex ? ex->overwrite_grads : 0, fuse, ad, im,
+                                                      (ex && ex->comm && fuse && !seed_is_loss) ? *ex->comm : lnb_tc_comm{});
     LNB_CHECK_LAUNCH();
     return LNB_OK;
 }

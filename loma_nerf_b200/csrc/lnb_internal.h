@@ -146,7 +146,20 @@ int lnb_launch_axpy2d(lnb_ctx *ctx, float *dst, long long ldd, const float *src,
 //   overwrite_grads : d_ws / d_bs are written (=) instead of accumulated (+=)
 //   fuse_adam       : the reduce kernel applies the reference's Adam update to (param, m, v) with
 //                     the device step counter and refreshes `wimg_out` (the next step's image)
+// peer-memory all-reduce state of one rank (trainer.cu sets it up; fused_tc.cu uses it)
+struct lnb_tc_comm {
+    int world = 0, rank = 0;
+    unsigned *my_flags = nullptr;     // [2] step number published per parity slot
+    float *my_data = nullptr;         // [2][n_slot]
+    const unsigned *peer_flags[8] = {};
+    const float *peer_data[8] = {};
+    int n_slot = 0;                   // gradient elements + 1 (the loss)
+    unsigned *done_counter = nullptr; // local: the last block publishes the flag
+    int *status = nullptr;            // local: 1 after a spin timeout
+};
+
 struct lnb_tc_extra {
+    const lnb_tc_comm *comm = nullptr; // when set (and fuse_adam): gradients are summed over the ranks
     const void *wimg = nullptr;
     int overwrite_grads = 0;
     int fuse_adam = 0;

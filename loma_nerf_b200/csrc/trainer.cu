@@ -24,7 +24,19 @@ struct lnb_trainer {
     void *wimg = nullptr;    // tensor-core weight image, kept in sync with params
     bool tc_ok = false;
     bool t_bumped = false;   // the last lnb_trainer_grad already incremented *t_dev
+    // peer-memory all-reduce (lnb_trainer_comm_*): header [flags 2 | counter | status | pad] + data
+    char *comm_buf = nullptr;
+    size_t comm_bytes = 0;
+    lnb_tc_comm comm{};
+    void *peer_base[8] = {};
 };
+
+static int comm_slots(const lnb_trainer *t)
+{
+    int n = 1;
+    for (int l = 0; l < t->mlp.n_layers; ++l) n += (t->mlp.dims[l] + 1) * t->mlp.dims[l + 1];
+    return n; // live gradient elements + the loss
+}
 
 extern "C" int lnb_trainer_create(lnb_ctx *ctx, const lnb_mlp *mlp, const float *ws_host, const float *bs_host,
                                   int optimizer, double lr, double beta1, double beta2, double eps, lnb_trainer **out)
@@ -67,6 +79,9 @@ extern "C" void lnb_trainer_destroy(lnb_trainer *t)
     if (!t) return;
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
+    for (int r = 0; r < 8; ++r)
+        if (t->peer_base[r]) cudaIpcCloseMemHandle(t->peer_base[r]);
+    if (t->comm_buf) cudaFree(t->comm_buf);
     cudaFree(t->params); cudaFree(t->grads); cudaFree(t->m); cudaFree(t->v); cudaFree(t->t_dev);
     if (t->wimg) cudaFree(t->wimg);
     delete t;
@@ -88,6 +103,7 @@ static int trainer_run(lnb_trainer *t, const lnb_step_args *batch, int nerf, boo
         lnb_tc_extra ex;
         ex.wimg = t->wimg; ex.overwrite_grads = 1; ex.t_dev = t->t_dev;
         if (fuse_update) {
+            if (t->comm.world > 1) ex.comm = &t->comm;
             ex.fuse_adam = 1; ex.param = t->params; ex.m = t->opt == LNB_OPT_ADAM ? t->m : nullptr; ex.v = t->v;
             ex.lr = t->lr; ex.b1 = t->b1; ex.b2 = t->b2; ex.eps = t->eps; ex.wimg_out = t->wimg;
         }
@@ -199,6 +215,67 @@ extern "C" int lnb_trainer_step_host(lnb_trainer *t, const lnb_step_args *batch,
     LNB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (loss_out) *loss_out = *pl;
     return LNB_OK;
+}
+
+// ---- peer-memory all-reduce set-up: export my comm buffer, attach everybody's -------------------
+extern "C" int lnb_trainer_comm_export(lnb_trainer *t, void *handle64)
+{
+    if (!t || !handle64) return LNB_ERR_ARG;
+    lnb_ctx *ctx = t->ctx;
+    LNB_ARG(t->tc_ok, "peer all-reduce is part of the tensor-core trainer step");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
+    if (!t->comm_buf) {
+        t->comm_bytes = 256 + 2 * (size_t)comm_slots(t) * sizeof(float);
+        LNB_CUDA(cudaMalloc((void **)&t->comm_buf, t->comm_bytes));
+        LNB_CUDA(cudaMemset(t->comm_buf, 0, t->comm_bytes));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    LNB_CUDA(cudaIpcGetMemHandle(&h, t->comm_buf));
+    memcpy(handle64, &h, 64);
+    return LNB_OK;
+}
+
+extern "C" int lnb_trainer_comm_attach(lnb_trainer *t, int rank, int world, const void *handles)
+{
+    if (!t || !handles) return LNB_ERR_ARG;
+    lnb_ctx *ctx = t->ctx;
+    LNB_ARG(world >= 1 && world <= 8 && rank >= 0 && rank < world, "comm: 1 <= world <= 8");
+    LNB_ARG(t->comm_buf, "comm: call lnb_trainer_comm_export first");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
+    const int n_slot = comm_slots(t);
+    lnb_tc_comm c{};
+    c.world = world; c.rank = rank; c.n_slot = n_slot;
+    c.my_flags = reinterpret_cast<unsigned *>(t->comm_buf);
+    c.done_counter = reinterpret_cast<unsigned *>(t->comm_buf) + 2;
+    c.status = reinterpret_cast<int *>(t->comm_buf) + 3;
+    c.my_data = reinterpret_cast<float *>(t->comm_buf + 256);
+    for (int r = 0; r < world; ++r) {
+        char *base = t->comm_buf;
+        if (r != rank) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const char *)handles + (size_t)r * 64, 64);
+            void *p = nullptr;
+            LNB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            t->peer_base[r] = p;
+            base = (char *)p;
+        }
+        c.peer_flags[r] = reinterpret_cast<const unsigned *>(base);
+        c.peer_data[r] = reinterpret_cast<const float *>(base + 256);
+    }
+    t->comm = c;
+    return LNB_OK;
+}
+
+// 0 = fine; 1 = a peer's flag never arrived (the step went on with what it had). Synchronises.
+extern "C" int lnb_trainer_comm_status(lnb_trainer *t)
+{
+    if (!t || !t->comm_buf) return 0;
+    int st = 0;
+    cudaSetDevice(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+    cudaMemcpy(&st, t->comm_buf + 12, 4, cudaMemcpyDeviceToHost);
+    return st;
 }
 
 extern "C" float *lnb_trainer_grad_buffer(lnb_trainer *t, long long *n_floats)
