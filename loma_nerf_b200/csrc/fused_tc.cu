@@ -840,40 +840,36 @@ __global__ void __launch_bounds__(1024) tc_reduce_kernel(const float *__restrict
     }
     float loss_total = sloss;
     if (cm.world > 1) {
-        // ---- exchange: publish my vector, wait for the peers, sum in rank order
+        // ---- exchange (low-latency push): every element travels as one 8-byte {value, step} word
+        // written straight into each peer's receive slot; the receiver polls its LOCAL slot until the
+        // step tag matches -- no fences, no separate flags, one NVLink traversal.  Slots are double-
+        // buffered by step parity; ranks cannot drift more than one step apart (each needs every
+        // peer's words of step s to finish step s).
         const unsigned step = (unsigned)ad.t_dev[0], par = step & 1u;
-        if (grp == 0 && e_glob < n_el) cm.my_data[(size_t)par * cm.n_slot + e_glob] = g_local;
-        if (blockIdx.x == 0 && threadIdx.x == 0) cm.my_data[(size_t)par * cm.n_slot + n_el] = sloss;
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            if (atomicAdd(cm.done_counter, 1u) == gridDim.x - 1) { // last block of this rank: everything is written
-                *cm.done_counter = 0u;
-                __threadfence_system();
-                st_release_sys(cm.my_flags + par, step);
-            }
+        const bool mine = grp == 0 && e_glob < n_el;
+        const bool loss_thread = blockIdx.x == 0 && threadIdx.x == 32;
+        if (mine || loss_thread) {
+            const int slot = mine ? e_glob : n_el;
+            const float val = mine ? g_local : sloss;
+            const unsigned long long word = ((unsigned long long)step << 32) | (unsigned long long)__float_as_uint(val);
+            const size_t off = ((size_t)par * cm.world + cm.rank) * cm.n_slot + slot;
+            for (int r = 0; r < cm.world; ++r)
+                if (r != cm.rank) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(cm.peer_recv[r] + off), "l"(word) : "memory");
+            float tot = 0.0f;
             for (int r = 0; r < cm.world; ++r) {
-                if (r == cm.rank) continue;
+                if (r == cm.rank) { tot += val; continue; }
+                const unsigned long long *src = cm.my_recv + ((size_t)par * cm.world + r) * cm.n_slot + slot;
+                unsigned long long w;
                 unsigned spins = 0;
-                while ((int)(ld_acquire_sys(cm.peer_flags[r] + par) - step) < 0) {
-                    __nanosleep(64);
-                    if (++spins > (1u << 22)) { *cm.status = 1; break; } // a lost peer must not hang the GPU
+                for (;;) {
+                    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+                    if ((unsigned)(w >> 32) == step) break;
+                    if (++spins > (1u << 24)) { *cm.status = 1; break; } // a lost peer must not hang the GPU
                 }
+                tot += __uint_as_float((unsigned)w);
             }
-        }
-        __syncthreads();
-        if (grp == 0 && e_glob < n_el) {
-            float tot = 0.0f;
-            for (int r = 0; r < cm.world; ++r)
-                tot += r == cm.rank ? g_local : __ldcv(cm.peer_data[r] + (size_t)par * cm.n_slot + e_glob);
-            g_local = tot;
-        }
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            float tot = 0.0f;
-            for (int r = 0; r < cm.world; ++r)
-                tot += r == cm.rank ? sloss : __ldcv(cm.peer_data[r] + (size_t)par * cm.n_slot + n_el);
-            loss_total = tot;
-            if (loss) loss[0] = tot;
+            if (mine) g_local = tot;
+            else { loss_total = tot; if (loss) loss[0] = tot; }
         }
     }
     (void)loss_total;

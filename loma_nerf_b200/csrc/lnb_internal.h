@@ -149,13 +149,10 @@ int lnb_launch_axpy2d(lnb_ctx *ctx, float *dst, long long ldd, const float *src,
 // peer-memory all-reduce state of one rank (trainer.cu sets it up; fused_tc.cu uses it)
 struct lnb_tc_comm {
     int world = 0, rank = 0;
-    unsigned *my_flags = nullptr;     // [2] step number published per parity slot
-    float *my_data = nullptr;         // [2][n_slot]
-    const unsigned *peer_flags[8] = {};
-    const float *peer_data[8] = {};
-    int n_slot = 0;                   // gradient elements + 1 (the loss)
-    unsigned *done_counter = nullptr; // local: the last block publishes the flag
-    int *status = nullptr;            // local: 1 after a spin timeout
+    int n_slot = 0;                          // gradient elements + 1 (the loss)
+    unsigned long long *my_recv = nullptr;   // [2 parities][world senders][n_slot] {step<<32 | float bits}
+    unsigned long long *peer_recv[8] = {};   // the same array on every rank (peer-mapped; [rank] = own)
+    int *status = nullptr;                   // local: 1 after a spin timeout
 };
 
 struct lnb_tc_extra {

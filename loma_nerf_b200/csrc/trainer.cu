@@ -24,7 +24,7 @@ struct lnb_trainer {
     void *wimg = nullptr;    // tensor-core weight image, kept in sync with params
     bool tc_ok = false;
     bool t_bumped = false;   // the last lnb_trainer_grad already incremented *t_dev
-    // peer-memory all-reduce (lnb_trainer_comm_*): header [flags 2 | counter | status | pad] + data
+    // peer-memory all-reduce (lnb_trainer_comm_*): header [status | pad] + receive slots for 8 senders
     char *comm_buf = nullptr;
     size_t comm_bytes = 0;
     lnb_tc_comm comm{};
@@ -225,7 +225,7 @@ extern "C" int lnb_trainer_comm_export(lnb_trainer *t, void *handle64)
     LNB_ARG(t->tc_ok, "peer all-reduce is part of the tensor-core trainer step");
     if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
     if (!t->comm_buf) {
-        t->comm_bytes = 256 + 2 * (size_t)comm_slots(t) * sizeof(float);
+        t->comm_bytes = 256 + 2 * 8 * (size_t)comm_slots(t) * sizeof(unsigned long long);
         LNB_CUDA(cudaMalloc((void **)&t->comm_buf, t->comm_bytes));
         LNB_CUDA(cudaMemset(t->comm_buf, 0, t->comm_bytes));
     }
@@ -246,10 +246,8 @@ extern "C" int lnb_trainer_comm_attach(lnb_trainer *t, int rank, int world, cons
     const int n_slot = comm_slots(t);
     lnb_tc_comm c{};
     c.world = world; c.rank = rank; c.n_slot = n_slot;
-    c.my_flags = reinterpret_cast<unsigned *>(t->comm_buf);
-    c.done_counter = reinterpret_cast<unsigned *>(t->comm_buf) + 2;
-    c.status = reinterpret_cast<int *>(t->comm_buf) + 3;
-    c.my_data = reinterpret_cast<float *>(t->comm_buf + 256);
+    c.status = reinterpret_cast<int *>(t->comm_buf);
+    c.my_recv = reinterpret_cast<unsigned long long *>(t->comm_buf + 256);
     for (int r = 0; r < world; ++r) {
         char *base = t->comm_buf;
         if (r != rank) {
@@ -260,8 +258,7 @@ extern "C" int lnb_trainer_comm_attach(lnb_trainer *t, int rank, int world, cons
             t->peer_base[r] = p;
             base = (char *)p;
         }
-        c.peer_flags[r] = reinterpret_cast<const unsigned *>(base);
-        c.peer_data[r] = reinterpret_cast<const float *>(base + 256);
+        c.peer_recv[r] = reinterpret_cast<unsigned long long *>(base + 256);
     }
     t->comm = c;
     return LNB_OK;
@@ -274,7 +271,7 @@ extern "C" int lnb_trainer_comm_status(lnb_trainer *t)
     int st = 0;
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
-    cudaMemcpy(&st, t->comm_buf + 12, 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(&st, t->comm_buf, 4, cudaMemcpyDeviceToHost);
     return st;
 }
 
