@@ -401,9 +401,13 @@ def run_ours(args):
             from oracle import cpu_bench
             cores = cpu_bench.host_cores()
             r = cpu_bench.run(cores, 40, S=S)
+            r1 = cpu_bench.run(1, 40, S=S)
             line["cpu_baseline"] = {"value": r["samples"] / r["seconds"], "unit": UNIT, "cores": cores, "kind": r["kind"],
                                     "sample": "%d cores x 40 chunks x 256 samples (4 rays x 64), forward + grad call per chunk, "
-                                              "time inside the C calls only" % cores}
+                                              "time inside the C calls only" % cores,
+                                    "value_1core": r1["samples"] / r1["seconds"],
+                                    "note": "the reference's own end-to-end rate is ~1e3 samples/s: its Python marshalling "
+                                            "(mlp_utils.py:33-164) costs ~0.1 s per 120-sample chunk (SURVEY.md 6); excluded here"}
         print(json.dumps(line))
     trainer.close()
     if world > 1:

@@ -37,3 +37,24 @@ def test_shipped_reference_model_layout_is_the_padded_layout():
         render.save_weights(d + os.sep, np.zeros((3, 16, 16)), np.zeros((3, 16)))
         ws, bs = render.load_weights(d + os.sep)
         assert ws.shape == (3, 16, 16) and bs.shape == (3, 16) and ws.dtype == np.float32
+
+
+def test_blender_scene_reader_follows_the_reference_conventions(tmp_path):
+    import json
+    from PIL import Image
+    from loma_nerf_b200.dataset import BlenderScene
+    os.makedirs(tmp_path / "train")
+    rng = np.random.default_rng(1)
+    frames = []
+    for i in range(3):
+        Image.fromarray(rng.integers(0, 255, (8, 8, 4), dtype=np.uint8), "RGBA").save(tmp_path / "train" / ("r_%d.png" % i))
+        pose = np.eye(4); pose[:3, 3] = [i, 0, 4.0]
+        frames.append({"file_path": "./train/r_%d" % i, "transform_matrix": pose.tolist()})
+    json.dump({"camera_angle_x": 0.6911, "frames": frames}, open(tmp_path / "transforms_train.json", "w"))
+    sc = BlenderScene(str(tmp_path), img_size=4, phase="train")
+    assert len(sc) == 3
+    s = sc[1]
+    assert s["image"].shape == (4, 4, 3) and s["image"].dtype == np.float32 and 0.0 <= s["image"].min() and s["image"].max() <= 1.0
+    assert np.isclose(s["focal_length"], 0.5 / np.tan(0.5 * 0.6911))      # dataloader.py:54
+    assert np.array_equal(s["pose"][:3, 3], [1, 0, 4.0])
+    assert np.isclose(sc.normalized_K[0, 0], s["focal_length"]) and sc.normalized_K[0, 2] == 0.5
