@@ -295,7 +295,7 @@ int step_layerwise(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, boo
     int max_w = 0;
     for (int l = 0; l <= L; ++l) max_w = mlp->dims[l] > max_w ? mlp->dims[l] : max_w;
     int n_chunks = (N + 511) / 512;
-    if (n_chunks > 2 * ctx->sm_count) n_chunks = 2 * ctx->sm_count;
+    if (n_chunks > 4 * ctx->sm_count) n_chunks = 4 * ctx->sm_count;
     if (n_chunks < 1) n_chunks = 1;
 
     // ---- arena plan

@@ -18,10 +18,13 @@ __device__ __forceinline__ float sigmoidf_(float z) { return 1.0f / (1.0f + expf
 template <int BM, int BN>
 __global__ void __launch_bounds__(256) row_gemm_kernel(lnb_gemm_args g)
 {
-    constexpr int BK = 16;
+    // K slab of 40: the reference's layer widths (22..33 inputs, 16..30 hidden) fit one slab.  A is
+    // kept row-major in shared memory (pitch BK+1): a warp stages one row segment per load
+    // (coalesced, conflict-free) and reads 4 rows x 1 scalar per k (4 distinct banks + broadcast).
+    constexpr int BK = 40;
     static_assert(BM * BN == 4096, "256 threads x 4x4");
     constexpr int TXN = BN / 4; // threads along n
-    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ float As[BM][BK + 1];
     __shared__ __align__(16) float Bs[BK][BN + 4];
     const int t = threadIdx.x;
     const int tx = t % TXN, ty = t / TXN;
@@ -34,29 +37,27 @@ __global__ void __launch_bounds__(256) row_gemm_kernel(lnb_gemm_args g)
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
     for (int k0 = 0; k0 < g.k_dim; k0 += BK) {
-        // A tile: BM x BK, consecutive threads along k
-#pragma unroll
+        const int kmax = g.k_dim - k0 < BK ? g.k_dim - k0 : BK;
         for (int e = t; e < BM * BK; e += 256) {
-            int i = e / BK, kk = e % BK;
-            long long r = row0 + i;
+            const int i = e / BK, kk = e % BK;
+            const long long r = row0 + i;
             float v = 0.0f;
-            if (r < g.a_rows && k0 + kk < g.k_dim) v = __ldg(g.A + r * g.lda + (k0 + kk));
-            As[kk][i] = v;
+            if (r < g.a_rows && kk < kmax) v = __ldg(g.A + r * g.lda + (k0 + kk));
+            As[i][kk] = v;
         }
-#pragma unroll
         for (int e = t; e < BK * BN; e += 256) {
-            int kk = e / BN, n = e % BN;
+            const int kk = e / BN, n = e % BN;
             float v = 0.0f;
-            if (k0 + kk < g.k_dim && n0 + n < g.n_dim)
+            if (kk < kmax && n0 + n < g.n_dim)
                 v = __ldg(g.B + (long long)(k0 + kk) * g.sbk + (long long)(n0 + n) * g.sbn);
             Bs[kk][n] = v;
         }
         __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < BK; ++kk) {
-            float4 a = *reinterpret_cast<const float4 *>(&As[kk][ty * 4]);
-            float4 b = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
-            float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll 4
+        for (int kk = 0; kk < kmax; ++kk) {
+            const float4 b = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
+            const float av[4] = {As[ty * 4][kk], As[ty * 4 + 1][kk], As[ty * 4 + 2][kk], As[ty * 4 + 3][kk]};
+            const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -152,6 +153,73 @@ dw_partials_kernel(const float *__restrict__ H, int ldh, const float *__restrict
             if (j < out_dim) out[(size_t)k * out_dim + j] = acc[a][b];
         }
     }
+}
+
+// Fast path for narrow layers (in_dim + 1 <= KP <= 64, out_dim <= 32): one warp per row, lane j
+// owns output column j and keeps the whole column dW[0..in_dim][j] (+ the bias row) in registers;
+// the row of H is staged in shared memory and read back as broadcast float4s.  8 warps stride
+// over the block's rows and are combined through shared memory in warp order (deterministic).
+template <int KP>
+__global__ void __launch_bounds__(256)
+dw_rows_kernel(const float *__restrict__ H, int ldh, const float *__restrict__ dZ, int ldz,
+               float *__restrict__ partial, int in_dim, int out_dim, long long rows,
+               long long rows_per_chunk)
+{
+    __shared__ __align__(16) float hs[8][2][KP];
+    __shared__ float accs[KP][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int e = threadIdx.x; e < KP * 33; e += 256) (&accs[0][0])[e] = 0.0f;
+    const long long r_begin = (long long)blockIdx.x * rows_per_chunk;
+    long long r_end = r_begin + rows_per_chunk;
+    if (r_end > rows) r_end = rows;
+    float acc[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) acc[k] = 0.0f;
+    constexpr int NH = (KP + 31) / 32; // H elements per lane per row
+    // two rows per iteration (r and r + 8), the next pair's loads issued before this pair's math
+    auto load_row = [&](long long r, float (&h)[NH], float &dz) {
+#pragma unroll
+        for (int q = 0; q < NH; ++q) {
+            const int k = lane + 32 * q;
+            h[q] = (r < r_end && k < in_dim) ? __ldg(H + r * ldh + k) : ((r < r_end && k == in_dim) ? 1.0f : 0.0f);
+        }
+        dz = (r < r_end && lane < out_dim) ? __ldg(dZ + r * ldz + lane) : 0.0f;
+    };
+    float ha[NH], hb[NH], dza, dzb;
+    long long r = r_begin + warp;
+    load_row(r, ha, dza);
+    load_row(r + 8, hb, dzb);
+    for (; r < r_end; r += 16) {
+#pragma unroll
+        for (int q = 0; q < NH; ++q) {
+            const int k = lane + 32 * q;
+            if (k < KP) { hs[warp][0][k] = ha[q]; hs[warp][1][k] = hb[q]; }
+        }
+        const float za = dza, zb = dzb;
+        load_row(r + 16, ha, dza);
+        load_row(r + 24, hb, dzb);
+        __syncwarp();
+#pragma unroll
+        for (int k4 = 0; k4 < KP / 4; ++k4) {
+            const float4 h0 = *reinterpret_cast<const float4 *>(&hs[warp][0][k4 * 4]);
+            const float4 h1 = *reinterpret_cast<const float4 *>(&hs[warp][1][k4 * 4]);
+            acc[k4 * 4] = fmaf(h1.x, zb, fmaf(h0.x, za, acc[k4 * 4]));
+            acc[k4 * 4 + 1] = fmaf(h1.y, zb, fmaf(h0.y, za, acc[k4 * 4 + 1]));
+            acc[k4 * 4 + 2] = fmaf(h1.z, zb, fmaf(h0.z, za, acc[k4 * 4 + 2]));
+            acc[k4 * 4 + 3] = fmaf(h1.w, zb, fmaf(h0.w, za, acc[k4 * 4 + 3]));
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int w = 0; w < 8; ++w) { // warps add in a fixed order: the result is deterministic
+        if (warp == w) {
+#pragma unroll
+            for (int k = 0; k < KP; ++k) accs[k][lane] += acc[k];
+        }
+        __syncthreads();
+    }
+    float *out = partial + (size_t)blockIdx.x * (size_t)(in_dim + 1) * out_dim;
+    for (int e = threadIdx.x; e < (in_dim + 1) * out_dim; e += 256) out[e] = accs[e / out_dim][e % out_dim];
 }
 
 __global__ void dw_reduce_kernel(const float *__restrict__ partial, int n_chunks, int in_dim,
@@ -437,6 +505,17 @@ int lnb_launch_dw_partials(lnb_ctx *ctx, const float *H, int ldh, const float *d
     if (rows <= 0 || n_chunks <= 0) return LNB_OK;
     long long rpc = ((long long)rows + n_chunks - 1) / n_chunks;
     rpc = (rpc + 31) / 32 * 32;
+    if (out_dim <= 32 && in_dim + 1 <= 64) {
+        const int kp = (in_dim + 1 + 15) / 16 * 16;
+#define LNB_DWR(KPV) dw_rows_kernel<KPV><<<(unsigned)n_chunks, 256, 0, ctx->stream>>>(H, ldh, dZ, ldz, partial, in_dim, out_dim, rows, rpc)
+        if (kp == 16) LNB_DWR(16);
+        else if (kp == 32) LNB_DWR(32);
+        else if (kp == 48) LNB_DWR(48);
+        else LNB_DWR(64);
+#undef LNB_DWR
+        LNB_CHECK_LAUNCH();
+        return LNB_OK;
+    }
     const int tj = out_dim <= 32 ? 2 : 4;
     const int tk = (in_dim + 1) <= 32 ? 2 : ((in_dim + 1) <= 48 ? 3 : 4);
     dim3 grid((unsigned)n_chunks, (unsigned)((in_dim + 1 + 16 * tk - 1) / (16 * tk)),
