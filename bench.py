@@ -61,7 +61,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -385,8 +385,24 @@ def run_ours(args):
                 # the fused kernel reads pre-encoded features: HBM-bound by SURVEY.md 8d's per-unit bytes
                 peak = peaks.get("hbm_gbs", 6650.0)
                 ach = alg_bytes / sec / 1e9
+                traffic, traffic_src = None, None
+                prof_csv = os.path.join(ROOT, "profiles", "r01_fused_tc_features_ncu_full_summary.csv")
+                if args.workload == "c2" and os.path.exists(prof_csv):
+                    # DRAM bytes of one launch of this kernel on this workload, from the committed ncu --set full capture
+                    try:
+                        vals = {}
+                        for ln in open(prof_csv):
+                            parts = [c.strip('"') for c in ln.strip().split('","')]
+                            if len(parts) == 3 and parts[0].lstrip('"') in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                                mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(parts[1], None)
+                                if mult:
+                                    vals[parts[0].lstrip('"')] = float(parts[2].rstrip('"')) * mult
+                        if len(vals) == 2:
+                            traffic, traffic_src = sum(vals.values()), "profiles/r01_fused_tc_features_ncu_full_summary.csv"
+                    except Exception:
+                        pass
                 line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                                    "traffic": None, "kernel": prof["kernel"], "us_per_launch": sec * 1e6,
+                                    "traffic": traffic, "traffic_source": traffic_src, "kernel": prof["kernel"], "us_per_launch": sec * 1e6,
                                     "launches_timed": prof["launches"], "algorithmic_bytes_per_launch": alg_bytes,
                                     "algorithmic_tflops": N * fl / sec / 1e12,
                                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"}

@@ -2,7 +2,7 @@
 //
 // These implement the reference's path one stage at a time with every intermediate materialised,
 // which is what the compat ABI needs (the reference hosts read intermediate_outputs, rgba, alpha,
-// cumprod_alpha, weights_samples back) and what the fused kernels (fused_f32.cu, fused_tc.cu) are
+// cumprod_alpha, weights_samples back) and what the fused tensor-core kernel (fused_tc.cu) is
 // checked against on the device.  Reference: /root/reference/scripts/nerf.py:67-304,
 // scripts/mlp_fit.py:39-147 and their reverse (loma_public/reverse_diff.py:576-951).
 #include "lnb_internal.h"
@@ -12,8 +12,8 @@ namespace {
 __device__ __forceinline__ float sigmoidf_(float z) { return 1.0f / (1.0f + expf(0.0f - z)); }
 
 // ------------------------------------------------------------------------------------------------
-// Row GEMM with fused epilogue.  256 threads, thread tile 4x4, block tile (16*BY*... ) see below.
-//   BM x BN block tile, BK = 16.  Thread (tx,ty): rows ty*4.., cols tx*4..
+// Row GEMM with fused epilogue.  256 threads, thread tile 4x4, BM x BN block tile (128x32 or 64x64).
+//   Thread (tx,ty): rows ty*4.., cols tx*4..
 // ------------------------------------------------------------------------------------------------
 template <int BM, int BN>
 __global__ void __launch_bounds__(256) row_gemm_kernel(lnb_gemm_args g)

@@ -107,3 +107,19 @@ def test_marshal_views_are_zero_copy():
     b = marshal.as_ragged(np.arange(6, dtype=np.int32).reshape(3, 2))
     assert b.ptr[2][1] == 5
     assert np.array_equal(marshal.ragged_to_numpy(r.ptr, (2, 3, 4)), r.array)
+
+
+def test_compat_symbols_fail_loudly_without_a_gpu(lib):
+    """On a box without CUDA the drop-in symbols must signal failure the way the reference hosts
+    can see it (NaN loss / NaN outputs, train_nerf.py:486-489), never compute on the host."""
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from loma_nerf_b200 import compiler, marshal
+    l2 = compiler.bind()
+    a = marshal.as_ragged(np.array([[1, 2], [3, 4], [5, 6]], np.float32))
+    b = marshal.as_ragged(np.array([[100], [200]], np.float32))
+    c = marshal.as_ragged(np.zeros((3, 1), np.float32))
+    l2.mult_a_b(a.ptr, 3, 2, b.ptr, 2, 1, c.ptr)
+    assert np.isnan(c.array).all()
