@@ -388,3 +388,82 @@ def test_render_frame_matches_reference_per_ray_colours(ctx, torch_cuda):
     img_tc = render.render_frame(ctx, dims, ws, bs, H, H, K, c2w, S, E, path="tc")
     assert rel_err(img_tc.reshape(-1, 3), f["color"]) <= 3e-2
     assert render.compute_psnr(img_tc, img) > 35.0
+
+
+def _ragged_like_the_reference(arr):
+    """float** / float*** built the way the reference hosts build them (mlp_utils.py:33-118): every
+    row is its OWN ctypes allocation (not a view of one contiguous block), values copied in."""
+    import ctypes
+    from ctypes import POINTER, c_float, cast
+    a = np.asarray(arr, np.float32)
+    fp = POINTER(c_float)
+    keep = []
+    if a.ndim == 2:
+        tab = (fp * a.shape[0])()
+        for i in range(a.shape[0]):
+            row = (c_float * a.shape[1])(*a[i].tolist())
+            keep.append(row)
+            tab[i] = cast(row, fp)
+        return cast(tab, POINTER(fp)), keep + [tab]
+    outer = (POINTER(fp) * a.shape[0])()
+    for i in range(a.shape[0]):
+        inner, k = _ragged_like_the_reference(a[i])
+        keep.append(k)
+        outer[i] = inner
+    return cast(outer, POINTER(POINTER(fp))), keep + [outer]
+
+
+def _read_ragged(ptr, shape):
+    out = np.empty(shape, np.float32)
+    for idx in np.ndindex(*shape[:-1]):
+        p = ptr
+        for i in idx:
+            p = p[i]
+        out[idx] = [p[j] for j in range(shape[-1])]
+    return out
+
+
+def test_compat_symbols_with_truly_ragged_rows_as_the_reference_marshaller_builds_them(compat, c_oracle):
+    """Same call sequence as train_nerf.py:325-483: per-row ctypes allocations in, results read back
+    through the ctypes objects element by element."""
+    import ctypes
+    case = O.make_nerf_case(215, 4, 30, stratified=False)           # the reference's own chunk shape
+    R, S, N = 4, 30, 120
+    dims = [int(v) for v in case["dims"]]
+    L, rows, cols = len(dims) - 1, 256, 256
+    wsh, bsh, ish = compat._shapes(dims, rows)
+    lib = compat.lib
+    K = []
+    def rg(a):
+        p, k = _ragged_like_the_reference(a); K.append(k); return p
+    X, ws, bs, tg, dd = rg(case["X"]), rg(case["ws"]), rg(case["bs"]), rg(case["target"]), rg(case["dists"])
+    inter, rgba = rg(np.zeros((L, rows, cols))), rg(np.zeros((R, S, 4)))
+    al, cu, wg, acc = rg(np.zeros((R, S))), rg(np.zeros((R, S))), rg(np.zeros((R, S))), rg(np.zeros((R, 3)))
+    ip = lambda a: O.rows2(a, O.c_int_p)  # noqa: E731
+    loss = lib.nerf_evaluate_and_march(X, N, dims[0], ws, bs, tg, R, 3, L, ip(wsh), ip(bsh), ip(ish), inter, rgba, S, dd,
+                                       al, cu, wg, acc)
+    f = c_oracle.nerf_forward(case["X"], case["ws"], case["bs"], case["dims"], case["target"], case["dists"], R, S, rows=256)
+    assert rel_err(loss, f["loss"]) <= TOL
+    assert rel_err(_read_ragged(acc, (R, 3)), f["color"]) <= TOL
+    assert rel_err(_read_ragged(wg, (R, S)), f["weights"]) <= TOL
+    assert rel_err(_read_ragged(inter, (L, N, 30)), f["inter"][:, :N, :30]) <= TOL
+    # the grad call, exactly the 41 positional arguments (train_nerf.py:395-478), _dreturn = loss
+    z = lambda shape: rg(np.zeros(shape))  # noqa: E731
+    d_X, d_ws, d_bs, d_tg, d_dd = z((N, dims[0])), z(case["ws"].shape), z(case["bs"].shape), z((R, 3)), z((R, S))
+    d_inter, d_rgba, d_al, d_cu, d_wg, d_acc = z((L, rows, cols)), z((R, S, 4)), z((R, S)), z((R, S)), z((R, S)), z((R, 3))
+    p_inter, p_rgba, p_al, p_cu, p_wg, p_acc = z((L, rows, cols)), z((R, S, 4)), z((R, S)), z((R, S)), z((R, S)), z((R, 3))
+    di = [ctypes.c_int(0) for _ in range(7)]
+    zi = lambda a: O.rows2(np.zeros_like(a), O.c_int_p)  # noqa: E731
+    lib.grad_nerf_evaluate_and_march(
+        X, d_X, N, ctypes.byref(di[0]), dims[0], ctypes.byref(di[1]), ws, d_ws, bs, d_bs, tg, d_tg, R, ctypes.byref(di[2]),
+        3, ctypes.byref(di[3]), L, ctypes.byref(di[4]), ip(wsh), zi(wsh), ip(bsh), zi(bsh), ip(ish), zi(ish),
+        p_inter, d_inter, p_rgba, d_rgba, S, ctypes.byref(di[5]), dd, d_dd, p_al, d_al, p_cu, d_cu, p_wg, d_wg,
+        p_acc, d_acc, float(loss))
+    b = c_oracle.nerf_backward(case["X"], case["ws"], case["bs"], case["dims"], case["target"], case["dists"], R, S,
+                               float(f["loss"]), rows=256)
+    mi, mo = case["ws"].shape[1], case["ws"].shape[2]
+    assert rel_err(_read_ragged(d_ws, (L, mi, mo)), b["d_ws"]) <= TOL
+    assert rel_err(_read_ragged(d_bs, (L, mo)), b["d_bs"]) <= TOL
+    assert rel_err(_read_ragged(d_X, (N, dims[0])), b["d_X"]) <= TOL
+    assert not _read_ragged(p_acc, (R, 3)).any() and not _read_ragged(d_wg, (R, S)).any()
+    assert all(v.value == 0 for v in di)
