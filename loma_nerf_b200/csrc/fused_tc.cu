@@ -330,6 +330,11 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // Programmatic dependent launch: everything above (shared-memory zeroing, barrier init, TMEM
+    // allocation, the MMA program) overlaps the tail of the previous kernel in the stream; from here
+    // on we read what it produced (weight image, tile counter, step counter).  No-op without PDL.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
         const uint32_t wb = (uint32_t)LY::wimg_bytes(L, K0P);
         mbar_expect_tx(bar_w, wb);
@@ -802,6 +807,8 @@ __global__ void __launch_bounds__(1024) tc_reduce_kernel(const float *__restrict
                                  lnb_tc_comm cm)
 {
     __shared__ float sloss;
+    asm volatile("griddepcontrol.wait;" ::: "memory");              // the fused kernel's partials are complete
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); // the next step may start its prologue
     // every block sums the loss partials itself (same order everywhere) so the seed needs no second pass
     if (threadIdx.x < 32) {
         float s = 0.0f;
@@ -1053,15 +1060,22 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     cudaMemset(dbg_dev, 0, (size_t)grid * 28 * sizeof(float));
     p.dbg = dbg_dev;
 #endif
+    cudaLaunchAttribute pdl_attr[1];
+    pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+    const bool use_pdl = getenv("LNB_NO_PDL") == nullptr;
     if (N > 0) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TILE); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+    cfg.attrs = pdl_attr; cfg.numAttrs = use_pdl ? 1 : 0;
 #define LNB_TC(HPV)                                                                              \
     do {                                                                                         \
         if (rays) {                                                                              \
             LNB_CUDA(cudaFuncSetAttribute(fused_tc_kernel<true, HPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            fused_tc_kernel<true, HPV><<<grid, TILE, smem, ctx->stream>>>(p);                    \
+            LNB_CUDA(cudaLaunchKernelEx(&cfg, fused_tc_kernel<true, HPV>, p));                   \
         } else {                                                                                 \
             LNB_CUDA(cudaFuncSetAttribute(fused_tc_kernel<false, HPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            fused_tc_kernel<false, HPV><<<grid, TILE, smem, ctx->stream>>>(p);                   \
+            LNB_CUDA(cudaLaunchKernelEx(&cfg, fused_tc_kernel<false, HPV>, p));                  \
         }                                                                                        \
     } while (0)
         if (!(ex && ex->wimg)) {
@@ -1118,10 +1132,15 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     const int fuse = ex && ex->fuse_adam && a->want_grad;
     if (fuse) ad = AdamArgs{ex->param, ex->m, ex->v, ex->t_dev, ex->lr, ex->b1, ex->b2, ex->eps, (uint8_t *)ex->wimg_out,
                             (long long)L * mlp->max_in * mlp->max_out, ex->m == nullptr};
-    tc_reduce_kernel<<<blocks, 1024, 0, ctx->stream>>>(p.part, grid, p.part_stride, p, a->want_grad ? a->d_ws : nullptr,
-                                                      a->want_grad ? a->d_bs : nullptr, loss, seed_val, seed_is_loss,
-                                                      ex ? ex->overwrite_grads : 0, fuse, ad, im,
-                                                      (ex && ex->comm && fuse && !seed_is_loss) ? *ex->comm : lnb_tc_comm{});
+    {
+        cudaLaunchConfig_t rc{};
+        rc.gridDim = dim3((unsigned)blocks); rc.blockDim = dim3(1024); rc.dynamicSmemBytes = 0; rc.stream = ctx->stream;
+        rc.attrs = pdl_attr; rc.numAttrs = use_pdl ? 1 : 0;
+        const lnb_tc_comm comm_arg = (ex && ex->comm && fuse && !seed_is_loss) ? *ex->comm : lnb_tc_comm{};
+        LNB_CUDA(cudaLaunchKernelEx(&rc, tc_reduce_kernel, (const float *)p.part, grid, p.part_stride, p,
+                                    a->want_grad ? a->d_ws : (float *)nullptr, a->want_grad ? a->d_bs : (float *)nullptr, loss,
+                                    seed_val, seed_is_loss, ex ? ex->overwrite_grads : 0, fuse, ad, im, comm_arg));
+    }
     LNB_CHECK_LAUNCH();
     return LNB_OK;
 }
