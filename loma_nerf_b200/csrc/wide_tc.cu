@@ -1,0 +1,325 @@
+// wide_tc.cu -- tensor-core GEMMs for WIDE coordinate MLPs (hidden width up to 256, e.g. BASELINE
+// config 5: 63 -> 8 x 256 -> 4), where the fused small-MLP kernel (fused_tc.cu) does not apply:
+// 9 x 256 x 256 bf16 weights (1.15 MB) and 128 x 256 activations per layer do not fit one CTA's
+// shared memory, and the work per sample (2.86 MFLOP train) is firmly compute-bound.  So the wide
+// path is LAYERWISE on the tensor cores, activations as bf16 in HBM:
+//
+//   forward   H_{l+1} = relu(H_l W_l + b_l)              (scripts/nerf.py:67-146)
+//   backward  dZ_{l-1} = (dZ_l W_l^T) * [H_l > 0]         (reverse_diff.py rules)
+//   gradient  dW_l = H_l^T dZ_l, db_l = colsum(dZ_l)      (contraction over all samples)
+//
+// One warp-specialised persistent kernel serves the first two (gemm_tc_kernel): a TMA producer warp
+// streams 128 x 64 A tiles and N x 64 B tiles (128-byte swizzle) through a 4-stage shared-memory
+// ring, one thread issues tcgen05.mma (M = 128, N <= 256, K = 16) into one of two TMEM accumulators,
+// four epilogue warps drain the other (tcgen05.ld -> bias / activation / mask -> bf16 -> global).
+// The weight-gradient kernel (dw_tc_kernel) reads the same row-major bf16 activations as MN-major
+// operands (features contiguous) and accumulates a 256 x N tile over a slab of samples in TMEM.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdio.h>
+
+#include "lnb_internal.h"
+
+namespace {
+
+constexpr int BM = 128;     // rows (samples) per tile
+constexpr int BK = 64;      // K elements per pipeline stage = one 128-byte swizzle atom of bf16
+constexpr int STAGES = 4;
+constexpr int GEMM_THREADS = 192; // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (uint32_t it = 0; !done; ++it) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity), "r"(100000u) : "memory");
+        if (it > (1u << 22)) __trap(); // a lost arrival must fail loudly, not hang the GPU
+    }
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) { asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor for a 128-byte-swizzled tile whose rows are 128 B (64 bf16) apart and
+// whose 8-row swizzle atoms are 1024 B apart (what a TMA box {64, rows} with SWIZZLE_128B writes).
+//   K-major use  (rows = M or N, the 128 B direction = K): SBO = 1024 between 8-row groups.
+//   MN-major use (rows = K, the 128 B direction = M or N): SBO = 1024 between 8-K groups, LBO = the
+//   byte distance between 64-element MN atoms (= the next TMA box).
+// layout_type SWIZZLE_128B = 2 (bits 61..63), version 1 (bit 46).
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint32_t instr_desc(int M, int N, int a_mn_major, int b_mn_major)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b)
+{
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+enum { EPI_RELU_BF16 = 0,   // C = bf16(relu(acc + bias))
+       EPI_MASK_BF16 = 1,   // C = bf16(mask > 0 ? acc : 0)            (ReLU adjoint)
+       EPI_HEAD_F32 = 2,    // C[row][0..3] = nerf/sigmoid head of (acc + bias), fp32 [M][4]
+       EPI_NONE_F32 = 3 };  // C = acc (+ bias) as fp32 [M][ldc]        (tests)
+
+struct GemmParams {
+    int M, N, K;            // N multiple of 16 (<= 256), K multiple of 64
+    const float *bias;      // [N] or NULL
+    const __nv_bfloat16 *mask; int ldmask;
+    void *C; int ldc;       // elements
+    int epi, head;
+};
+
+// D[M x N] = A[M x K] * B[N x K]^T, A and B bf16 row-major (K contiguous), fp32 accumulation in TMEM.
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a_bytes = BM * BK * 2, b_bytes = p.N * BK * 2;
+    uint8_t *sA = smem, *sB = smem + STAGES * a_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + STAGES * ((b_bytes + 1023) / 1024 * 1024));
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull0 = smem_u32(bars + 2 * STAGES),
+                   tempty0 = smem_u32(bars + 2 * STAGES + 2);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+    const int b_stride = (b_bytes + 1023) / 1024 * 1024;
+    const int n_tiles = (p.M + BM - 1) / BM, kb_count = p.K / BK;
+    const uint32_t acc_cols = p.N <= 32 ? 32 : (p.N <= 64 ? 64 : (p.N <= 128 ? 128 : 256));
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * acc_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ---- TMA producer
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < kb_count; ++kb) {
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    mbar_expect_tx(full0 + 8 * stage, (uint32_t)(a_bytes + b_bytes));
+                    tma_load_2d(smem_u32(sA + stage * a_bytes), &mapA, kb * BK, tile * BM, full0 + 8 * stage);
+                    tma_load_2d(smem_u32(sB + stage * b_stride), &mapB, kb * BK, 0, full0 + 8 * stage);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc(128, p.N, 0, 0);
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < kb_count; ++kb) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(sA + stage * a_bytes), b0 = smem_u32(sB + stage * b_stride);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16(tmem + acc * acc_cols, sw128_desc(a0 + k * 32, 16, 1024), sw128_desc(b0 + k * 32, 16, 1024), idesc,
+                                  (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(empty0 + 8 * stage);   // frees the smem stage when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull0 + 8 * acc);          // accumulator ready for the epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ---- epilogue warps 2..5: warp w may touch TMEM lanes 32*(w%4) .. +31
+        const int q = warp & 3;
+        uint32_t acc = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(tfull0 + 8 * acc, acc_phase);
+            tc_fence_after();
+            const long long row = (long long)tile * BM + q * 32 + lane;
+            const bool live = row < p.M;
+            const uint32_t tbase = tmem + acc * acc_cols + ((uint32_t)(q * 32) << 16);
+            if (p.epi == EPI_HEAD_F32) {
+                uint32_t v[16];
+                tmem_ld16(tbase, v);
+                tmem_ld_wait();
+                if (live) {
+                    float z[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) z[j] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + j) : 0.0f);
+                    float4 o;
+                    o.x = 1.0f / (1.0f + __expf(-z[0])); o.y = 1.0f / (1.0f + __expf(-z[1])); o.z = 1.0f / (1.0f + __expf(-z[2]));
+                    o.w = p.head == LNB_HEAD_NERF ? fmaxf(z[3], 0.0f) : 1.0f / (1.0f + __expf(-z[3]));
+                    reinterpret_cast<float4 *>(p.C)[row] = o;
+                }
+            } else {
+                for (int c0 = 0; c0 < p.N; c0 += 32) {
+                    uint32_t v[32];
+                    if (p.N - c0 >= 32) tmem_ld32(tbase + c0, v);
+                    else tmem_ld16(tbase + c0, reinterpret_cast<uint32_t (&)[16]>(v));
+                    tmem_ld_wait();
+                    const int nc = p.N - c0 >= 32 ? 32 : 16;
+                    if (!live) continue;
+                    if (p.epi == EPI_NONE_F32) {
+                        float *o = reinterpret_cast<float *>(p.C) + row * p.ldc + c0;
+                        for (int j = 0; j < nc; ++j) o[j] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.0f);
+                    } else {
+                        uint32_t pk[16];
+                        if (p.epi == EPI_RELU_BF16) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float b0v = p.bias ? __ldg(p.bias + c0 + 2 * j) : 0.0f, b1v = p.bias ? __ldg(p.bias + c0 + 2 * j + 1) : 0.0f;
+                                pk[j] = pack_bf16(fmaxf(__uint_as_float(v[2 * j]) + b0v, 0.0f), fmaxf(__uint_as_float(v[2 * j + 1]) + b1v, 0.0f));
+                            }
+                        } else { // EPI_MASK_BF16
+                            const uint4 *mrow = reinterpret_cast<const uint4 *>(p.mask + row * p.ldmask + c0);
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                if (g * 8 >= nc) break;
+                                const uint4 m4 = __ldg(mrow + g);
+                                const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    pk[g * 4 + j] = pack_bf16(__uint_as_float(v[g * 8 + 2 * j]), __uint_as_float(v[g * 8 + 2 * j + 1])) & __vcmpne2(mw[j], 0u);
+                            }
+                        }
+                        uint4 *o = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.C) + row * p.ldc + c0);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            if (g * 8 < nc) o[g] = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty0 + 8 * acc);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 2 * acc_cols);
+}
+
+// ---- host helpers ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 2-D bf16 row-major [rows][cols] (cols contiguous, row pitch ld elements), box {64 cols, box_rows}, 128B swizzle
+int make_map(lnb_ctx *ctx, CUtensorMap *m, const void *base, long long rows, int cols, int ld, int box_rows)
+{
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { ctx->err = "cuTensorMapEncodeTiled is not available"; return LNB_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ctx->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; return LNB_ERR_CUDA; }
+    return LNB_OK;
+}
+
+size_t gemm_smem(int N)
+{
+    const size_t b_stride = ((size_t)N * BK * 2 + 1023) / 1024 * 1024;
+    return STAGES * (size_t)(BM * BK * 2) + STAGES * b_stride + (2 * STAGES + 4) * 8 + 16;
+}
+
+} // namespace
+
+// C = epilogue(A[M x K] * B[N x K]^T): A, B bf16 device pointers, row pitches lda / ldb elements
+// (multiples of 8), K multiple of 64, N multiple of 16 and <= 256.
+int lnb_wide_gemm(lnb_ctx *ctx, const void *A, int lda, const void *B, int ldb, long long M, int N, int K, const float *bias,
+                  const void *mask, int ldmask, void *C, int ldc, int epi, int head)
+{
+    LNB_ARG(M >= 0 && N >= 16 && N <= 256 && N % 16 == 0 && K >= 64 && K % 64 == 0, "wide gemm: shape");
+    LNB_ARG(lda % 8 == 0 && ldb % 8 == 0, "wide gemm: row pitches must be multiples of 8 elements");
+    if (M == 0) return LNB_OK;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
+    CUtensorMap mapA, mapB;
+    LNB_TRY(make_map(ctx, &mapA, A, M, K, lda, BM));
+    LNB_TRY(make_map(ctx, &mapB, B, N, K, ldb, N));
+    GemmParams p{};
+    p.M = (int)M; p.N = N; p.K = K; p.bias = bias; p.mask = (const __nv_bfloat16 *)mask; p.ldmask = ldmask; p.C = C; p.ldc = ldc;
+    p.epi = epi; p.head = head;
+    const size_t smem = gemm_smem(N);
+    LNB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int n_tiles = (int)((M + BM - 1) / BM);
+    const int grid = n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count;
+    lnb_prof_begin(ctx, "gemm_tc_kernel");
+    gemm_tc_kernel<<<grid, GEMM_THREADS, smem, ctx->stream>>>(mapA, mapB, p);
+    lnb_prof_end(ctx);
+    LNB_CHECK_LAUNCH();
+    return LNB_OK;
+}
+
+// test hook (tests/test_gpu_wide.py): fp32 C = A * B^T (+ bias) from bf16 operands
+extern "C" LNB_API int lnb_test_wide_gemm(lnb_ctx *ctx, const void *A, const void *B, long long M, int N, int K, const float *bias,
+                                          float *C)
+{
+    if (!ctx) return LNB_ERR_ARG;
+    return lnb_wide_gemm(ctx, A, K, B, K, M, N, K, bias, nullptr, 0, C, N, EPI_NONE_F32, 0);
+}
