@@ -24,7 +24,7 @@ namespace {
 
 constexpr int BM = 128;     // rows (samples) per tile
 constexpr int BK = 64;      // K elements per pipeline stage = one 128-byte swizzle atom of bf16
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;     // 3 x 48 KB operand ring + 32 KB epilogue staging (bf16 outputs leave by TMA store)
 constexpr int GEMM_THREADS = 192; // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -45,6 +45,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols)
@@ -117,16 +125,20 @@ struct GemmParams {
 
 // D[M x N] = A[M x K] * B[N x K]^T, A and B bf16 row-major (K contiguous), fp32 accumulation in TMEM.
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmParams p)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapMask, const GemmParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a_bytes = BM * BK * 2, b_bytes = p.N * BK * 2;
     uint8_t *sA = smem, *sB = smem + STAGES * a_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + STAGES * ((b_bytes + 1023) / 1024 * 1024));
+    // epilogue staging: per epilogue warp two 32-row x 128-byte boxes (128B-swizzled, as TMA expects)
+    uint8_t *sC = sB + STAGES * ((b_bytes + 1023) / 1024 * 1024);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sC + 4 * 2 * 4096);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull0 = smem_u32(bars + 2 * STAGES),
                    tempty0 = smem_u32(bars + 2 * STAGES + 2);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+    const uint32_t mbar0 = smem_u32(bars + 2 * STAGES + 6);
     const int b_stride = (b_bytes + 1023) / 1024 * 1024;
     const int n_tiles = (p.M + BM - 1) / BM, kb_count = p.K / BK;
     const uint32_t acc_cols = p.N <= 32 ? 32 : (p.N <= 64 ? 64 : (p.N <= 128 ? 128 : 256));
@@ -134,6 +146,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 128); }
+        for (int w = 0; w < 4; ++w) mbar_init(smem_u32(bars + 2 * STAGES + 6 + w), 1); // mask-tile arrivals, one per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * acc_cols);
@@ -182,7 +195,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     } else {
         // ---- epilogue warps 2..5: warp w may touch TMEM lanes 32*(w%4) .. +31
         const int q = warp & 3;
-        uint32_t acc = 0, acc_phase = 0;
+        uint32_t acc = 0, acc_phase = 0, cbuf = 0, mphase = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
@@ -203,40 +216,65 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     reinterpret_cast<float4 *>(p.C)[row] = o;
                 }
             } else {
-                for (int c0 = 0; c0 < p.N; c0 += 32) {
-                    uint32_t v[32];
-                    if (p.N - c0 >= 32) tmem_ld32(tbase + c0, v);
-                    else tmem_ld16(tbase + c0, reinterpret_cast<uint32_t (&)[16]>(v));
-                    tmem_ld_wait();
-                    const int nc = p.N - c0 >= 32 ? 32 : 16;
-                    if (!live) continue;
-                    if (p.epi == EPI_NONE_F32) {
+                if (p.epi == EPI_NONE_F32) {
+                    for (int c0 = 0; c0 < p.N; c0 += 32) {
+                        uint32_t v[32];
+                        if (p.N - c0 >= 32) tmem_ld32(tbase + c0, v);
+                        else tmem_ld16(tbase + c0, reinterpret_cast<uint32_t (&)[16]>(v));
+                        tmem_ld_wait();
+                        const int nc = p.N - c0 >= 32 ? 32 : 16;
+                        if (!live) continue;
                         float *o = reinterpret_cast<float *>(p.C) + row * p.ldc + c0;
                         for (int j = 0; j < nc; ++j) o[j] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.0f);
-                    } else {
-                        uint32_t pk[16];
-                        if (p.epi == EPI_RELU_BF16) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const float b0v = p.bias ? __ldg(p.bias + c0 + 2 * j) : 0.0f, b1v = p.bias ? __ldg(p.bias + c0 + 2 * j + 1) : 0.0f;
-                                pk[j] = pack_bf16(fmaxf(__uint_as_float(v[2 * j]) + b0v, 0.0f), fmaxf(__uint_as_float(v[2 * j + 1]) + b1v, 0.0f));
+                    }
+                } else {
+                    // bf16 outputs, 64 columns (one 128-byte row segment) at a time: registers -> this warp's
+                    // swizzled staging box -> TMA store (coalesced 128 B rows in global memory).  The ReLU-mask
+                    // tile is fetched into the same box by TMA first.
+                    uint8_t *box = sC + q * 8192;
+                    const uint32_t mb = mbar0 + 8 * q;
+                    for (int c0 = 0; c0 < p.N; c0 += 64) {
+                        const int nc = p.N - c0 >= 64 ? 64 : p.N - c0;   // 64, 32 or 16 live columns
+                        uint8_t *buf = box + (cbuf & 1) * 4096;
+                        tma_store_wait_read1();                          // the store issued two chunks ago has left this buffer
+                        __syncwarp();
+                        if (p.epi == EPI_MASK_BF16) {
+                            if (lane == 0) {
+                                mbar_expect_tx(mb, 4096);
+                                tma_load_2d(smem_u32(buf), &mapMask, c0, (int)(tile * BM + q * 32), mb);
                             }
-                        } else { // EPI_MASK_BF16
-                            const uint4 *mrow = reinterpret_cast<const uint4 *>(p.mask + row * p.ldmask + c0);
+                            mbar_wait(mb, mphase);
+                            mphase ^= 1;
+                        }
+                        uint32_t v[64];
+                        tmem_ld32(tbase + c0, reinterpret_cast<uint32_t (&)[32]>(v[0]));
+                        if (nc > 32) tmem_ld32(tbase + c0 + 32, reinterpret_cast<uint32_t (&)[32]>(v[32]));
+                        tmem_ld_wait();
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                if (g * 8 >= nc) break;
-                                const uint4 m4 = __ldg(mrow + g);
+                        for (int g = 0; g < 8; ++g) {                    // eight 16-byte chunks of this row
+                            if (g * 8 >= nc) break;
+                            uint4 *slot = reinterpret_cast<uint4 *>(buf + lane * 128 + ((g ^ (lane & 7)) << 4));
+                            uint32_t pk[4];
+                            if (p.epi == EPI_RELU_BF16) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const int c = c0 + g * 8 + 2 * j;
+                                    const float b0v = p.bias ? __ldg(p.bias + c) : 0.0f, b1v = p.bias ? __ldg(p.bias + c + 1) : 0.0f;
+                                    pk[j] = pack_bf16(fmaxf(__uint_as_float(v[g * 8 + 2 * j]) + b0v, 0.0f), fmaxf(__uint_as_float(v[g * 8 + 2 * j + 1]) + b1v, 0.0f));
+                                }
+                            } else {
+                                const uint4 m4 = *slot;                  // mask chunk sits where the output chunk will go
                                 const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
 #pragma unroll
                                 for (int j = 0; j < 4; ++j)
-                                    pk[g * 4 + j] = pack_bf16(__uint_as_float(v[g * 8 + 2 * j]), __uint_as_float(v[g * 8 + 2 * j + 1])) & __vcmpne2(mw[j], 0u);
+                                    pk[j] = pack_bf16(__uint_as_float(v[g * 8 + 2 * j]), __uint_as_float(v[g * 8 + 2 * j + 1])) & __vcmpne2(mw[j], 0u);
                             }
+                            *slot = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         }
-                        uint4 *o = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(p.C) + row * p.ldc + c0);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            if (g * 8 < nc) o[g] = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) tma_store_2d(&mapC, smem_u32(buf), c0, (int)(tile * BM + q * 32));
+                        ++cbuf;
                     }
                 }
             }
@@ -245,6 +283,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
+    if (warp >= 2) tma_store_wait_all();
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, 2 * acc_cols);
@@ -285,7 +324,7 @@ int make_map(lnb_ctx *ctx, CUtensorMap *m, const void *base, long long rows, int
 size_t gemm_smem(int N)
 {
     const size_t b_stride = ((size_t)N * BK * 2 + 1023) / 1024 * 1024;
-    return STAGES * (size_t)(BM * BK * 2) + STAGES * b_stride + (2 * STAGES + 4) * 8 + 16;
+    return STAGES * (size_t)(BM * BK * 2) + STAGES * b_stride + 4 * 2 * 4096 + (2 * STAGES + 10) * 8 + 16;
 }
 
 } // namespace
@@ -299,9 +338,18 @@ int lnb_wide_gemm(lnb_ctx *ctx, const void *A, int lda, const void *B, int ldb, 
     LNB_ARG(lda % 8 == 0 && ldb % 8 == 0, "wide gemm: row pitches must be multiples of 8 elements");
     if (M == 0) return LNB_OK;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
-    CUtensorMap mapA, mapB;
+    CUtensorMap mapA, mapB, mapC, mapMask;
     LNB_TRY(make_map(ctx, &mapA, A, M, K, lda, BM));
     LNB_TRY(make_map(ctx, &mapB, B, N, K, ldb, N));
+    mapC = mapA; mapMask = mapA; // placeholders when unused
+    if (epi == EPI_RELU_BF16 || epi == EPI_MASK_BF16) {
+        LNB_ARG(ldc % 8 == 0 && ldc >= ((N + 63) / 64) * 64, "wide gemm: bf16 output pitch must cover whole 64-column boxes");
+        LNB_TRY(make_map(ctx, &mapC, C, M, ((N + 63) / 64) * 64, ldc, 32));
+    }
+    if (epi == EPI_MASK_BF16) {
+        LNB_ARG(mask && ldmask % 8 == 0 && ldmask >= ((N + 63) / 64) * 64, "wide gemm: mask pitch");
+        LNB_TRY(make_map(ctx, &mapMask, mask, M, ((N + 63) / 64) * 64, ldmask, 32));
+    }
     GemmParams p{};
     p.M = (int)M; p.N = N; p.K = K; p.bias = bias; p.mask = (const __nv_bfloat16 *)mask; p.ldmask = ldmask; p.C = C; p.ldc = ldc;
     p.epi = epi; p.head = head;
@@ -310,7 +358,7 @@ int lnb_wide_gemm(lnb_ctx *ctx, const void *A, int lda, const void *B, int ldb, 
     const int n_tiles = (int)((M + BM - 1) / BM);
     const int grid = n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count;
     lnb_prof_begin(ctx, "gemm_tc_kernel");
-    gemm_tc_kernel<<<grid, GEMM_THREADS, smem, ctx->stream>>>(mapA, mapB, p);
+    gemm_tc_kernel<<<grid, GEMM_THREADS, smem, ctx->stream>>>(mapA, mapB, mapC, mapMask, p);
     lnb_prof_end(ctx);
     LNB_CHECK_LAUNCH();
     return LNB_OK;
@@ -322,4 +370,12 @@ extern "C" LNB_API int lnb_test_wide_gemm(lnb_ctx *ctx, const void *A, const voi
 {
     if (!ctx) return LNB_ERR_ARG;
     return lnb_wide_gemm(ctx, A, K, B, K, M, N, K, bias, nullptr, 0, C, N, EPI_NONE_F32, 0);
+}
+
+// test hook: bf16 C = relu(A B^T + bias), or masked by `mask` (> 0) when mask != NULL
+extern "C" LNB_API int lnb_test_wide_gemm_bf16(lnb_ctx *ctx, const void *A, const void *B, long long M, int N, int K, const float *bias,
+                                               const void *mask, void *C)
+{
+    if (!ctx) return LNB_ERR_ARG;
+    return lnb_wide_gemm(ctx, A, K, B, K, M, N, K, bias, mask, N, C, N, mask ? EPI_MASK_BF16 : EPI_RELU_BF16, 0);
 }

@@ -41,3 +41,25 @@ def test_wide_gemm_matches_fp32_product_of_bf16_operands(ctx, torch_cuda, M, N, 
     ctx.synchronize()
     ref = A.float() @ B.float().t() + bias
     assert rel_err(C.cpu().numpy(), ref.cpu().numpy()) <= 2e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (1000, 256, 256), (4096 + 77, 128, 64), (50000, 256, 256)])
+@pytest.mark.parametrize("masked", [False, True])
+def test_wide_gemm_bf16_epilogues(ctx, torch_cuda, M, N, K, masked):
+    torch = torch_cuda
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + int(masked))
+    A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16).contiguous()
+    B = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(torch.bfloat16).contiguous()
+    bias = torch.randn(N, device="cuda", generator=g)
+    mask = torch.relu(torch.randn(M, N, device="cuda", generator=g)).to(torch.bfloat16).contiguous()
+    C = torch.full((M, N), float("nan"), device="cuda").to(torch.bfloat16)
+    lib = ctx.lib
+    lib.lnb_test_wide_gemm_bf16.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_longlong, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 3
+    ctx._check(lib.lnb_test_wide_gemm_bf16(ctx.h, A.data_ptr(), B.data_ptr(), M, N, K, None if masked else bias.data_ptr(),
+                                           mask.data_ptr() if masked else None, C.data_ptr()))
+    ctx.synchronize()
+    acc = A.float() @ B.float().t()
+    ref = torch.where(mask > 0, acc, torch.zeros_like(acc)) if masked else torch.relu(acc + bias)
+    got = C.float().cpu().numpy()
+    assert np.isfinite(got).all()
+    assert rel_err(got, ref.to(torch.bfloat16).float().cpu().numpy()) <= 1e-2    # one bf16 rounding of the output
