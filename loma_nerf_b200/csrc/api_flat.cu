@@ -436,7 +436,14 @@ static int step_dispatch(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *
     if (a->path == LNB_PATH_TC) {
         StepDims d;
         LNB_TRY(validate(ctx, mlp, a, nerf, &d));
-        return lnb_fused_tc_step(ctx, mlp, a, nerf, ex); // never silently changes arithmetic
+        int rc = lnb_fused_tc_step(ctx, mlp, a, nerf, ex); // never silently changes arithmetic
+        if (rc == LNB_ERR_UNSUPPORTED && !ex) {
+            // wide MLPs: layerwise tensor-core path (same operand precision, same outputs)
+            const std::string why = ctx->err;
+            rc = lnb_wide_tc_step(ctx, mlp, a, nerf);
+            if (rc == LNB_ERR_UNSUPPORTED) ctx->err = why + "; " + ctx->err;
+        }
+        return rc;
     }
     LNB_ARG(false, "unknown path");
     return LNB_ERR_ARG;

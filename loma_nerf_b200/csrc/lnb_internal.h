@@ -169,6 +169,8 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
                       const lnb_tc_extra *ex);
 // validated dispatch of one step with tensor-core extras (api_flat.cu)
 int lnb_step_ex(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, bool nerf, const lnb_tc_extra *ex);
+// layerwise tensor-core step for wide MLPs (wide_tc.cu); LNB_ERR_UNSUPPORTED when it does not apply
+int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, bool nerf);
 // padded widths of the fused kernel for this MLP, 0 when unsupported; bytes of its weight image
 int lnb_tc_layout(const lnb_mlp *mlp, int *HP, int *K0P, int *wimg_bytes);
 // build the weight image from fp32 padded weights (one small kernel)

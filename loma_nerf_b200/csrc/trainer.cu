@@ -98,8 +98,7 @@ static int trainer_run(lnb_trainer *t, const lnb_step_args *batch, int nerf, boo
     a.d_ws = t->grads; a.d_bs = t->grads + t->n_w; a.loss = t->grads + t->n_w + t->n_b;
     a.d_X = a.d_target = a.d_dists = a.d_color = a.d_inter = nullptr;
     a.inter = a.rgba = a.alpha = a.cumprod = a.weights = nullptr;
-    if (a.path == LNB_PATH_TC) {
-        LNB_ARG(t->tc_ok, "trainer: this MLP does not fit the tensor-core path");
+    if (a.path == LNB_PATH_TC && t->tc_ok) {
         lnb_tc_extra ex;
         ex.wimg = t->wimg; ex.overwrite_grads = 1; ex.t_dev = t->t_dev;
         if (fuse_update) {
@@ -111,7 +110,8 @@ static int trainer_run(lnb_trainer *t, const lnb_step_args *batch, int nerf, boo
         t->t_bumped = !fuse_update;
         return LNB_OK;
     }
-    // exact fp32 path: zero the gradient buffer (its kernels accumulate), step, optional update
+    // exact fp32 path, or a wide MLP on the layerwise tensor-core path: zero the gradient buffer
+    // (those kernels accumulate), step, optional update
     LNB_CUDA(cudaMemsetAsync(t->grads, 0, (size_t)(t->n_w + t->n_b + 1) * 4, ctx->stream));
     LNB_TRY(nerf ? lnb_nerf_step(ctx, &t->mlp, &a) : lnb_fit_step(ctx, &t->mlp, &a));
     t->t_bumped = false;

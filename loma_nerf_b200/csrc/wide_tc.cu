@@ -327,6 +327,171 @@ size_t gemm_smem(int N)
     return STAGES * (size_t)(BM * BK * 2) + STAGES * b_stride + 4 * 2 * 4096 + (2 * STAGES + 10) * 8 + 16;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Weight gradient dW[in x out] = H^T dZ, contraction over samples.  H [rows][in_pad] and dZ
+// [rows][out_pad] are the row-major bf16 activations / adjoints already in HBM; a TMA box
+// {64 features, 64 samples} with the 128-byte swizzle lands as a tile whose rows are samples (the
+// MMA's K) and whose 128-byte direction is the feature axis, i.e. exactly an MN-major operand.
+// Each CTA owns a slab of samples and accumulates the whole [in_pad x out_pad] product in TMEM
+// (two M = 128 halves x up to 256 columns = all 512 columns), then writes one fp32 partial.
+// ---------------------------------------------------------------------------------------------
+constexpr int DW_STAGES = 3;
+struct DwParams {
+    long long rows, rows_per_cta;
+    int in_pad, out_pad;    // multiples of 64, <= 256
+    float *partial;         // [grid][in_pad][out_pad]
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+dw_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapZ, const DwParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a_boxes = p.in_pad / 64, b_boxes = p.out_pad / 64;
+    const int a_bytes = a_boxes * 8192, b_bytes = b_boxes * 8192;       // per 64-sample stage
+    uint8_t *sA = smem, *sB = smem + DW_STAGES * a_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + DW_STAGES * b_bytes);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + DW_STAGES), done0 = smem_u32(bars + 2 * DW_STAGES);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * DW_STAGES + 1);
+    const long long r_begin = (long long)blockIdx.x * p.rows_per_cta;
+    long long r_end = r_begin + p.rows_per_cta;
+    if (r_end > p.rows) r_end = p.rows;
+    const int kb_count = r_end > r_begin ? (int)((r_end - r_begin + 63) / 64) : 0;
+    const int halves = (p.in_pad + 127) / 128;
+    const uint32_t tcols = (uint32_t)(halves * p.out_pad) <= 32 ? 32 : ((halves * p.out_pad) <= 64 ? 64 : ((halves * p.out_pad) <= 128 ? 128 : ((halves * p.out_pad) <= 256 ? 256 : 512)));
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < DW_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(done0, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), tcols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    if (warp == 0 && lane == 0) {
+        uint32_t stage = 0, phase = 0;
+        for (int kb = 0; kb < kb_count; ++kb) {
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            mbar_expect_tx(full0 + 8 * stage, (uint32_t)(a_bytes + b_bytes));
+            const int r0 = (int)(r_begin + (long long)kb * 64);   // slabs are multiples of 64 rows: a block never straddles
+            for (int b = 0; b < a_boxes; ++b)                      // two CTAs; rows past the end of the tensor are zero-filled by TMA
+                tma_load_2d(smem_u32(sA + stage * a_bytes + b * 8192), &mapH, b * 64, r0, full0 + 8 * stage);
+            for (int b = 0; b < b_boxes; ++b)
+                tma_load_2d(smem_u32(sB + stage * b_bytes + b * 8192), &mapZ, b * 64, r0, full0 + 8 * stage);
+            if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1 && lane == 0) {
+        const uint32_t idesc = instr_desc(128, p.out_pad, 1, 1);
+        uint32_t stage = 0, phase = 0;
+        for (int kb = 0; kb < kb_count; ++kb) {
+            mbar_wait(full0 + 8 * stage, phase);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(sA + stage * a_bytes), b0 = smem_u32(sB + stage * b_bytes);
+            for (int h = 0; h < halves; ++h) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)   // 16 samples per MMA: +2048 B (16 rows x 128 B) inside every box
+                    umma_bf16(tmem + h * p.out_pad, sw128_desc(a0 + h * 2 * 8192 + k * 2048, 8192, 1024),
+                              sw128_desc(b0 + k * 2048, 8192, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(empty0 + 8 * stage);
+            if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(done0);
+    } else if (warp >= 2) {
+        mbar_wait(done0, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        float *out = p.partial + (size_t)blockIdx.x * p.in_pad * p.out_pad;
+        for (int h = 0; h < halves; ++h) {
+            const int feat = h * 128 + q * 32 + lane;
+            for (int c0 = 0; c0 < p.out_pad; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + h * p.out_pad + c0, v);
+                tmem_ld_wait();
+                if (feat < p.in_pad) {
+                    float4 *o = reinterpret_cast<float4 *>(out + (size_t)feat * p.out_pad + c0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        o[j] = kb_count ? make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, tcols);
+}
+
+// d_w[k*ldw + j] += scale * sum_z partial[z][k][j] for k < in_dim, j < out_dim (fixed order)
+__global__ void wide_dw_reduce_kernel(const float *__restrict__ partial, int n_part, int in_pad, int out_pad, int in_dim, int out_dim,
+                                      float *__restrict__ d_w, int ldw, float seed_value, const float *__restrict__ seed_dev)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= in_dim * out_dim) return;
+    const int k = e / out_dim, j = e % out_dim;
+    float s = 0.0f;
+    for (int z = 0; z < n_part; ++z) s += partial[((size_t)z * in_pad + k) * out_pad + j];
+    d_w[(size_t)k * ldw + j] += seed_value * (seed_dev ? __ldg(seed_dev) : 1.0f) * s;
+}
+
+// d_b[j] += scale * sum_i dZ[i][j]; dZ bf16 [rows][ld].  One block per 64 columns x row slab, then atomics-free
+// two-level: blocks write partials, a second launch reduces (reuses wide_dw_reduce_kernel with in_dim = 1).
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16 *__restrict__ Z, int ld, long long rows, long long rows_per_block,
+                                                          int cols, float *__restrict__ partial)
+{
+    // thread t: column pair (t & 31) * 2 of a 64-column group?  keep it simple: 256 threads = 8 row lanes x 32 column pairs
+    __shared__ float acc[8][64];
+    const int cp = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c0 = blockIdx.y * 64 + cp * 2;
+    const long long r_begin = (long long)blockIdx.x * rows_per_block;
+    long long r_end = r_begin + rows_per_block;
+    if (r_end > rows) r_end = rows;
+    float s0 = 0.f, s1 = 0.f;
+    if (c0 < cols)
+        for (long long r = r_begin + rl; r < r_end; r += 8) {
+            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162 *>(Z + r * ld + c0);
+            s0 += __bfloat162float(v.x); s1 += __bfloat162float(v.y);
+        }
+    acc[rl][cp * 2] = s0; acc[rl][cp * 2 + 1] = s1;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        float s = 0.f;
+        for (int i = 0; i < 8; ++i) s += acc[i][threadIdx.x];
+        const int c = blockIdx.y * 64 + threadIdx.x;
+        if (c < cols) partial[(size_t)blockIdx.x * cols + c] = s;
+    }
+}
+
+__global__ void f32_to_bf16_rows_kernel(const float *__restrict__ src, int lds, int cols, long long rows, __nv_bfloat16 *__restrict__ dst, int ldd)
+{
+    // dst[i][j] = j < cols ? src[i][j] : 0 for j < ldd
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * ldd) return;
+    const long long i = e / ldd;
+    const int j = (int)(e % ldd);
+    dst[e] = __float2bfloat16_rn(j < cols ? src[i * lds + j] : 0.0f);
+}
+
+// weight images: Wf[l] = [out_pad][in_pad] (forward B operand, K = in), Wb[l] = [in_pad][out_pad] (backward, K = out)
+__global__ void wide_prep_kernel(const float *__restrict__ w, int ldw, int in_dim, int out_dim, int in_pad, int out_pad,
+                                 __nv_bfloat16 *__restrict__ Wf, __nv_bfloat16 *__restrict__ Wb)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= in_pad * out_pad) return;
+    const int k = e / out_pad, j = e % out_pad;
+    const float v = (k < in_dim && j < out_dim) ? w[(size_t)k * ldw + j] : 0.0f;
+    Wb[(size_t)k * out_pad + j] = __float2bfloat16_rn(v);
+    Wf[(size_t)j * in_pad + k] = __float2bfloat16_rn(v);
+}
+
+size_t dw_smem(int in_pad, int out_pad)
+{
+    return (size_t)DW_STAGES * ((in_pad / 64) + (out_pad / 64)) * 8192 + (2 * DW_STAGES + 4) * 8 + 16;
+}
+
 } // namespace
 
 // C = epilogue(A[M x K] * B[N x K]^T): A, B bf16 device pointers, row pitches lda / ldb elements
@@ -378,4 +543,178 @@ extern "C" LNB_API int lnb_test_wide_gemm_bf16(lnb_ctx *ctx, const void *A, cons
 {
     if (!ctx) return LNB_ERR_ARG;
     return lnb_wide_gemm(ctx, A, K, B, K, M, N, K, bias, mask, N, C, N, mask ? EPI_MASK_BF16 : EPI_RELU_BF16, 0);
+}
+
+// dW partials of one layer: returns the number of partials through *n_part
+int lnb_wide_dw(lnb_ctx *ctx, const void *H, int ldh, int in_pad, const void *dZ, int ldz, int out_pad, long long rows,
+                float *partial, int n_part)
+{
+    LNB_ARG(in_pad % 64 == 0 && in_pad >= 64 && in_pad <= 256 && out_pad % 64 == 0 && out_pad >= 64 && out_pad <= 256, "wide dW: padded widths");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
+    CUtensorMap mapH, mapZ;
+    LNB_TRY(make_map(ctx, &mapH, H, rows, in_pad, ldh, 64));
+    LNB_TRY(make_map(ctx, &mapZ, dZ, rows, out_pad, ldz, 64));
+    DwParams p{};
+    p.rows = rows;
+    p.rows_per_cta = ((rows + n_part - 1) / n_part + 63) / 64 * 64;
+    p.in_pad = in_pad; p.out_pad = out_pad; p.partial = partial;
+    const size_t smem = dw_smem(in_pad, out_pad);
+    LNB_CUDA(cudaFuncSetAttribute(dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lnb_prof_begin(ctx, "dw_tc_kernel");
+    dw_tc_kernel<<<n_part, GEMM_THREADS, smem, ctx->stream>>>(mapH, mapZ, p);
+    lnb_prof_end(ctx);
+    LNB_CHECK_LAUNCH();
+    return LNB_OK;
+}
+
+// test hook: fp32 dW[in_pad][out_pad] = H^T dZ from bf16 H [rows][in_pad], dZ [rows][out_pad]
+extern "C" LNB_API int lnb_test_wide_dw(lnb_ctx *ctx, const void *H, int in_pad, const void *dZ, int out_pad, long long rows, float *dW)
+{
+    if (!ctx) return LNB_ERR_ARG;
+    const int n_part = ctx->sm_count;
+    LNB_TRY(lnb_arena_reserve(ctx, (size_t)n_part * in_pad * out_pad * sizeof(float) + 4096));
+    float *partial = (float *)lnb_arena_take(ctx, (size_t)n_part * in_pad * out_pad * sizeof(float));
+    LNB_TRY(lnb_wide_dw(ctx, H, in_pad, in_pad, dZ, out_pad, out_pad, rows, partial, n_part));
+    LNB_CUDA(cudaMemsetAsync(dW, 0, (size_t)in_pad * out_pad * sizeof(float), ctx->stream));
+    wide_dw_reduce_kernel<<<(in_pad * out_pad + 255) / 256, 256, 0, ctx->stream>>>(partial, n_part, in_pad, out_pad, in_pad, out_pad, dW, out_pad, 1.0f, nullptr);
+    LNB_CHECK_LAUNCH();
+    return LNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The wide-MLP step: layerwise on the tensor cores (see the header of this file).  Produces what
+// the fused kernel produces: loss, colour, d_ws, d_bs.  Returns LNB_ERR_UNSUPPORTED otherwise.
+// ---------------------------------------------------------------------------------------------
+static int pad64(int v) { return (v + 63) / 64 * 64; }
+
+int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, bool nerf)
+{
+    auto unsupported = [&](const char *why) {
+        ctx->err = std::string("wide tensor-core path: ") + why;
+        return LNB_ERR_UNSUPPORTED;
+    };
+    const int L = mlp->n_layers;
+    if (!nerf) return unsupported("mlp_fit runs on the fused kernel or the fp32 path");
+    if (L < 2 || L > LNB_MAX_LAYERS) return unsupported("needs 2..16 layers");
+    for (int l = 0; l <= L; ++l)
+        if (mlp->dims[l] > 256) return unsupported("layer widths above 256");
+    if (mlp->dims[L] > 16) return unsupported("more than 16 output channels");
+    if (a->inter || a->rgba || a->alpha || a->cumprod || a->weights || a->d_X || a->d_target || a->d_dists || a->d_color || a->d_inter)
+        return unsupported("only loss, colour, d_ws and d_bs are produced (use the fp32 path for the rest)");
+    if (a->color && a->color_accumulate) return unsupported("colour accumulation");
+    const int R = a->R, S = a->S;
+    const long long N = a->n_rows > 0 ? a->n_rows : (long long)R * S;
+    if (N != (long long)R * S || a->rows > N) return unsupported("needs n_rows == R*S and no extra rows");
+    if (N > 0x7fffffffLL - 256) return unsupported("too many samples for one call");
+    if (a->want_grad && !a->target) return unsupported("gradient without target");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
+    const bool rays = !a->X && a->rays_o;
+    const int c_in = mlp->dims[0];
+    int in_pad[LNB_MAX_LAYERS], out_pad[LNB_MAX_LAYERS];
+    for (int l = 0; l < L; ++l) { in_pad[l] = pad64(mlp->dims[l]); out_pad[l] = pad64(mlp->dims[l + 1]); }
+    const int n_part = ctx->sm_count;
+
+    // ---- arena plan
+    size_t need = 1 << 16;
+    auto add = [&](size_t bytes) { need += (bytes + 255) / 256 * 256 + 256; };
+    size_t h_bytes[LNB_MAX_LAYERS];
+    for (int l = 0; l < L; ++l) { h_bytes[l] = (size_t)N * in_pad[l] * 2; add(h_bytes[l]); }
+    int max_pad = 64;
+    for (int l = 0; l < L; ++l) { max_pad = in_pad[l] > max_pad ? in_pad[l] : max_pad; max_pad = out_pad[l] > max_pad ? out_pad[l] : max_pad; }
+    if (a->want_grad) { add((size_t)N * max_pad * 2); add((size_t)N * max_pad * 2); add((size_t)N * 16); }
+    add((size_t)N * 16);                                        // head fp32 [N][4]
+    if (rays) { add((size_t)N * c_in * 4); add((size_t)R * S * 4); }
+    for (int l = 0; l < L; ++l) { add((size_t)in_pad[l] * out_pad[l] * 2); add((size_t)in_pad[l] * out_pad[l] * 2); add((size_t)out_pad[l] * 4); }
+    add((size_t)n_part * 256 * 256 * 4);
+    add((size_t)2 * n_part * 256 * 4);
+    add((size_t)R * 4 + 16); add((size_t)R * 12 + 16); add(64);
+    LNB_TRY(lnb_arena_reserve(ctx, need));
+    auto take = [&](size_t bytes) { return lnb_arena_take(ctx, bytes); };
+    __nv_bfloat16 *H[LNB_MAX_LAYERS];
+    for (int l = 0; l < L; ++l) H[l] = (__nv_bfloat16 *)take(h_bytes[l]);
+    __nv_bfloat16 *dZa = nullptr, *dZb = nullptr;
+    float *dzh = nullptr;
+    if (a->want_grad) { dZa = (__nv_bfloat16 *)take((size_t)N * max_pad * 2); dZb = (__nv_bfloat16 *)take((size_t)N * max_pad * 2); dzh = (float *)take((size_t)N * 16); }
+    float *head = (float *)take((size_t)N * 16);
+    const float *X = a->X, *dists = a->dists;
+    if (rays) {
+        float *Xe = (float *)take((size_t)N * c_in * 4), *de = (float *)take((size_t)R * S * 4);
+        LNB_TRY(lnb_launch_sample_encode(ctx, a->rays_o, a->rays_d, a->t, a->ray_dtype == LNB_RAY_F64, R, S, a->pe_bands, Xe, de));
+        X = Xe; dists = de;
+    }
+    __nv_bfloat16 *Wf[LNB_MAX_LAYERS], *Wb[LNB_MAX_LAYERS];
+    float *biasP[LNB_MAX_LAYERS];
+    for (int l = 0; l < L; ++l) {
+        Wf[l] = (__nv_bfloat16 *)take((size_t)in_pad[l] * out_pad[l] * 2);
+        Wb[l] = (__nv_bfloat16 *)take((size_t)in_pad[l] * out_pad[l] * 2);
+        biasP[l] = (float *)take((size_t)out_pad[l] * 4);
+    }
+    float *partial = (float *)take((size_t)n_part * 256 * 256 * 4);
+    float *bpartial = (float *)take((size_t)2 * n_part * 256 * 4);
+    float *ray_sse = (float *)take((size_t)R * 4 + 16);
+    float *color = a->color ? a->color : (float *)take((size_t)R * 12 + 16);
+    float *loss = a->loss ? a->loss : (float *)take(64);
+    if (N == 0) {
+        if (a->loss) LNB_TRY(lnb_launch_fill(ctx, loss, 1, 0.0f));
+        return LNB_OK;
+    }
+
+    // ---- weight images, padded biases, bf16 features
+    for (int l = 0; l < L; ++l) {
+        const int n = in_pad[l] * out_pad[l];
+        wide_prep_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(a->ws + (size_t)l * mlp->max_in * mlp->max_out, mlp->max_out, mlp->dims[l],
+                                                                   mlp->dims[l + 1], in_pad[l], out_pad[l], Wf[l], Wb[l]);
+        LNB_CHECK_LAUNCH();
+        LNB_CUDA(cudaMemsetAsync(biasP[l], 0, (size_t)out_pad[l] * 4, ctx->stream));
+        LNB_CUDA(cudaMemcpyAsync(biasP[l], a->bs + (size_t)l * mlp->max_out, (size_t)mlp->dims[l + 1] * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    {
+        const long long n = N * in_pad[0];
+        f32_to_bf16_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(X, c_in, c_in, N, H[0], in_pad[0]);
+        LNB_CHECK_LAUNCH();
+    }
+    // ---- forward
+    for (int l = 0; l < L - 1; ++l)
+        LNB_TRY(lnb_wide_gemm(ctx, H[l], in_pad[l], Wf[l], in_pad[l], N, out_pad[l], in_pad[l], biasP[l], nullptr, 0, H[l + 1], out_pad[l],
+                              EPI_RELU_BF16, 0));
+    LNB_TRY(lnb_wide_gemm(ctx, H[L - 1], in_pad[L - 1], Wf[L - 1], in_pad[L - 1], N, 16, in_pad[L - 1], biasP[L - 1], nullptr, 0, head, 4,
+                          EPI_HEAD_F32, mlp->head));
+    LNB_TRY(lnb_launch_composite_fwd(ctx, head, 4, dists, a->target, R, S, nullptr, nullptr, nullptr, nullptr, color, 0, ray_sse));
+    if (a->target) LNB_TRY(lnb_launch_sum(ctx, ray_sse, R, loss));
+    else if (a->loss) LNB_TRY(lnb_launch_fill(ctx, loss, 1, 0.0f));
+    if (!a->want_grad) return LNB_OK;
+
+    // ---- backward (unit seed inside; d_ws / d_bs scaled by the seed as they are accumulated)
+    const float *seed_dev = a->seed_mode == LNB_SEED_LOSS ? loss : nullptr;
+    const float seed_val = a->seed_mode == LNB_SEED_LOSS ? 1.0f : a->seed;
+    LNB_TRY(lnb_launch_composite_bwd(ctx, head, 4, dists, a->target, color, R, S, dzh, 4, 4, nullptr, nullptr));
+    {
+        const long long n = N * out_pad[L - 1];
+        f32_to_bf16_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dzh, 4, 4, N, dZa, out_pad[L - 1]);
+        LNB_CHECK_LAUNCH();
+    }
+    __nv_bfloat16 *dZ = dZa, *dZn = dZb;
+    for (int l = L - 1; l >= 0; --l) {
+        const int in_l = mlp->dims[l], out_l = mlp->dims[l + 1];
+        LNB_TRY(lnb_wide_dw(ctx, H[l], in_pad[l], in_pad[l], dZ, out_pad[l], out_pad[l], N, partial, n_part));
+        wide_dw_reduce_kernel<<<(in_l * out_l + 255) / 256, 256, 0, ctx->stream>>>(partial, n_part, in_pad[l], out_pad[l], in_l, out_l,
+                                                                                  a->d_ws + (size_t)l * mlp->max_in * mlp->max_out, mlp->max_out,
+                                                                                  seed_val, seed_dev);
+        LNB_CHECK_LAUNCH();
+        {
+            const int nblk = 2 * n_part;
+            const long long rpb = (N + nblk - 1) / nblk;
+            colsum_bf16_kernel<<<dim3(nblk, out_pad[l] / 64), 256, 0, ctx->stream>>>(dZ, out_pad[l], N, rpb, out_pad[l], bpartial);
+            LNB_CHECK_LAUNCH();
+            wide_dw_reduce_kernel<<<(out_l + 255) / 256, 256, 0, ctx->stream>>>(bpartial, nblk, 1, out_pad[l], 1, out_l,
+                                                                                a->d_bs + (size_t)l * mlp->max_out, mlp->max_out, seed_val, seed_dev);
+            LNB_CHECK_LAUNCH();
+        }
+        if (l == 0) break;
+        // dZ_{l-1} = (dZ_l W_l^T) masked by H_l > 0
+        LNB_TRY(lnb_wide_gemm(ctx, dZ, out_pad[l], Wb[l], out_pad[l], N, in_pad[l], out_pad[l], nullptr, H[l], in_pad[l], dZn, in_pad[l],
+                              EPI_MASK_BF16, 0));
+        __nv_bfloat16 *t = dZ; dZ = dZn; dZn = t;
+    }
+    return LNB_OK;
 }

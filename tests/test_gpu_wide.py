@@ -63,3 +63,72 @@ def test_wide_gemm_bf16_epilogues(ctx, torch_cuda, M, N, K, masked):
     got = C.float().cpu().numpy()
     assert np.isfinite(got).all()
     assert rel_err(got, ref.to(torch.bfloat16).float().cpu().numpy()) <= 1e-2    # one bf16 rounding of the output
+
+
+@pytest.mark.parametrize("rows,in_pad,out_pad", [(64, 64, 64), (1000, 256, 256), (100000, 64, 256), (33333, 256, 64), (5000, 128, 192)])
+def test_wide_dw_matches_fp32_product(ctx, torch_cuda, rows, in_pad, out_pad):
+    torch = torch_cuda
+    g = torch.Generator(device="cuda").manual_seed(rows + in_pad)
+    H = torch.relu(torch.randn(rows, in_pad, device="cuda", generator=g)).to(torch.bfloat16).contiguous()
+    Z = (torch.randn(rows, out_pad, device="cuda", generator=g) * 0.1).to(torch.bfloat16).contiguous()
+    dW = torch.full((in_pad, out_pad), float("nan"), device="cuda")
+    lib = ctx.lib
+    lib.lnb_test_wide_dw.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p]
+    ctx._check(lib.lnb_test_wide_dw(ctx.h, H.data_ptr(), in_pad, Z.data_ptr(), out_pad, rows, dW.data_ptr()))
+    ctx.synchronize()
+    ref = (H.double().t() @ Z.double()).float()
+    assert rel_err(dW.cpu().numpy(), ref.cpu().numpy()) <= 2e-5
+
+
+from conftest import golden_files, load_golden  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+WIDE_TOL = 6e-2   # bf16 operands through up to 9 layers of 256; measured errors are logged
+
+
+def _log(msg):
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/tc_errors.log", "a") as fh:
+        fh.write(msg + "\n")
+
+
+def _run_wide(ctx, torch, case, seed, rays=False):
+    cv = lambda a: torch.as_tensor(np.ascontiguousarray(a, np.float32)).cuda()  # noqa: E731
+    dims = [int(v) for v in case["dims"]]
+    R, S = int(case["R"]), int(case["S"])
+    if rays:
+        r = [torch.as_tensor(np.ascontiguousarray(case[k], np.float64)).cuda() for k in ("rays_o", "rays_d", "t")]
+        out = ctx.nerf_step_rays(dims, r[0], r[1], r[2], int(case["E"]), cv(case["ws"]), cv(case["bs"]), cv(case["target"]),
+                                 grad=True, seed=seed, outputs=("color", "loss"), path="tc")
+    else:
+        out = ctx.nerf_step(dims, cv(case["X"]), cv(case["ws"]), cv(case["bs"]), cv(case["dists"]), cv(case["target"]), R=R, S=S,
+                            grad=True, seed=seed, outputs=("color", "loss"), path="tc")
+    ctx.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def test_wide_path_paper_size_mlp_against_reference_golden(ctx, torch_cuda):
+    """BASELINE config 5 shape: 63 -> 8 x 256 -> 4, 192 samples per ray, golden vector recorded from the
+    real reference (max_iter-only edit of scripts/nerf.py)."""
+    gd = load_golden([p for p in golden_files("nerf_") if "c5" in p][0])
+    o = _run_wide(ctx, torch_cuda, gd, "loss")
+    errs = dict(loss=rel_err(o["loss"][0], gd["loss"]), color=rel_err(o["color"], gd["color"]),
+                d_ws=rel_err(o["d_ws"], gd["d_ws"]), d_bs=rel_err(o["d_bs"], gd["d_bs"]))
+    _log("wide c5 golden %s" % errs)
+    # a single ray: the gradient is proportional to the residual colour - target (0.05-0.1 here), so
+    # the 1 % bf16 error of the colour itself shows up ten times larger in d_ws / d_bs; batches of
+    # rays average it out (next test, same network: 2e-3)
+    assert errs["loss"] <= 1e-2 and errs["color"] <= 3e-2 and max(errs["d_ws"], errs["d_bs"]) <= 0.2, errs
+
+
+@pytest.mark.parametrize("R,S,E,width,layers,rays", [(64, 192, 10, 256, 9, False), (300, 64, 10, 256, 5, True), (1000, 33, 5, 128, 4, False),
+                                                      (50, 128, 4, 200, 3, True), (2048, 64, 10, 64, 6, False)])
+def test_wide_path_against_f64_restatement(ctx, torch_cuda, R, S, E, width, layers, rays):
+    case = O.make_nerf_case(1300 + width + layers, R, S, E=E, width=width, n_layers=layers)
+    o = _run_wide(ctx, torch_cuda, case, 1.0, rays=rays)
+    f = O.nerf_f64(case["X"], case["ws"], case["bs"], case["dims"], case["target"], case["dists"], R, S, g=1.0)
+    errs = dict(loss=rel_err(o["loss"][0], f["loss"]), color=rel_err(o["color"], f["color"]),
+                d_ws=rel_err(o["d_ws"], f["d_ws"]), d_bs=rel_err(o["d_bs"], f["d_bs"]))
+    _log("wide R=%d S=%d E=%d w=%d L=%d rays=%s %s" % (R, S, E, width, layers, rays, errs))
+    assert max(errs.values()) <= WIDE_TOL, errs
