@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "lnb_internal.h"
 
@@ -25,7 +26,9 @@ namespace {
 constexpr int BM = 128;     // rows (samples) per tile
 constexpr int BK = 64;      // K elements per pipeline stage = one 128-byte swizzle atom of bf16
 constexpr int STAGES = 3;     // 3 x 48 KB operand ring + 32 KB epilogue staging (bf16 outputs leave by TMA store)
-constexpr int GEMM_THREADS = 192; // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int GEMM_THREADS = 320; // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant: one warp per
+                                  // scheduler cannot hide its own ALU latency, and the epilogue is the long pole)
+constexpr int DW_THREADS = 192;   // weight-gradient kernel: warp 0 TMA, warp 1 MMA, warps 2..5 column sums + epilogue
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
@@ -50,7 +53,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t sr
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -110,43 +113,51 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
-enum { EPI_RELU_BF16 = 0,   // C = bf16(relu(acc + bias))
-       EPI_MASK_BF16 = 1,   // C = bf16(mask > 0 ? acc : 0)            (ReLU adjoint)
+enum { EPI_RELU_BF16 = 0,   // C = bf16(relu(acc + bias)), optionally + the ReLU pattern as bits
+       EPI_MASK_BF16 = 1,   // C = bf16(bit ? acc : 0)                 (ReLU adjoint, pattern from the forward pass)
        EPI_HEAD_F32 = 2,    // C[row][0..3] = nerf/sigmoid head of (acc + bias), fp32 [M][4]
        EPI_NONE_F32 = 3 };  // C = acc (+ bias) as fp32 [M][ldc]        (tests)
 
+constexpr int MAX_A_STAGES = 8;
+constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
+
 struct GemmParams {
-    int M, N, K;            // N multiple of 16 (<= 256), K multiple of 64
+    int M, N, K;            // N multiple of 16 (<= 256), K multiple of 64 (<= 256)
     const float *bias;      // [N] or NULL
-    const __nv_bfloat16 *mask; int ldmask;
+    const uint32_t *bits_in;   // EPI_MASK_BF16: [M][ldbits] words, bit j of word w <-> column 32 w + j
+    uint32_t *bits_out;        // EPI_RELU_BF16: optional, same layout: which outputs are > 0
+    int ldbits;
     void *C; int ldc;       // elements
-    int epi, head;
+    int epi, head, a_stages;
 };
 
 // D[M x N] = A[M x K] * B[N x K]^T, A and B bf16 row-major (K contiguous), fp32 accumulation in TMEM.
+// B (a layer's weights, <= 128 KB) is loaded ONCE per CTA and stays in shared memory; everything
+// else is a ring of 16 KB A stages, so all TMA bytes in flight are HBM reads of activations.
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapMask, const GemmParams p)
+               const __grid_constant__ CUtensorMap mapC, const GemmParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int a_bytes = BM * BK * 2, b_bytes = p.N * BK * 2;
-    uint8_t *sA = smem, *sB = smem + STAGES * a_bytes;
-    // epilogue staging: per epilogue warp two 32-row x 128-byte boxes (128B-swizzled, as TMA expects)
-    uint8_t *sC = sB + STAGES * ((b_bytes + 1023) / 1024 * 1024);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sC + 4 * 2 * 4096);
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull0 = smem_u32(bars + 2 * STAGES),
-                   tempty0 = smem_u32(bars + 2 * STAGES + 2);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
-    const uint32_t mbar0 = smem_u32(bars + 2 * STAGES + 6);
-    const int b_stride = (b_bytes + 1023) / 1024 * 1024;
+    const int b_bytes = p.N * BK * 2, b_stride = (b_bytes + 1023) / 1024 * 1024;
     const int n_tiles = (p.M + BM - 1) / BM, kb_count = p.K / BK;
+    const int AS = p.a_stages;
+    uint8_t *sB = smem, *sA = smem + kb_count * b_stride;
+    // epilogue staging: per epilogue warp one 32-row x 128-byte box (128B-swizzled, as TMA expects)
+    uint8_t *sC = sA + AS * A_STAGE_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sC + 8 * 4096);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + MAX_A_STAGES), tfull0 = smem_u32(bars + 2 * MAX_A_STAGES),
+                   tempty0 = smem_u32(bars + 2 * MAX_A_STAGES + 2), bfull = smem_u32(bars + 2 * MAX_A_STAGES + 4);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_A_STAGES + 5);
+    float *sBias = reinterpret_cast<float *>(bars + 2 * MAX_A_STAGES + 8);
+    for (int i = threadIdx.x; i < p.N; i += GEMM_THREADS) sBias[i] = p.bias ? __ldg(p.bias + i) : 0.0f;
     const uint32_t acc_cols = p.N <= 32 ? 32 : (p.N <= 64 ? 64 : (p.N <= 128 ? 128 : 256));
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 128); }
-        for (int w = 0; w < 4; ++w) mbar_init(smem_u32(bars + 2 * STAGES + 6 + w), 1); // mask-tile arrivals, one per epilogue warp
+        for (int s = 0; s < AS; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 256); }
+        mbar_init(bfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * acc_cols);
@@ -158,14 +169,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (warp == 0) {
         // ---- TMA producer
         if (lane == 0) {
+            mbar_expect_tx(bfull, (uint32_t)(kb_count * b_bytes));
+            for (int kb = 0; kb < kb_count; ++kb) tma_load_2d(smem_u32(sB + kb * b_stride), &mapB, kb * BK, 0, bfull);
             uint32_t stage = 0, phase = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int kb = 0; kb < kb_count; ++kb) {
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                    mbar_expect_tx(full0 + 8 * stage, (uint32_t)(a_bytes + b_bytes));
-                    tma_load_2d(smem_u32(sA + stage * a_bytes), &mapA, kb * BK, tile * BM, full0 + 8 * stage);
-                    tma_load_2d(smem_u32(sB + stage * b_stride), &mapB, kb * BK, 0, full0 + 8 * stage);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    mbar_expect_tx(full0 + 8 * stage, (uint32_t)A_STAGE_BYTES);
+                    tma_load_2d(smem_u32(sA + stage * A_STAGE_BYTES), &mapA, kb * BK, tile * BM, full0 + 8 * stage);
+                    if (++stage == (uint32_t)AS) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -174,108 +186,122 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (lane == 0) {
             const uint32_t idesc = instr_desc(128, p.N, 0, 0);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            mbar_wait(bfull, 0);
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
                 for (int kb = 0; kb < kb_count; ++kb) {
                     mbar_wait(full0 + 8 * stage, phase);
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(sA + stage * a_bytes), b0 = smem_u32(sB + stage * b_stride);
+                    const uint32_t a0 = smem_u32(sA + stage * A_STAGE_BYTES), b0 = smem_u32(sB + kb * b_stride);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
                         umma_bf16(tmem + acc * acc_cols, sw128_desc(a0 + k * 32, 16, 1024), sw128_desc(b0 + k * 32, 16, 1024), idesc,
                                   (kb > 0 || k > 0) ? 1u : 0u);
-                    umma_commit(empty0 + 8 * stage);   // frees the smem stage when these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    umma_commit(empty0 + 8 * stage);   // frees the A stage when these MMAs retire
+                    if (++stage == (uint32_t)AS) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(tfull0 + 8 * acc);          // accumulator ready for the epilogue
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
-        // ---- epilogue warps 2..5: warp w may touch TMEM lanes 32*(w%4) .. +31
-        const int q = warp & 3;
-        uint32_t acc = 0, acc_phase = 0, cbuf = 0, mphase = 0;
+        // ---- epilogue warps 2..9: warp w may touch TMEM lanes 32*(w%4) .. +31; the two warps of a quadrant
+        // take alternate 64-column chunks
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        uint32_t acc = 0, acc_phase = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            mbar_wait(tfull0 + 8 * acc, acc_phase);
-            tc_fence_after();
             const long long row = (long long)tile * BM + q * 32 + lane;
             const bool live = row < p.M;
+            uint32_t mw[8];
+            if (p.epi == EPI_MASK_BF16) {   // this row's ReLU pattern, fetched while the MMAs of the tile still run
+#pragma unroll
+                for (int w = 0; w < 8; ++w) mw[w] = (live && w < p.ldbits) ? __ldg(p.bits_in + row * p.ldbits + w) : 0u;
+            }
+            mbar_wait(tfull0 + 8 * acc, acc_phase);
+            tc_fence_after();
             const uint32_t tbase = tmem + acc * acc_cols + ((uint32_t)(q * 32) << 16);
             if (p.epi == EPI_HEAD_F32) {
+                if (half == 0) {
                 uint32_t v[16];
                 tmem_ld16(tbase, v);
                 tmem_ld_wait();
                 if (live) {
                     float z[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) z[j] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + j) : 0.0f);
+                    for (int j = 0; j < 4; ++j) z[j] = __uint_as_float(v[j]) + sBias[j];
                     float4 o;
                     o.x = 1.0f / (1.0f + __expf(-z[0])); o.y = 1.0f / (1.0f + __expf(-z[1])); o.z = 1.0f / (1.0f + __expf(-z[2]));
                     o.w = p.head == LNB_HEAD_NERF ? fmaxf(z[3], 0.0f) : 1.0f / (1.0f + __expf(-z[3]));
                     reinterpret_cast<float4 *>(p.C)[row] = o;
                 }
+                }
+            } else if (p.epi == EPI_NONE_F32) {
+                for (int c0 = half * 32; c0 < p.N; c0 += 64) {
+                    uint32_t v[32];
+                    if (p.N - c0 >= 32) tmem_ld32(tbase + c0, v);
+                    else tmem_ld16(tbase + c0, reinterpret_cast<uint32_t (&)[16]>(v));
+                    tmem_ld_wait();
+                    const int nc = p.N - c0 >= 32 ? 32 : 16;
+                    if (!live) continue;
+                    float *o = reinterpret_cast<float *>(p.C) + row * p.ldc + c0;
+                    for (int j = 0; j < nc; ++j) o[j] = __uint_as_float(v[j]) + sBias[c0 + j];
+                }
             } else {
-                if (p.epi == EPI_NONE_F32) {
-                    for (int c0 = 0; c0 < p.N; c0 += 32) {
-                        uint32_t v[32];
-                        if (p.N - c0 >= 32) tmem_ld32(tbase + c0, v);
-                        else tmem_ld16(tbase + c0, reinterpret_cast<uint32_t (&)[16]>(v));
-                        tmem_ld_wait();
-                        const int nc = p.N - c0 >= 32 ? 32 : 16;
-                        if (!live) continue;
-                        float *o = reinterpret_cast<float *>(p.C) + row * p.ldc + c0;
-                        for (int j = 0; j < nc; ++j) o[j] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.0f);
-                    }
-                } else {
-                    // bf16 outputs, 64 columns (one 128-byte row segment) at a time: registers -> this warp's
-                    // swizzled staging box -> TMA store (coalesced 128 B rows in global memory).  The ReLU-mask
-                    // tile is fetched into the same box by TMA first.
-                    uint8_t *box = sC + q * 8192;
-                    const uint32_t mb = mbar0 + 8 * q;
-                    for (int c0 = 0; c0 < p.N; c0 += 64) {
-                        const int nc = p.N - c0 >= 64 ? 64 : p.N - c0;   // 64, 32 or 16 live columns
-                        uint8_t *buf = box + (cbuf & 1) * 4096;
-                        tma_store_wait_read1();                          // the store issued two chunks ago has left this buffer
-                        __syncwarp();
-                        if (p.epi == EPI_MASK_BF16) {
-                            if (lane == 0) {
-                                mbar_expect_tx(mb, 4096);
-                                tma_load_2d(smem_u32(buf), &mapMask, c0, (int)(tile * BM + q * 32), mb);
-                            }
-                            mbar_wait(mb, mphase);
-                            mphase ^= 1;
+                // bf16 outputs, 64 columns (one 128-byte row segment) at a time: registers -> this warp's
+                // swizzled staging box -> TMA store (coalesced 128 B rows in global memory).
+                uint8_t *buf = sC + (warp - 2) * 4096;
+                for (int c0 = half * 64; c0 < p.N; c0 += 128) {
+                    const int nc = p.N - c0 >= 64 ? 64 : p.N - c0;   // 64, 32 or 16 live columns
+                    uint32_t lo = 0, hi = 0;
+                    if (p.epi == EPI_MASK_BF16) {
+                        switch (c0 >> 6) {
+                        case 0: lo = mw[0]; hi = mw[1]; break;
+                        case 1: lo = mw[2]; hi = mw[3]; break;
+                        case 2: lo = mw[4]; hi = mw[5]; break;
+                        default: lo = mw[6]; hi = mw[7]; break;
                         }
-                        uint32_t v[64];
-                        tmem_ld32(tbase + c0, reinterpret_cast<uint32_t (&)[32]>(v[0]));
-                        if (nc > 32) tmem_ld32(tbase + c0 + 32, reinterpret_cast<uint32_t (&)[32]>(v[32]));
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int g = 0; g < 8; ++g) {                    // eight 16-byte chunks of this row
-                            if (g * 8 >= nc) break;
-                            uint4 *slot = reinterpret_cast<uint4 *>(buf + lane * 128 + ((g ^ (lane & 7)) << 4));
-                            uint32_t pk[4];
-                            if (p.epi == EPI_RELU_BF16) {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const int c = c0 + g * 8 + 2 * j;
-                                    const float b0v = p.bias ? __ldg(p.bias + c) : 0.0f, b1v = p.bias ? __ldg(p.bias + c + 1) : 0.0f;
-                                    pk[j] = pack_bf16(fmaxf(__uint_as_float(v[g * 8 + 2 * j]) + b0v, 0.0f), fmaxf(__uint_as_float(v[g * 8 + 2 * j + 1]) + b1v, 0.0f));
-                                }
-                            } else {
-                                const uint4 m4 = *slot;                  // mask chunk sits where the output chunk will go
-                                const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
-#pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    pk[j] = pack_bf16(__uint_as_float(v[g * 8 + 2 * j]), __uint_as_float(v[g * 8 + 2 * j + 1])) & __vcmpne2(mw[j], 0u);
-                            }
-                            *slot = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        }
-                        fence_async_smem();
-                        __syncwarp();
-                        if (lane == 0) tma_store_2d(&mapC, smem_u32(buf), c0, (int)(tile * BM + q * 32));
-                        ++cbuf;
                     }
+                    uint32_t v[64];
+                    tmem_ld32(tbase + c0, reinterpret_cast<uint32_t (&)[32]>(v[0]));
+                    if (nc > 32) tmem_ld32(tbase + c0 + 32, reinterpret_cast<uint32_t (&)[32]>(v[32]));
+                    tmem_ld_wait();
+                    tma_store_wait_read0();                          // this warp's previous store has left the buffer
+                    __syncwarp();
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {                    // eight 16-byte chunks of this row
+                        if (g * 8 >= nc) break;
+                        uint4 *slot = reinterpret_cast<uint4 *>(buf + lane * 128 + ((g ^ (lane & 7)) << 4));
+                        uint32_t pk[4];
+                        if (p.epi == EPI_RELU_BF16) {
+                            uint32_t b8 = 0;
+#pragma unroll
+                            const float4 bA = *reinterpret_cast<const float4 *>(sBias + c0 + g * 8), bB = *reinterpret_cast<const float4 *>(sBias + c0 + g * 8 + 4);
+                            const float bv[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float r0 = fmaxf(__uint_as_float(v[g * 8 + 2 * j]) + bv[2 * j], 0.0f);
+                                const float r1 = fmaxf(__uint_as_float(v[g * 8 + 2 * j + 1]) + bv[2 * j + 1], 0.0f);
+                                pk[j] = pack_bf16(r0, r1);
+                                b8 |= ((pk[j] & 0xFFFFu) ? 1u : 0u) << (2 * j);
+                                b8 |= ((pk[j] >> 16) ? 1u : 0u) << (2 * j + 1);
+                            }
+                            if (g < 4) lo |= b8 << (g * 8);
+                            else hi |= b8 << ((g - 4) * 8);
+                        } else {
+                            const uint32_t b8 = ((g < 4 ? lo : hi) >> ((g & 3) * 8)) & 0xFFu;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                pk[j] = pack_bf16(((b8 >> (2 * j)) & 1u) ? __uint_as_float(v[g * 8 + 2 * j]) : 0.0f,
+                                                  ((b8 >> (2 * j + 1)) & 1u) ? __uint_as_float(v[g * 8 + 2 * j + 1]) : 0.0f);
+                        }
+                        *slot = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                    if (p.epi == EPI_RELU_BF16 && p.bits_out && live)
+                        *reinterpret_cast<uint2 *>(p.bits_out + row * p.ldbits + (c0 >> 5)) = make_uint2(lo, hi);
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) tma_store_2d(&mapC, smem_u32(buf), c0, (int)(tile * BM + q * 32));
                 }
             }
             tc_fence_before();
@@ -321,10 +347,17 @@ int make_map(lnb_ctx *ctx, CUtensorMap *m, const void *base, long long rows, int
     return LNB_OK;
 }
 
-size_t gemm_smem(int N)
+int gemm_a_stages(int N, int K)
 {
     const size_t b_stride = ((size_t)N * BK * 2 + 1023) / 1024 * 1024;
-    return STAGES * (size_t)(BM * BK * 2) + STAGES * b_stride + 4 * 2 * 4096 + (2 * STAGES + 10) * 8 + 16;
+    const long long room = 232448LL - 2048 - 8 * 4096 - (long long)(K / BK) * (long long)b_stride;
+    long long st = room / A_STAGE_BYTES;
+    return (int)(st > MAX_A_STAGES ? MAX_A_STAGES : st);
+}
+size_t gemm_smem(int N, int K, int a_stages)
+{
+    const size_t b_stride = ((size_t)N * BK * 2 + 1023) / 1024 * 1024;
+    return (size_t)(K / BK) * b_stride + (size_t)a_stages * A_STAGE_BYTES + 8 * 4096 + (2 * MAX_A_STAGES + 8) * 8 + 1024 + 16;
 }
 
 
@@ -341,9 +374,10 @@ struct DwParams {
     long long rows, rows_per_cta;
     int in_pad, out_pad;    // multiples of 64, <= 256
     float *partial;         // [grid][in_pad][out_pad]
+    float *colsum;          // [grid][out_pad] column sums of dZ over the CTA's slab (bias gradient), or NULL
 };
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(DW_THREADS, 1)
 dw_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapZ, const DwParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -361,7 +395,7 @@ dw_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ C
     const int halves = (p.in_pad + 127) / 128;
     const uint32_t tcols = (uint32_t)(halves * p.out_pad) <= 32 ? 32 : ((halves * p.out_pad) <= 64 ? 64 : ((halves * p.out_pad) <= 128 ? 128 : ((halves * p.out_pad) <= 256 ? 256 : 512)));
     if (threadIdx.x == 0) {
-        for (int s = 0; s < DW_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < DW_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 5); } // MMA commit + 4 column-sum warps
         mbar_init(done0, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -400,6 +434,34 @@ dw_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ C
         }
         umma_commit(done0);
     } else if (warp >= 2) {
+        // While the MMAs run, the four epilogue warps add up the columns of the dZ tiles as they pass
+        // through shared memory (d_bs = colsum(dZ)): thread t owns features 2t, 2t+1, i.e. one 32-bit
+        // word of every 128-byte row of box t/32; a warp reads a whole swizzled row, conflict-free.
+        {
+            const int t = (warp - 2) * 32 + lane, box = t >> 5, pr = t & 31;
+            const bool have = box < b_boxes;
+            float s0 = 0.0f, s1 = 0.0f;
+            uint32_t stage = 0, phase = 0;
+            for (int kb = 0; kb < kb_count; ++kb) {
+                mbar_wait(full0 + 8 * stage, phase);
+                if (have && p.colsum) {
+                    const uint8_t *base = sB + stage * b_bytes + box * 8192 + (pr & 3) * 4;
+#pragma unroll 8
+                    for (int r = 0; r < 64; ++r) {
+                        const uint32_t w = *reinterpret_cast<const uint32_t *>(base + r * 128 + (((pr >> 2) ^ (r & 7)) << 4));
+                        s0 += __uint_as_float(w << 16);
+                        s1 += __uint_as_float(w & 0xFFFF0000u);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty0 + 8 * stage);
+                if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (have && p.colsum) {
+                p.colsum[(size_t)blockIdx.x * p.out_pad + 2 * t] = s0;
+                p.colsum[(size_t)blockIdx.x * p.out_pad + 2 * t + 1] = s1;
+            }
+        }
         mbar_wait(done0, 0);
         tc_fence_after();
         const int q = warp & 3;
@@ -425,54 +487,58 @@ dw_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ C
     if (warp == 1) tmem_dealloc(tmem, tcols);
 }
 
-// d_w[k*ldw + j] += scale * sum_z partial[z][k][j] for k < in_dim, j < out_dim (fixed order)
-__global__ void wide_dw_reduce_kernel(const float *__restrict__ partial, int n_part, int in_pad, int out_pad, int in_dim, int out_dim,
-                                      float *__restrict__ d_w, int ldw, float seed_value, const float *__restrict__ seed_dev)
+// d_w[k*ldw + j] += scale * sum_z partial[z][k][j] for k < in_dim, j < out_dim.  A block covers 128
+// consecutive padded elements (32 lanes x float4) with 8 groups of partials in parallel; each group
+// adds its partials in index order and the groups are combined in order, so the result is fixed.
+__global__ void __launch_bounds__(256) wide_dw_reduce_kernel(const float *__restrict__ partial, int n_part, int in_pad, int out_pad, int in_dim,
+                                                             int out_dim, float *__restrict__ d_w, int ldw, float seed_value,
+                                                             const float *__restrict__ seed_dev)
 {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= in_dim * out_dim) return;
-    const int k = e / out_dim, j = e % out_dim;
-    float s = 0.0f;
-    for (int z = 0; z < n_part; ++z) s += partial[((size_t)z * in_pad + k) * out_pad + j];
-    d_w[(size_t)k * ldw + j] += seed_value * (seed_dev ? __ldg(seed_dev) : 1.0f) * s;
-}
-
-// d_b[j] += scale * sum_i dZ[i][j]; dZ bf16 [rows][ld].  One block per 64 columns x row slab, then atomics-free
-// two-level: blocks write partials, a second launch reduces (reuses wide_dw_reduce_kernel with in_dim = 1).
-__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16 *__restrict__ Z, int ld, long long rows, long long rows_per_block,
-                                                          int cols, float *__restrict__ partial)
-{
-    // thread t: column pair (t & 31) * 2 of a 64-column group?  keep it simple: 256 threads = 8 row lanes x 32 column pairs
-    __shared__ float acc[8][64];
-    const int cp = threadIdx.x & 31, rl = threadIdx.x >> 5;
-    const int c0 = blockIdx.y * 64 + cp * 2;
-    const long long r_begin = (long long)blockIdx.x * rows_per_block;
-    long long r_end = r_begin + rows_per_block;
-    if (r_end > rows) r_end = rows;
-    float s0 = 0.f, s1 = 0.f;
-    if (c0 < cols)
-        for (long long r = r_begin + rl; r < r_end; r += 8) {
-            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162 *>(Z + r * ld + c0);
-            s0 += __bfloat162float(v.x); s1 += __bfloat162float(v.y);
+    __shared__ float4 acc[8][32];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int e = (blockIdx.x * 32 + lane) * 4;                 // first of four consecutive padded elements
+    const size_t stride = (size_t)in_pad * out_pad;
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+    if (e < in_pad * out_pad) {
+        int z = grp;
+        for (; z + 8 < n_part; z += 16) {
+            const float4 a = *reinterpret_cast<const float4 *>(partial + (size_t)z * stride + e);
+            const float4 b = *reinterpret_cast<const float4 *>(partial + (size_t)(z + 8) * stride + e);
+            s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+            s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
         }
-    acc[rl][cp * 2] = s0; acc[rl][cp * 2 + 1] = s1;
+        if (z < n_part) {
+            const float4 a = *reinterpret_cast<const float4 *>(partial + (size_t)z * stride + e);
+            s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+        }
+    }
+    acc[grp][lane] = make_float4(s0.x + s1.x, s0.y + s1.y, s0.z + s1.z, s0.w + s1.w);
     __syncthreads();
-    if (threadIdx.x < 64) {
-        float s = 0.f;
-        for (int i = 0; i < 8; ++i) s += acc[i][threadIdx.x];
-        const int c = blockIdx.y * 64 + threadIdx.x;
-        if (c < cols) partial[(size_t)blockIdx.x * cols + c] = s;
+    if (grp == 0 && e < in_pad * out_pad) {
+        float4 s = acc[0][lane];
+        for (int g = 1; g < 8; ++g) { s.x += acc[g][lane].x; s.y += acc[g][lane].y; s.z += acc[g][lane].z; s.w += acc[g][lane].w; }
+        const float scale = seed_value * (seed_dev ? __ldg(seed_dev) : 1.0f);
+        const int k = e / out_pad, j = e % out_pad;
+        if (k < in_dim) {
+            const float v[4] = {s.x, s.y, s.z, s.w};
+            for (int i = 0; i < 4; ++i)
+                if (j + i < out_dim) d_w[(size_t)k * ldw + j + i] += scale * v[i];
+        }
     }
 }
 
+// dst[i][j] = bf16(j < cols ? src[i][j] : 0) for j < ldd (ldd multiple of 8): a thread makes one 16-byte store
 __global__ void f32_to_bf16_rows_kernel(const float *__restrict__ src, int lds, int cols, long long rows, __nv_bfloat16 *__restrict__ dst, int ldd)
 {
-    // dst[i][j] = j < cols ? src[i][j] : 0 for j < ldd
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= rows * ldd) return;
-    const long long i = e / ldd;
-    const int j = (int)(e % ldd);
-    dst[e] = __float2bfloat16_rn(j < cols ? src[i * lds + j] : 0.0f);
+    const int per_row = ldd >> 3;
+    if (e >= rows * per_row) return;
+    const long long i = e / per_row;
+    const int c8 = (int)(e % per_row) * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = c8 + j < cols ? __ldg(src + i * lds + c8 + j) : 0.0f;
+    *reinterpret_cast<uint4 *>(dst + i * ldd + c8) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
 }
 
 // weight images: Wf[l] = [out_pad][in_pad] (forward B operand, K = in), Wb[l] = [in_pad][out_pad] (backward, K = out)
@@ -495,35 +561,39 @@ size_t dw_smem(int in_pad, int out_pad)
 } // namespace
 
 // C = epilogue(A[M x K] * B[N x K]^T): A, B bf16 device pointers, row pitches lda / ldb elements
-// (multiples of 8), K multiple of 64, N multiple of 16 and <= 256.
+// (multiples of 8), K multiple of 64 (<= 256), N multiple of 16 and <= 256.
 int lnb_wide_gemm(lnb_ctx *ctx, const void *A, int lda, const void *B, int ldb, long long M, int N, int K, const float *bias,
-                  const void *mask, int ldmask, void *C, int ldc, int epi, int head)
+                  const uint32_t *bits_in, uint32_t *bits_out, int ldbits, void *C, int ldc, int epi, int head)
 {
-    LNB_ARG(M >= 0 && N >= 16 && N <= 256 && N % 16 == 0 && K >= 64 && K % 64 == 0, "wide gemm: shape");
+    LNB_ARG(M >= 0 && N >= 16 && N <= 256 && N % 16 == 0 && K >= 64 && K <= 256 && K % 64 == 0, "wide gemm: shape");
     LNB_ARG(lda % 8 == 0 && ldb % 8 == 0, "wide gemm: row pitches must be multiples of 8 elements");
     if (M == 0) return LNB_OK;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
-    CUtensorMap mapA, mapB, mapC, mapMask;
+    CUtensorMap mapA, mapB, mapC;
     LNB_TRY(make_map(ctx, &mapA, A, M, K, lda, BM));
     LNB_TRY(make_map(ctx, &mapB, B, N, K, ldb, N));
-    mapC = mapA; mapMask = mapA; // placeholders when unused
+    mapC = mapA; // placeholder when unused
     if (epi == EPI_RELU_BF16 || epi == EPI_MASK_BF16) {
         LNB_ARG(ldc % 8 == 0 && ldc >= ((N + 63) / 64) * 64, "wide gemm: bf16 output pitch must cover whole 64-column boxes");
         LNB_TRY(make_map(ctx, &mapC, C, M, ((N + 63) / 64) * 64, ldc, 32));
-    }
-    if (epi == EPI_MASK_BF16) {
-        LNB_ARG(mask && ldmask % 8 == 0 && ldmask >= ((N + 63) / 64) * 64, "wide gemm: mask pitch");
-        LNB_TRY(make_map(ctx, &mapMask, mask, M, ((N + 63) / 64) * 64, ldmask, 32));
+        LNB_ARG((epi != EPI_MASK_BF16 || bits_in) && (!(bits_in || bits_out) || (ldbits % 2 == 0 && ldbits * 32 >= ((N + 63) / 64) * 64 && ldbits <= 8)),
+                "wide gemm: ReLU bit pattern needs two words per 64 columns");
     }
     GemmParams p{};
-    p.M = (int)M; p.N = N; p.K = K; p.bias = bias; p.mask = (const __nv_bfloat16 *)mask; p.ldmask = ldmask; p.C = C; p.ldc = ldc;
+    p.M = (int)M; p.N = N; p.K = K; p.bias = bias; p.bits_in = bits_in; p.bits_out = bits_out; p.ldbits = ldbits; p.C = C; p.ldc = ldc;
     p.epi = epi; p.head = head;
-    const size_t smem = gemm_smem(N);
-    LNB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    p.a_stages = gemm_a_stages(N, K);
+    LNB_ARG(p.a_stages >= 2, "wide gemm: shared memory");
+    const size_t smem = gemm_smem(N, K, p.a_stages);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        LNB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
     const int n_tiles = (int)((M + BM - 1) / BM);
     const int grid = n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count;
     lnb_prof_begin(ctx, "gemm_tc_kernel");
-    gemm_tc_kernel<<<grid, GEMM_THREADS, smem, ctx->stream>>>(mapA, mapB, mapC, mapMask, p);
+    gemm_tc_kernel<<<grid, GEMM_THREADS, smem, ctx->stream>>>(mapA, mapB, mapC, p);
     lnb_prof_end(ctx);
     LNB_CHECK_LAUNCH();
     return LNB_OK;
@@ -534,20 +604,23 @@ extern "C" LNB_API int lnb_test_wide_gemm(lnb_ctx *ctx, const void *A, const voi
                                           float *C)
 {
     if (!ctx) return LNB_ERR_ARG;
-    return lnb_wide_gemm(ctx, A, K, B, K, M, N, K, bias, nullptr, 0, C, N, EPI_NONE_F32, 0);
+    return lnb_wide_gemm(ctx, A, K, B, K, M, N, K, bias, nullptr, nullptr, 0, C, N, EPI_NONE_F32, 0);
 }
 
-// test hook: bf16 C = relu(A B^T + bias), or masked by `mask` (> 0) when mask != NULL
+// test hook: bf16 C = relu(A B^T + bias) (+ its ReLU bit pattern into bits_out), or, when bits_in != NULL,
+// C = A B^T where the bit is set and 0 elsewhere.  Bit rows are N/32 words.
 extern "C" LNB_API int lnb_test_wide_gemm_bf16(lnb_ctx *ctx, const void *A, const void *B, long long M, int N, int K, const float *bias,
-                                               const void *mask, void *C)
+                                               const void *bits_in, void *bits_out, void *C)
 {
     if (!ctx) return LNB_ERR_ARG;
-    return lnb_wide_gemm(ctx, A, K, B, K, M, N, K, bias, mask, N, C, N, mask ? EPI_MASK_BF16 : EPI_RELU_BF16, 0);
+    return lnb_wide_gemm(ctx, A, K, B, K, M, N, K, bias, (const uint32_t *)bits_in, (uint32_t *)bits_out, ((N + 63) / 64) * 2, C, N,
+                         bits_in ? EPI_MASK_BF16 : EPI_RELU_BF16, 0);
 }
 
-// dW partials of one layer: returns the number of partials through *n_part
+// dW partials of one layer ([n_part][in_pad][out_pad] fp32) and, if colsum != NULL, the column sums of
+// dZ per CTA ([n_part][out_pad])
 int lnb_wide_dw(lnb_ctx *ctx, const void *H, int ldh, int in_pad, const void *dZ, int ldz, int out_pad, long long rows,
-                float *partial, int n_part)
+                float *partial, float *colsum, int n_part)
 {
     LNB_ARG(in_pad % 64 == 0 && in_pad >= 64 && in_pad <= 256 && out_pad % 64 == 0 && out_pad >= 64 && out_pad <= 256, "wide dW: padded widths");
     if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
@@ -557,33 +630,50 @@ int lnb_wide_dw(lnb_ctx *ctx, const void *H, int ldh, int in_pad, const void *dZ
     DwParams p{};
     p.rows = rows;
     p.rows_per_cta = ((rows + n_part - 1) / n_part + 63) / 64 * 64;
-    p.in_pad = in_pad; p.out_pad = out_pad; p.partial = partial;
+    p.in_pad = in_pad; p.out_pad = out_pad; p.partial = partial; p.colsum = colsum;
     const size_t smem = dw_smem(in_pad, out_pad);
-    LNB_CUDA(cudaFuncSetAttribute(dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        LNB_CUDA(cudaFuncSetAttribute(dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
     lnb_prof_begin(ctx, "dw_tc_kernel");
-    dw_tc_kernel<<<n_part, GEMM_THREADS, smem, ctx->stream>>>(mapH, mapZ, p);
+    dw_tc_kernel<<<n_part, DW_THREADS, smem, ctx->stream>>>(mapH, mapZ, p);
     lnb_prof_end(ctx);
     LNB_CHECK_LAUNCH();
     return LNB_OK;
 }
 
-// test hook: fp32 dW[in_pad][out_pad] = H^T dZ from bf16 H [rows][in_pad], dZ [rows][out_pad]
-extern "C" LNB_API int lnb_test_wide_dw(lnb_ctx *ctx, const void *H, int in_pad, const void *dZ, int out_pad, long long rows, float *dW)
+// test hook: fp32 dW[in_pad][out_pad] = H^T dZ and db[out_pad] = colsum(dZ) from bf16 H [rows][in_pad], dZ [rows][out_pad]
+extern "C" LNB_API int lnb_test_wide_dw(lnb_ctx *ctx, const void *H, int in_pad, const void *dZ, int out_pad, long long rows, float *dW,
+                                        float *db)
 {
     if (!ctx) return LNB_ERR_ARG;
     const int n_part = ctx->sm_count;
-    LNB_TRY(lnb_arena_reserve(ctx, (size_t)n_part * in_pad * out_pad * sizeof(float) + 4096));
+    LNB_TRY(lnb_arena_reserve(ctx, (size_t)n_part * (in_pad + 1) * out_pad * sizeof(float) + 8192));
     float *partial = (float *)lnb_arena_take(ctx, (size_t)n_part * in_pad * out_pad * sizeof(float));
-    LNB_TRY(lnb_wide_dw(ctx, H, in_pad, in_pad, dZ, out_pad, out_pad, rows, partial, n_part));
+    float *bpartial = (float *)lnb_arena_take(ctx, (size_t)n_part * out_pad * sizeof(float));
+    LNB_TRY(lnb_wide_dw(ctx, H, in_pad, in_pad, dZ, out_pad, out_pad, rows, partial, db ? bpartial : nullptr, n_part));
     LNB_CUDA(cudaMemsetAsync(dW, 0, (size_t)in_pad * out_pad * sizeof(float), ctx->stream));
-    wide_dw_reduce_kernel<<<(in_pad * out_pad + 255) / 256, 256, 0, ctx->stream>>>(partial, n_part, in_pad, out_pad, in_pad, out_pad, dW, out_pad, 1.0f, nullptr);
+    wide_dw_reduce_kernel<<<(in_pad * out_pad + 127) / 128, 256, 0, ctx->stream>>>(partial, n_part, in_pad, out_pad, in_pad, out_pad, dW, out_pad, 1.0f, nullptr);
     LNB_CHECK_LAUNCH();
+    if (db) {
+        LNB_CUDA(cudaMemsetAsync(db, 0, (size_t)out_pad * sizeof(float), ctx->stream));
+        wide_dw_reduce_kernel<<<(out_pad + 127) / 128, 256, 0, ctx->stream>>>(bpartial, n_part, 1, out_pad, 1, out_pad, db, out_pad, 1.0f, nullptr);
+        LNB_CHECK_LAUNCH();
+    }
     return LNB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
 // The wide-MLP step: layerwise on the tensor cores (see the header of this file).  Produces what
 // the fused kernel produces: loss, colour, d_ws, d_bs.  Returns LNB_ERR_UNSUPPORTED otherwise.
+//
+// The forward and the adjoint chain run over SLABS of whole rays small enough that a layer's
+// activations (slab x 256 bf16) are still in the 126 MB L2 when the next layer reads them, so HBM
+// sees each activation / adjoint tensor written once (they are kept: the weight gradient needs
+// H_l and dZ_l of every layer) instead of written and read back.  The weight gradients then run
+// once per layer over the whole batch, which keeps their per-CTA TMEM accumulation long.
 // ---------------------------------------------------------------------------------------------
 static int pad64(int v) { return (v + 63) / 64 * 64; }
 
@@ -609,37 +699,49 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
     if (a->want_grad && !a->target) return unsupported("gradient without target");
     if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
     const bool rays = !a->X && a->rays_o;
+    const bool grad = a->want_grad != 0;
     const int c_in = mlp->dims[0];
     int in_pad[LNB_MAX_LAYERS], out_pad[LNB_MAX_LAYERS];
     for (int l = 0; l < L; ++l) { in_pad[l] = pad64(mlp->dims[l]); out_pad[l] = pad64(mlp->dims[l + 1]); }
     const int n_part = ctx->sm_count;
 
+    // ---- slab of rays: k waves of 128-sample tiles over the SMs (LNB_WIDE_SLAB_WAVES, 0 = whole batch)
+    static const int slab_waves = [] { const char *e = getenv("LNB_WIDE_SLAB_WAVES"); return e ? atoi(e) : 0; }();
+    int slab_rays = R;
+    if (slab_waves > 0 && S > 0) {
+        const long long r = (long long)slab_waves * ctx->sm_count * BM / S;
+        slab_rays = (int)(r < 1 ? 1 : (r > R ? R : r));
+    }
+
     // ---- arena plan
     size_t need = 1 << 16;
     auto add = [&](size_t bytes) { need += (bytes + 255) / 256 * 256 + 256; };
-    size_t h_bytes[LNB_MAX_LAYERS];
-    for (int l = 0; l < L; ++l) { h_bytes[l] = (size_t)N * in_pad[l] * 2; add(h_bytes[l]); }
-    int max_pad = 64;
-    for (int l = 0; l < L; ++l) { max_pad = in_pad[l] > max_pad ? in_pad[l] : max_pad; max_pad = out_pad[l] > max_pad ? out_pad[l] : max_pad; }
-    if (a->want_grad) { add((size_t)N * max_pad * 2); add((size_t)N * max_pad * 2); add((size_t)N * 16); }
-    add((size_t)N * 16);                                        // head fp32 [N][4]
+    for (int l = 0; l < L; ++l) {
+        add((size_t)N * in_pad[l] * 2);                          // H_l (bf16)
+        if (grad) { add((size_t)N * out_pad[l] * 2); add((size_t)N * (in_pad[l] / 32) * 4); }   // dZ_l, ReLU bits of H_l
+    }
+    if (grad) add((size_t)N * 16);                               // head adjoint fp32 [N][4]
+    add((size_t)N * 16);                                         // head fp32 [N][4]
     if (rays) { add((size_t)N * c_in * 4); add((size_t)R * S * 4); }
     for (int l = 0; l < L; ++l) { add((size_t)in_pad[l] * out_pad[l] * 2); add((size_t)in_pad[l] * out_pad[l] * 2); add((size_t)out_pad[l] * 4); }
     add((size_t)n_part * 256 * 256 * 4);
-    add((size_t)2 * n_part * 256 * 4);
+    add((size_t)n_part * 256 * 4);
     add((size_t)R * 4 + 16); add((size_t)R * 12 + 16); add(64);
     LNB_TRY(lnb_arena_reserve(ctx, need));
     auto take = [&](size_t bytes) { return lnb_arena_take(ctx, bytes); };
-    __nv_bfloat16 *H[LNB_MAX_LAYERS];
-    for (int l = 0; l < L; ++l) H[l] = (__nv_bfloat16 *)take(h_bytes[l]);
-    __nv_bfloat16 *dZa = nullptr, *dZb = nullptr;
-    float *dzh = nullptr;
-    if (a->want_grad) { dZa = (__nv_bfloat16 *)take((size_t)N * max_pad * 2); dZb = (__nv_bfloat16 *)take((size_t)N * max_pad * 2); dzh = (float *)take((size_t)N * 16); }
+    __nv_bfloat16 *H[LNB_MAX_LAYERS], *dZ[LNB_MAX_LAYERS];
+    uint32_t *bits[LNB_MAX_LAYERS];
+    for (int l = 0; l < L; ++l) {
+        H[l] = (__nv_bfloat16 *)take((size_t)N * in_pad[l] * 2);
+        dZ[l] = grad ? (__nv_bfloat16 *)take((size_t)N * out_pad[l] * 2) : nullptr;
+        bits[l] = grad ? (uint32_t *)take((size_t)N * (in_pad[l] / 32) * 4) : nullptr;
+    }
+    float *dzh = grad ? (float *)take((size_t)N * 16) : nullptr;
     float *head = (float *)take((size_t)N * 16);
     const float *X = a->X, *dists = a->dists;
     if (rays) {
         float *Xe = (float *)take((size_t)N * c_in * 4), *de = (float *)take((size_t)R * S * 4);
-        LNB_TRY(lnb_launch_sample_encode(ctx, a->rays_o, a->rays_d, a->t, a->ray_dtype == LNB_RAY_F64, R, S, a->pe_bands, Xe, de));
+        if (N > 0) LNB_TRY(lnb_launch_sample_encode(ctx, a->rays_o, a->rays_d, a->t, a->ray_dtype == LNB_RAY_F64, R, S, a->pe_bands, Xe, de));
         X = Xe; dists = de;
     }
     __nv_bfloat16 *Wf[LNB_MAX_LAYERS], *Wb[LNB_MAX_LAYERS];
@@ -650,7 +752,7 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
         biasP[l] = (float *)take((size_t)out_pad[l] * 4);
     }
     float *partial = (float *)take((size_t)n_part * 256 * 256 * 4);
-    float *bpartial = (float *)take((size_t)2 * n_part * 256 * 4);
+    float *bpartial = (float *)take((size_t)n_part * 256 * 4);
     float *ray_sse = (float *)take((size_t)R * 4 + 16);
     float *color = a->color ? a->color : (float *)take((size_t)R * 12 + 16);
     float *loss = a->loss ? a->loss : (float *)take(64);
@@ -659,7 +761,7 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
         return LNB_OK;
     }
 
-    // ---- weight images, padded biases, bf16 features
+    // ---- weight images, padded biases
     for (int l = 0; l < L; ++l) {
         const int n = in_pad[l] * out_pad[l];
         wide_prep_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(a->ws + (size_t)l * mlp->max_in * mlp->max_out, mlp->max_out, mlp->dims[l],
@@ -668,53 +770,53 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
         LNB_CUDA(cudaMemsetAsync(biasP[l], 0, (size_t)out_pad[l] * 4, ctx->stream));
         LNB_CUDA(cudaMemcpyAsync(biasP[l], a->bs + (size_t)l * mlp->max_out, (size_t)mlp->dims[l + 1] * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     }
-    {
-        const long long n = N * in_pad[0];
-        f32_to_bf16_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(X, c_in, c_in, N, H[0], in_pad[0]);
-        LNB_CHECK_LAUNCH();
-    }
-    // ---- forward
-    for (int l = 0; l < L - 1; ++l)
-        LNB_TRY(lnb_wide_gemm(ctx, H[l], in_pad[l], Wf[l], in_pad[l], N, out_pad[l], in_pad[l], biasP[l], nullptr, 0, H[l + 1], out_pad[l],
-                              EPI_RELU_BF16, 0));
-    LNB_TRY(lnb_wide_gemm(ctx, H[L - 1], in_pad[L - 1], Wf[L - 1], in_pad[L - 1], N, 16, in_pad[L - 1], biasP[L - 1], nullptr, 0, head, 4,
-                          EPI_HEAD_F32, mlp->head));
-    LNB_TRY(lnb_launch_composite_fwd(ctx, head, 4, dists, a->target, R, S, nullptr, nullptr, nullptr, nullptr, color, 0, ray_sse));
-    if (a->target) LNB_TRY(lnb_launch_sum(ctx, ray_sse, R, loss));
-    else if (a->loss) LNB_TRY(lnb_launch_fill(ctx, loss, 1, 0.0f));
-    if (!a->want_grad) return LNB_OK;
 
-    // ---- backward (unit seed inside; d_ws / d_bs scaled by the seed as they are accumulated)
-    const float *seed_dev = a->seed_mode == LNB_SEED_LOSS ? loss : nullptr;
-    const float seed_val = a->seed_mode == LNB_SEED_LOSS ? 1.0f : a->seed;
-    LNB_TRY(lnb_launch_composite_bwd(ctx, head, 4, dists, a->target, color, R, S, dzh, 4, 4, nullptr, nullptr));
-    {
-        const long long n = N * out_pad[L - 1];
-        f32_to_bf16_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dzh, 4, 4, N, dZa, out_pad[L - 1]);
-        LNB_CHECK_LAUNCH();
-    }
-    __nv_bfloat16 *dZ = dZa, *dZn = dZb;
-    for (int l = L - 1; l >= 0; --l) {
-        const int in_l = mlp->dims[l], out_l = mlp->dims[l + 1];
-        LNB_TRY(lnb_wide_dw(ctx, H[l], in_pad[l], in_pad[l], dZ, out_pad[l], out_pad[l], N, partial, n_part));
-        wide_dw_reduce_kernel<<<(in_l * out_l + 255) / 256, 256, 0, ctx->stream>>>(partial, n_part, in_pad[l], out_pad[l], in_l, out_l,
-                                                                                  a->d_ws + (size_t)l * mlp->max_in * mlp->max_out, mlp->max_out,
-                                                                                  seed_val, seed_dev);
-        LNB_CHECK_LAUNCH();
+    // ---- forward and adjoint chain, slab by slab (unit seed; the seed scales d_ws / d_bs at the end)
+    for (int r0 = 0; r0 < R; r0 += slab_rays) {
+        const int Rs = R - r0 < slab_rays ? R - r0 : slab_rays;
+        const long long n0 = (long long)r0 * S, Ns = (long long)Rs * S;
         {
-            const int nblk = 2 * n_part;
-            const long long rpb = (N + nblk - 1) / nblk;
-            colsum_bf16_kernel<<<dim3(nblk, out_pad[l] / 64), 256, 0, ctx->stream>>>(dZ, out_pad[l], N, rpb, out_pad[l], bpartial);
-            LNB_CHECK_LAUNCH();
-            wide_dw_reduce_kernel<<<(out_l + 255) / 256, 256, 0, ctx->stream>>>(bpartial, nblk, 1, out_pad[l], 1, out_l,
-                                                                                a->d_bs + (size_t)l * mlp->max_out, mlp->max_out, seed_val, seed_dev);
+            const long long n = Ns * (in_pad[0] / 8);
+            f32_to_bf16_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(X + n0 * c_in, c_in, c_in, Ns, H[0] + n0 * in_pad[0], in_pad[0]);
             LNB_CHECK_LAUNCH();
         }
-        if (l == 0) break;
-        // dZ_{l-1} = (dZ_l W_l^T) masked by H_l > 0
-        LNB_TRY(lnb_wide_gemm(ctx, dZ, out_pad[l], Wb[l], out_pad[l], N, in_pad[l], out_pad[l], nullptr, H[l], in_pad[l], dZn, in_pad[l],
-                              EPI_MASK_BF16, 0));
-        __nv_bfloat16 *t = dZ; dZ = dZn; dZn = t;
+        for (int l = 0; l < L - 1; ++l)
+            LNB_TRY(lnb_wide_gemm(ctx, H[l] + n0 * in_pad[l], in_pad[l], Wf[l], in_pad[l], Ns, out_pad[l], in_pad[l], biasP[l], nullptr,
+                                  grad ? bits[l + 1] + n0 * (in_pad[l + 1] / 32) : nullptr, in_pad[l + 1] / 32, H[l + 1] + n0 * out_pad[l], out_pad[l],
+                                  EPI_RELU_BF16, 0));
+        LNB_TRY(lnb_wide_gemm(ctx, H[L - 1] + n0 * in_pad[L - 1], in_pad[L - 1], Wf[L - 1], in_pad[L - 1], Ns, 16, in_pad[L - 1], biasP[L - 1],
+                              nullptr, nullptr, 0, head + n0 * 4, 4, EPI_HEAD_F32, mlp->head));
+        LNB_TRY(lnb_launch_composite_fwd(ctx, head + n0 * 4, 4, dists + n0, a->target ? a->target + (size_t)r0 * 3 : nullptr, Rs, S, nullptr, nullptr,
+                                         nullptr, nullptr, color + (size_t)r0 * 3, 0, ray_sse + r0));
+        if (!grad) continue;
+        LNB_TRY(lnb_launch_composite_bwd(ctx, head + n0 * 4, 4, dists + n0, a->target + (size_t)r0 * 3, color + (size_t)r0 * 3, Rs, S, dzh + n0 * 4, 4, 4,
+                                         nullptr, nullptr));
+        {
+            const long long n = Ns * (out_pad[L - 1] / 8);
+            f32_to_bf16_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dzh + n0 * 4, 4, 4, Ns, dZ[L - 1] + n0 * out_pad[L - 1], out_pad[L - 1]);
+            LNB_CHECK_LAUNCH();
+        }
+        for (int l = L - 1; l >= 1; --l)   // dZ_{l-1} = (dZ_l W_l^T) where H_l > 0
+            LNB_TRY(lnb_wide_gemm(ctx, dZ[l] + n0 * out_pad[l], out_pad[l], Wb[l], out_pad[l], Ns, in_pad[l], out_pad[l], nullptr,
+                                  bits[l] + n0 * (in_pad[l] / 32), nullptr, in_pad[l] / 32, dZ[l - 1] + n0 * in_pad[l], in_pad[l], EPI_MASK_BF16, 0));
+    }
+    if (a->target) LNB_TRY(lnb_launch_sum(ctx, ray_sse, R, loss));
+    else if (a->loss) LNB_TRY(lnb_launch_fill(ctx, loss, 1, 0.0f));
+    if (!grad) return LNB_OK;
+
+    // ---- weight and bias gradients over the whole batch
+    const float *seed_dev = a->seed_mode == LNB_SEED_LOSS ? loss : nullptr;
+    const float seed_val = a->seed_mode == LNB_SEED_LOSS ? 1.0f : a->seed;
+    for (int l = L - 1; l >= 0; --l) {
+        const int in_l = mlp->dims[l], out_l = mlp->dims[l + 1];
+        LNB_TRY(lnb_wide_dw(ctx, H[l], in_pad[l], in_pad[l], dZ[l], out_pad[l], out_pad[l], N, partial, bpartial, n_part));
+        wide_dw_reduce_kernel<<<(in_pad[l] * out_pad[l] + 127) / 128, 256, 0, ctx->stream>>>(partial, n_part, in_pad[l], out_pad[l], in_l, out_l,
+                                                                                            a->d_ws + (size_t)l * mlp->max_in * mlp->max_out,
+                                                                                            mlp->max_out, seed_val, seed_dev);
+        LNB_CHECK_LAUNCH();
+        wide_dw_reduce_kernel<<<(out_pad[l] + 127) / 128, 256, 0, ctx->stream>>>(bpartial, n_part, 1, out_pad[l], 1, out_l,
+                                                                                a->d_bs + (size_t)l * mlp->max_out, mlp->max_out, seed_val, seed_dev);
+        LNB_CHECK_LAUNCH();
     }
     return LNB_OK;
 }

@@ -43,7 +43,13 @@ def test_wide_gemm_matches_fp32_product_of_bf16_operands(ctx, torch_cuda, M, N, 
     assert rel_err(C.cpu().numpy(), ref.cpu().numpy()) <= 2e-5
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (1000, 256, 256), (4096 + 77, 128, 64), (50000, 256, 256)])
+def _pack_bits(torch, positive):
+    """[M][N] bool -> [M][N/32] uint32, bit j of word w <-> column 32 w + j (the kernel's ReLU pattern layout)"""
+    packed = np.packbits(positive.cpu().numpy().astype(np.uint8), axis=1, bitorder="little")
+    return torch.as_tensor(np.ascontiguousarray(packed).view(np.int32)).cuda()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (1000, 256, 256), (4096 + 77, 128, 64), (50000, 256, 256), (777, 192, 128)])
 @pytest.mark.parametrize("masked", [False, True])
 def test_wide_gemm_bf16_epilogues(ctx, torch_cuda, M, N, K, masked):
     torch = torch_cuda
@@ -51,18 +57,24 @@ def test_wide_gemm_bf16_epilogues(ctx, torch_cuda, M, N, K, masked):
     A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16).contiguous()
     B = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(torch.bfloat16).contiguous()
     bias = torch.randn(N, device="cuda", generator=g)
-    mask = torch.relu(torch.randn(M, N, device="cuda", generator=g)).to(torch.bfloat16).contiguous()
+    positive = torch.randn(M, N, device="cuda", generator=g) > 0
+    bits_in = _pack_bits(torch, positive)
+    bits_out = torch.full((M, N // 32), -1, dtype=torch.int32, device="cuda")
     C = torch.full((M, N), float("nan"), device="cuda").to(torch.bfloat16)
     lib = ctx.lib
-    lib.lnb_test_wide_gemm_bf16.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_longlong, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 3
+    lib.lnb_test_wide_gemm_bf16.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_longlong, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4
     ctx._check(lib.lnb_test_wide_gemm_bf16(ctx.h, A.data_ptr(), B.data_ptr(), M, N, K, None if masked else bias.data_ptr(),
-                                           mask.data_ptr() if masked else None, C.data_ptr()))
+                                           bits_in.data_ptr() if masked else None, None if masked else bits_out.data_ptr(), C.data_ptr()))
     ctx.synchronize()
     acc = A.float() @ B.float().t()
-    ref = torch.where(mask > 0, acc, torch.zeros_like(acc)) if masked else torch.relu(acc + bias)
+    ref = torch.where(positive, acc, torch.zeros_like(acc)) if masked else torch.relu(acc + bias)
     got = C.float().cpu().numpy()
     assert np.isfinite(got).all()
     assert rel_err(got, ref.to(torch.bfloat16).float().cpu().numpy()) <= 1e-2    # one bf16 rounding of the output
+    if masked:
+        assert (got[~positive.cpu().numpy()] == 0).all()
+    else:   # the recorded pattern is exactly the sign pattern of what was stored
+        assert (bits_out.cpu().numpy() == _pack_bits(torch, C.float() > 0).cpu().numpy()).all()
 
 
 @pytest.mark.parametrize("rows,in_pad,out_pad", [(64, 64, 64), (1000, 256, 256), (100000, 64, 256), (33333, 256, 64), (5000, 128, 192)])
@@ -72,12 +84,15 @@ def test_wide_dw_matches_fp32_product(ctx, torch_cuda, rows, in_pad, out_pad):
     H = torch.relu(torch.randn(rows, in_pad, device="cuda", generator=g)).to(torch.bfloat16).contiguous()
     Z = (torch.randn(rows, out_pad, device="cuda", generator=g) * 0.1).to(torch.bfloat16).contiguous()
     dW = torch.full((in_pad, out_pad), float("nan"), device="cuda")
+    db = torch.full((out_pad,), float("nan"), device="cuda")
     lib = ctx.lib
-    lib.lnb_test_wide_dw.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p]
-    ctx._check(lib.lnb_test_wide_dw(ctx.h, H.data_ptr(), in_pad, Z.data_ptr(), out_pad, rows, dW.data_ptr()))
+    lib.lnb_test_wide_dw.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong,
+                                     ctypes.c_void_p, ctypes.c_void_p]
+    ctx._check(lib.lnb_test_wide_dw(ctx.h, H.data_ptr(), in_pad, Z.data_ptr(), out_pad, rows, dW.data_ptr(), db.data_ptr()))
     ctx.synchronize()
     ref = (H.double().t() @ Z.double()).float()
     assert rel_err(dW.cpu().numpy(), ref.cpu().numpy()) <= 2e-5
+    assert rel_err(db.cpu().numpy(), Z.double().sum(0).float().cpu().numpy()) <= 2e-5
 
 
 from conftest import golden_files, load_golden  # noqa: E402
