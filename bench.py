@@ -355,10 +355,15 @@ def run_ours(args):
             frames.append(tuple(torch.as_tensor(v, device=device) for v in (fo, fd, ft)))
         col = torch.zeros((Hh * Hh, 3), dtype=torch.float32, device=device)
 
+        # the wide (layerwise) path keeps two bf16 activation tensors per call: bound a call to ~8 M samples
+        ray_chunk = Hh * Hh if w["width"] <= 62 else max(1024, (8 << 20) // S)
+
         def render_frame(i):
             fo, fd, ft = frames[i % 2]
-            ctx.nerf_step_rays(dims, fo, fd, ft, E, ws_d, bs_d, target=None, grad=False, outputs=("color",),
-                               out={"color": col}, path=path)
+            for r0 in range(0, Hh * Hh, ray_chunk):
+                r1 = min(Hh * Hh, r0 + ray_chunk)
+                ctx.nerf_step_rays(dims, fo[r0:r1], fd[r0:r1], ft[r0:r1], E, ws_d, bs_d, target=None, grad=False, outputs=("color",),
+                                   out={"color": col[r0:r1]}, path=path)
 
         ws_d, bs_d = (torch.as_tensor(v, device=device) for v in trainer.read()[:2])
         for i in range(2):
@@ -404,7 +409,44 @@ def run_ours(args):
                                                     "memory, sample positions and positional encoding on the device"}}
         fl = flops_per_sample(dims)
         alg_bytes = (N * 8 + R * 60) if use_rays else (N * (c_in * 4 + 4) + R * 12)
-        if prof:
+        if prof and prof["kernel"] == "gemm_tc_kernel":
+            # wide MLP: layerwise tensor-core GEMMs with bf16 activations in HBM (wide_tc.cu).  Per launch the
+            # kernel reads A (rows x K bf16) [+ 32 B/row of ReLU bits when masked] and writes rows x 256 bf16
+            # [+ 32 B/row of bits] (the head writes 16 B/row): summed over the step's launches below.
+            sec = prof["ms_per_launch"] * 1e-3
+            pad = lambda v: (v + 63) // 64 * 64  # noqa: E731
+            Lw = len(dims) - 1
+            gemms = [(pad(dims[l]), pad(dims[l + 1]), N * (pad(dims[l]) * 2 + pad(dims[l + 1]) * 2 + pad(dims[l + 1]) // 8)) for l in range(Lw - 1)]
+            gemms.append((pad(dims[Lw - 1]), 16, N * (pad(dims[Lw - 1]) * 2 + 16)))
+            gemms += [(pad(dims[l + 1]), pad(dims[l]), N * (pad(dims[l + 1]) * 2 + pad(dims[l]) * 2 + pad(dims[l]) // 8)) for l in range(Lw - 1, 0, -1)]
+            bytes_launch = sum(g[2] for g in gemms) / len(gemms)
+            flops_launch = sum(2.0 * N * g[0] * g[1] for g in gemms) / len(gemms)
+            peak = peaks.get("hbm_gbs", 6650.0)
+            ach = bytes_launch / sec / 1e9
+            traffic, traffic_src = None, None
+            prof_csv = os.path.join(ROOT, "profiles", "r01_wide_c5_ncu_full_per_launch.csv")
+            if args.workload == "c5" and os.path.exists(prof_csv):
+                try:
+                    import csv as _csv
+                    rows = [r for r in _csv.reader(open(prof_csv))][1:]
+                    g = [float(r[4]) + float(r[5]) for r in rows if r[2] == "gemm_tc_kernel"]   # Mbyte read + written
+                    if g:
+                        traffic, traffic_src = sum(g) / len(g) * 1e6, "profiles/r01_wide_c5_ncu_full_per_launch.csv (mean of the step's %d launches)" % len(g)
+                except Exception:
+                    pass
+            tpeak = peaks.get("bf16_tflops_sustained", 1389.4)
+            line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                "traffic": traffic, "traffic_source": traffic_src, "kernel": prof["kernel"], "us_per_launch": sec * 1e6,
+                                "launches_timed": prof["launches"], "launches_per_step": len(gemms),
+                                "algorithmic_bytes_per_launch": bytes_launch, "algorithmic_tflops": flops_launch / sec / 1e12,
+                                "step_tflops": N * fl / (ms / args.steps * 1e-3) / 1e12,
+                                "step_tensor_frac": N * fl / (ms / args.steps * 1e-3) / 1e12 / tpeak,
+                                "tensor_peak": tpeak,
+                                "note": "layerwise design: every GEMM streams its activations through HBM, so the kernel is bound by "
+                                        "HBM (frac) although the step as a whole is compute-heavy; step_tensor_frac is SURVEY 8d's "
+                                        "F_train x samples / step time against the sustained bf16 peak",
+                                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy), bf16_tflops_sustained" if peaks else "fallback 6650 GB/s, 1389 TFLOP/s"}
+        elif prof:
             sec = prof["ms_per_launch"] * 1e-3
             if use_rays:
                 peak = peaks.get("bf16_tflops", 1590.0)

@@ -637,9 +637,7 @@ int lnb_wide_dw(lnb_ctx *ctx, const void *H, int ldh, int in_pad, const void *dZ
         LNB_CUDA(cudaFuncSetAttribute(dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    lnb_prof_begin(ctx, "dw_tc_kernel");
     dw_tc_kernel<<<n_part, DW_THREADS, smem, ctx->stream>>>(mapH, mapZ, p);
-    lnb_prof_end(ctx);
     LNB_CHECK_LAUNCH();
     return LNB_OK;
 }
@@ -716,10 +714,13 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
     // ---- arena plan
     size_t need = 1 << 16;
     auto add = [&](size_t bytes) { need += (bytes + 255) / 256 * 256 + 256; };
+    int max_pad = 64;
+    for (int l = 0; l < L; ++l) max_pad = in_pad[l] > max_pad ? in_pad[l] : max_pad;
     for (int l = 0; l < L; ++l) {
-        add((size_t)N * in_pad[l] * 2);                          // H_l (bf16)
+        if (grad || l == 0) add((size_t)N * in_pad[l] * 2);      // H_l (bf16): all kept for the backward pass,
         if (grad) { add((size_t)N * out_pad[l] * 2); add((size_t)N * (in_pad[l] / 32) * 4); }   // dZ_l, ReLU bits of H_l
     }
+    if (!grad) { add((size_t)N * max_pad * 2); add((size_t)N * max_pad * 2); }   // render: two buffers in turn
     if (grad) add((size_t)N * 16);                               // head adjoint fp32 [N][4]
     add((size_t)N * 16);                                         // head fp32 [N][4]
     if (rays) { add((size_t)N * c_in * 4); add((size_t)R * S * 4); }
@@ -731,8 +732,10 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
     auto take = [&](size_t bytes) { return lnb_arena_take(ctx, bytes); };
     __nv_bfloat16 *H[LNB_MAX_LAYERS], *dZ[LNB_MAX_LAYERS];
     uint32_t *bits[LNB_MAX_LAYERS];
+    __nv_bfloat16 *pp[2] = {nullptr, nullptr};
+    if (!grad) { pp[0] = (__nv_bfloat16 *)take((size_t)N * max_pad * 2); pp[1] = (__nv_bfloat16 *)take((size_t)N * max_pad * 2); }
     for (int l = 0; l < L; ++l) {
-        H[l] = (__nv_bfloat16 *)take((size_t)N * in_pad[l] * 2);
+        H[l] = (grad || l == 0) ? (__nv_bfloat16 *)take((size_t)N * in_pad[l] * 2) : pp[(l - 1) & 1];
         dZ[l] = grad ? (__nv_bfloat16 *)take((size_t)N * out_pad[l] * 2) : nullptr;
         bits[l] = grad ? (uint32_t *)take((size_t)N * (in_pad[l] / 32) * 4) : nullptr;
     }

@@ -2,9 +2,10 @@
 the metric/unit/value CSV kept under profiles/."""
 import csv, subprocess, sys
 rep, out = sys.argv[1], sys.argv[2]
+idx = int(sys.argv[3]) if len(sys.argv) > 3 else 0   # which captured launch (0-based) to digest
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
-hdr, units, d = rows[0], rows[1], rows[2]
+hdr, units, d = rows[0], rows[1], rows[2 + idx]
 keep = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct',
         'sm__pipe_tensor_cycles_active.avg', 'sm__pipe_tc_cycles_active.avg', 'sm__warps_active.avg.pct', 'launch__registers_per_thread',
         'launch__grid_size', 'launch__block_size', 'launch__shared_mem_per_block_dynamic', 'launch__occupancy_limit',
