@@ -48,6 +48,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// L2 eviction-priority operands for TMA (the fixed encodings createpolicy.fractional produces for 1.0)
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull, L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap *map, uint32_t src, int c0, int c1, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(map), "r"(src), "r"(c0), "r"(c1), "l"(policy) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1)
 {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
@@ -89,6 +101,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr) : "memory");
 }
+// Programmatic dependent launch: a kernel launched with the attribute may start while its predecessor
+// drains; everything it reads that the predecessor wrote must come after pdl_wait().  Every kernel here
+// triggers its own dependents only AFTER its wait, so data from two or more launches back (weights,
+// biases) may be fetched before the wait.  Both are no-ops in a plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor for a 128-byte-swizzled tile whose rows are 128 B (64 bf16) apart and
@@ -124,11 +142,16 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 struct GemmParams {
     int M, N, K;            // N multiple of 16 (<= 256), K multiple of 64 (<= 256)
     const float *bias;      // [N] or NULL
-    const uint32_t *bits_in;   // EPI_MASK_BF16: [M][ldbits] words, bit j of word w <-> column 32 w + j
-    uint32_t *bits_out;        // EPI_RELU_BF16: optional, same layout: which outputs are > 0
+    // ReLU pattern, one bit per element, [M][ldbits] words; word w covers columns 32w .. 32w+31 and column
+    // 32w + 8g + 2j + p sits at bit 16p + 4g + j, so that the two flags of a packed bf16 pair are 16 bits
+    // apart: ((word >> (4g + j)) & 0x00010001) * 0xFFFF is the pair's AND-mask
+    const uint32_t *bits_in;   // EPI_MASK_BF16
+    uint32_t *bits_out;        // EPI_RELU_BF16: optional: which outputs are > 0
     int ldbits;
     void *C; int ldc;       // elements
     int epi, head, a_stages;
+    int reverse;            // walk the tiles from the last to the first (see lnb_wide_tc_step: serpentine order)
+    int l2_hints;           // bit 0: A loads evict-first (read once), bit 1: C stores evict-last (the next kernel reads them)
 };
 
 // D[M x N] = A[M x K] * B[N x K]^T, A and B bf16 row-major (K contiguous), fp32 accumulation in TMEM.
@@ -171,12 +194,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (lane == 0) {
             mbar_expect_tx(bfull, (uint32_t)(kb_count * b_bytes));
             for (int kb = 0; kb < kb_count; ++kb) tma_load_2d(smem_u32(sB + kb * b_stride), &mapB, kb * BK, 0, bfull);
+            pdl_wait();      // the activations below are the previous kernel's output
+            pdl_trigger();
             uint32_t stage = 0, phase = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int at = p.reverse ? n_tiles - 1 - tile : tile;
                 for (int kb = 0; kb < kb_count; ++kb) {
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     mbar_expect_tx(full0 + 8 * stage, (uint32_t)A_STAGE_BYTES);
-                    tma_load_2d(smem_u32(sA + stage * A_STAGE_BYTES), &mapA, kb * BK, tile * BM, full0 + 8 * stage);
+                    if (p.l2_hints & 1) tma_load_2d_hint(smem_u32(sA + stage * A_STAGE_BYTES), &mapA, kb * BK, at * BM, full0 + 8 * stage, L2_EVICT_FIRST);
+                    else tma_load_2d(smem_u32(sA + stage * A_STAGE_BYTES), &mapA, kb * BK, at * BM, full0 + 8 * stage);
                     if (++stage == (uint32_t)AS) { stage = 0; phase ^= 1; }
                 }
             }
@@ -210,7 +237,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // take alternate 64-column chunks
         const int q = warp & 3, half = (warp - 2) >> 2;
         uint32_t acc = 0, acc_phase = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        pdl_wait();          // bits_in is the previous kernels' output; stores must not overtake its reads
+        for (int tile_i = blockIdx.x; tile_i < n_tiles; tile_i += gridDim.x) {
+            const int tile = p.reverse ? n_tiles - 1 - tile_i : tile_i;
             const long long row = (long long)tile * BM + q * 32 + lane;
             const bool live = row < p.M;
             uint32_t mw[8];
@@ -283,17 +312,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                 const float r0 = fmaxf(__uint_as_float(v[g * 8 + 2 * j]) + bv[2 * j], 0.0f);
                                 const float r1 = fmaxf(__uint_as_float(v[g * 8 + 2 * j + 1]) + bv[2 * j + 1], 0.0f);
                                 pk[j] = pack_bf16(r0, r1);
-                                b8 |= ((pk[j] & 0xFFFFu) ? 1u : 0u) << (2 * j);
-                                b8 |= ((pk[j] >> 16) ? 1u : 0u) << (2 * j + 1);
+                                // a non-negative bf16 half is non-zero iff adding 0x7FFF carries into its top bit
+                                b8 |= ((((pk[j] & 0x7FFF7FFFu) + 0x7FFF7FFFu) >> (15 - j)) & (0x00010001u << j));
                             }
-                            if (g < 4) lo |= b8 << (g * 8);
-                            else hi |= b8 << ((g - 4) * 8);
+                            if (g < 4) lo |= b8 << (g * 4);
+                            else hi |= b8 << ((g - 4) * 4);
                         } else {
-                            const uint32_t b8 = ((g < 4 ? lo : hi) >> ((g & 3) * 8)) & 0xFFu;
+                            const uint32_t b8 = (g < 4 ? lo : hi) >> ((g & 3) * 4);
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
-                                pk[j] = pack_bf16(((b8 >> (2 * j)) & 1u) ? __uint_as_float(v[g * 8 + 2 * j]) : 0.0f,
-                                                  ((b8 >> (2 * j + 1)) & 1u) ? __uint_as_float(v[g * 8 + 2 * j + 1]) : 0.0f);
+                                pk[j] = pack_bf16(__uint_as_float(v[g * 8 + 2 * j]), __uint_as_float(v[g * 8 + 2 * j + 1])) &
+                                        (((b8 >> j) & 0x00010001u) * 0xFFFFu);
                         }
                         *slot = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
@@ -301,7 +330,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         *reinterpret_cast<uint2 *>(p.bits_out + row * p.ldbits + (c0 >> 5)) = make_uint2(lo, hi);
                     fence_async_smem();
                     __syncwarp();
-                    if (lane == 0) tma_store_2d(&mapC, smem_u32(buf), c0, (int)(tile * BM + q * 32));
+                    if (lane == 0) {
+                        if (p.l2_hints & 2) tma_store_2d_hint(&mapC, smem_u32(buf), c0, (int)(tile * BM + q * 32), L2_EVICT_LAST);
+                        else tma_store_2d(&mapC, smem_u32(buf), c0, (int)(tile * BM + q * 32));
+                    }
                 }
             }
             tc_fence_before();
@@ -371,7 +403,9 @@ size_t gemm_smem(int N, int K, int a_stages)
 // ---------------------------------------------------------------------------------------------
 constexpr int DW_STAGES = 3;
 struct DwParams {
-    long long rows, rows_per_cta;
+    long long rows;
+    int reverse;            // 64-sample blocks are dealt round-robin to the CTAs, from the first or from the last
+    int l2_hints;           // bit 2: H loads evict-first
     int in_pad, out_pad;    // multiples of 64, <= 256
     float *partial;         // [grid][in_pad][out_pad]
     float *colsum;          // [grid][out_pad] column sums of dZ over the CTA's slab (bias gradient), or NULL
@@ -388,10 +422,8 @@ dw_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ C
     uint64_t *bars = reinterpret_cast<uint64_t *>(sB + DW_STAGES * b_bytes);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + DW_STAGES), done0 = smem_u32(bars + 2 * DW_STAGES);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * DW_STAGES + 1);
-    const long long r_begin = (long long)blockIdx.x * p.rows_per_cta;
-    long long r_end = r_begin + p.rows_per_cta;
-    if (r_end > p.rows) r_end = p.rows;
-    const int kb_count = r_end > r_begin ? (int)((r_end - r_begin + 63) / 64) : 0;
+    const int n_blocks = (int)((p.rows + 63) / 64);
+    const int kb_count = (int)blockIdx.x < n_blocks ? (n_blocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int halves = (p.in_pad + 127) / 128;
     const uint32_t tcols = (uint32_t)(halves * p.out_pad) <= 32 ? 32 : ((halves * p.out_pad) <= 64 ? 64 : ((halves * p.out_pad) <= 128 ? 128 : ((halves * p.out_pad) <= 256 ? 256 : 512)));
     if (threadIdx.x == 0) {
@@ -406,12 +438,16 @@ dw_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ C
     const uint32_t tmem = *tmem_slot;
     if (warp == 0 && lane == 0) {
         uint32_t stage = 0, phase = 0;
+        pdl_wait();
+        pdl_trigger();
         for (int kb = 0; kb < kb_count; ++kb) {
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
             mbar_expect_tx(full0 + 8 * stage, (uint32_t)(a_bytes + b_bytes));
-            const int r0 = (int)(r_begin + (long long)kb * 64);   // slabs are multiples of 64 rows: a block never straddles
-            for (int b = 0; b < a_boxes; ++b)                      // two CTAs; rows past the end of the tensor are zero-filled by TMA
-                tma_load_2d(smem_u32(sA + stage * a_bytes + b * 8192), &mapH, b * 64, r0, full0 + 8 * stage);
+            const int blk = (int)blockIdx.x + kb * (int)gridDim.x;
+            const int r0 = (p.reverse ? n_blocks - 1 - blk : blk) * 64;
+            for (int b = 0; b < a_boxes; ++b)                      // rows past the end of the tensor are zero-filled by TMA
+                if (p.l2_hints & 4) tma_load_2d_hint(smem_u32(sA + stage * a_bytes + b * 8192), &mapH, b * 64, r0, full0 + 8 * stage, L2_EVICT_FIRST);
+                else tma_load_2d(smem_u32(sA + stage * a_bytes + b * 8192), &mapH, b * 64, r0, full0 + 8 * stage);
             for (int b = 0; b < b_boxes; ++b)
                 tma_load_2d(smem_u32(sB + stage * b_bytes + b * 8192), &mapZ, b * 64, r0, full0 + 8 * stage);
             if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
@@ -464,6 +500,7 @@ dw_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ C
         }
         mbar_wait(done0, 0);
         tc_fence_after();
+        pdl_wait();
         const int q = warp & 3;
         float *out = p.partial + (size_t)blockIdx.x * p.in_pad * p.out_pad;
         for (int h = 0; h < halves; ++h) {
@@ -527,6 +564,53 @@ __global__ void __launch_bounds__(256) wide_dw_reduce_kernel(const float *__rest
     }
 }
 
+// The same reduction for every layer of a step in ONE launch (the step's partials are all kept):
+// job j covers blocks [first_block[j], first_block[j+1]); a weight job and a bias job per layer.
+struct ReduceJob {
+    const float *partial; float *dst;
+    int in_pad, out_pad, in_dim, out_dim, ldw, first_block;
+};
+struct ReduceJobs { ReduceJob job[2 * LNB_MAX_LAYERS]; int n_jobs, n_part; float seed_value; const float *seed_dev; };
+
+__global__ void __launch_bounds__(256) wide_reduce_all_kernel(const __grid_constant__ ReduceJobs jobs)
+{
+    __shared__ float4 acc[8][32];
+    int j = 0;
+    while (j + 1 < jobs.n_jobs && (int)blockIdx.x >= jobs.job[j + 1].first_block) ++j;
+    const ReduceJob &J = jobs.job[j];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int e = (((int)blockIdx.x - J.first_block) * 32 + lane) * 4;
+    const int n_el = J.in_pad * J.out_pad;
+    const size_t stride = (size_t)n_el;
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+    if (e < n_el) {
+        int z = grp;
+        for (; z + 8 < jobs.n_part; z += 16) {
+            const float4 a = *reinterpret_cast<const float4 *>(J.partial + (size_t)z * stride + e);
+            const float4 b = *reinterpret_cast<const float4 *>(J.partial + (size_t)(z + 8) * stride + e);
+            s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+            s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
+        }
+        if (z < jobs.n_part) {
+            const float4 a = *reinterpret_cast<const float4 *>(J.partial + (size_t)z * stride + e);
+            s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+        }
+    }
+    acc[grp][lane] = make_float4(s0.x + s1.x, s0.y + s1.y, s0.z + s1.z, s0.w + s1.w);
+    __syncthreads();
+    if (grp == 0 && e < n_el) {
+        float4 s = acc[0][lane];
+        for (int g = 1; g < 8; ++g) { s.x += acc[g][lane].x; s.y += acc[g][lane].y; s.z += acc[g][lane].z; s.w += acc[g][lane].w; }
+        const float scale = jobs.seed_value * (jobs.seed_dev ? __ldg(jobs.seed_dev) : 1.0f);
+        const int k = e / J.out_pad, c = e % J.out_pad;
+        if (k < J.in_dim) {
+            const float v[4] = {s.x, s.y, s.z, s.w};
+            for (int i = 0; i < 4; ++i)
+                if (c + i < J.out_dim) J.dst[(size_t)k * J.ldw + c + i] += scale * v[i];
+        }
+    }
+}
+
 // dst[i][j] = bf16(j < cols ? src[i][j] : 0) for j < ldd (ldd multiple of 8): a thread makes one 16-byte store
 __global__ void f32_to_bf16_rows_kernel(const float *__restrict__ src, int lds, int cols, long long rows, __nv_bfloat16 *__restrict__ dst, int ldd)
 {
@@ -553,6 +637,16 @@ __global__ void wide_prep_kernel(const float *__restrict__ w, int ldw, int in_di
     Wf[(size_t)j * in_pad + k] = __float2bfloat16_rn(v);
 }
 
+// launch configuration with programmatic stream serialization (LNB_WIDE_NO_PDL=1 turns it off)
+void pdl_config(cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attr, int grid, int block, size_t smem, cudaStream_t stream)
+{
+    static const bool use_pdl = getenv("LNB_WIDE_NO_PDL") == nullptr;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg->gridDim = dim3((unsigned)grid); cfg->blockDim = dim3((unsigned)block); cfg->dynamicSmemBytes = smem; cfg->stream = stream;
+    cfg->attrs = attr; cfg->numAttrs = use_pdl ? 1 : 0;
+}
+
 size_t dw_smem(int in_pad, int out_pad)
 {
     return (size_t)DW_STAGES * ((in_pad / 64) + (out_pad / 64)) * 8192 + (2 * DW_STAGES + 4) * 8 + 16;
@@ -563,7 +657,7 @@ size_t dw_smem(int in_pad, int out_pad)
 // C = epilogue(A[M x K] * B[N x K]^T): A, B bf16 device pointers, row pitches lda / ldb elements
 // (multiples of 8), K multiple of 64 (<= 256), N multiple of 16 and <= 256.
 int lnb_wide_gemm(lnb_ctx *ctx, const void *A, int lda, const void *B, int ldb, long long M, int N, int K, const float *bias,
-                  const uint32_t *bits_in, uint32_t *bits_out, int ldbits, void *C, int ldc, int epi, int head)
+                  const uint32_t *bits_in, uint32_t *bits_out, int ldbits, void *C, int ldc, int epi, int head, int reverse)
 {
     LNB_ARG(M >= 0 && N >= 16 && N <= 256 && N % 16 == 0 && K >= 64 && K <= 256 && K % 64 == 0, "wide gemm: shape");
     LNB_ARG(lda % 8 == 0 && ldb % 8 == 0, "wide gemm: row pitches must be multiples of 8 elements");
@@ -581,7 +675,9 @@ int lnb_wide_gemm(lnb_ctx *ctx, const void *A, int lda, const void *B, int ldb, 
     }
     GemmParams p{};
     p.M = (int)M; p.N = N; p.K = K; p.bias = bias; p.bits_in = bits_in; p.bits_out = bits_out; p.ldbits = ldbits; p.C = C; p.ldc = ldc;
-    p.epi = epi; p.head = head;
+    p.epi = epi; p.head = head; p.reverse = reverse;
+    static const int l2_hints = [] { const char *e = getenv("LNB_WIDE_L2_HINTS"); return e ? atoi(e) : 2; }();
+    p.l2_hints = l2_hints;
     p.a_stages = gemm_a_stages(N, K);
     LNB_ARG(p.a_stages >= 2, "wide gemm: shared memory");
     const size_t smem = gemm_smem(N, K, p.a_stages);
@@ -592,8 +688,11 @@ int lnb_wide_gemm(lnb_ctx *ctx, const void *A, int lda, const void *B, int ldb, 
     }
     const int n_tiles = (int)((M + BM - 1) / BM);
     const int grid = n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count;
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    pdl_config(&cfg, attr, grid, GEMM_THREADS, smem, ctx->stream);
     lnb_prof_begin(ctx, "gemm_tc_kernel");
-    gemm_tc_kernel<<<grid, GEMM_THREADS, smem, ctx->stream>>>(mapA, mapB, mapC, p);
+    LNB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel, mapA, mapB, mapC, p));
     lnb_prof_end(ctx);
     LNB_CHECK_LAUNCH();
     return LNB_OK;
@@ -604,7 +703,7 @@ extern "C" LNB_API int lnb_test_wide_gemm(lnb_ctx *ctx, const void *A, const voi
                                           float *C)
 {
     if (!ctx) return LNB_ERR_ARG;
-    return lnb_wide_gemm(ctx, A, K, B, K, M, N, K, bias, nullptr, nullptr, 0, C, N, EPI_NONE_F32, 0);
+    return lnb_wide_gemm(ctx, A, K, B, K, M, N, K, bias, nullptr, nullptr, 0, C, N, EPI_NONE_F32, 0, (int)(M & 1));
 }
 
 // test hook: bf16 C = relu(A B^T + bias) (+ its ReLU bit pattern into bits_out), or, when bits_in != NULL,
@@ -614,13 +713,13 @@ extern "C" LNB_API int lnb_test_wide_gemm_bf16(lnb_ctx *ctx, const void *A, cons
 {
     if (!ctx) return LNB_ERR_ARG;
     return lnb_wide_gemm(ctx, A, K, B, K, M, N, K, bias, (const uint32_t *)bits_in, (uint32_t *)bits_out, ((N + 63) / 64) * 2, C, N,
-                         bits_in ? EPI_MASK_BF16 : EPI_RELU_BF16, 0);
+                         bits_in ? EPI_MASK_BF16 : EPI_RELU_BF16, 0, (int)(M & 1));
 }
 
 // dW partials of one layer ([n_part][in_pad][out_pad] fp32) and, if colsum != NULL, the column sums of
 // dZ per CTA ([n_part][out_pad])
 int lnb_wide_dw(lnb_ctx *ctx, const void *H, int ldh, int in_pad, const void *dZ, int ldz, int out_pad, long long rows,
-                float *partial, float *colsum, int n_part)
+                float *partial, float *colsum, int n_part, int reverse)
 {
     LNB_ARG(in_pad % 64 == 0 && in_pad >= 64 && in_pad <= 256 && out_pad % 64 == 0 && out_pad >= 64 && out_pad <= 256, "wide dW: padded widths");
     if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
@@ -629,7 +728,9 @@ int lnb_wide_dw(lnb_ctx *ctx, const void *H, int ldh, int in_pad, const void *dZ
     LNB_TRY(make_map(ctx, &mapZ, dZ, rows, out_pad, ldz, 64));
     DwParams p{};
     p.rows = rows;
-    p.rows_per_cta = ((rows + n_part - 1) / n_part + 63) / 64 * 64;
+    p.reverse = reverse;
+    static const int l2_hints = [] { const char *e = getenv("LNB_WIDE_L2_HINTS"); return e ? atoi(e) : 2; }();
+    p.l2_hints = l2_hints;
     p.in_pad = in_pad; p.out_pad = out_pad; p.partial = partial; p.colsum = colsum;
     const size_t smem = dw_smem(in_pad, out_pad);
     static size_t smem_set = 0;
@@ -637,7 +738,10 @@ int lnb_wide_dw(lnb_ctx *ctx, const void *H, int ldh, int in_pad, const void *dZ
         LNB_CUDA(cudaFuncSetAttribute(dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    dw_tc_kernel<<<n_part, DW_THREADS, smem, ctx->stream>>>(mapH, mapZ, p);
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    pdl_config(&cfg, attr, n_part, DW_THREADS, smem, ctx->stream);
+    LNB_CUDA(cudaLaunchKernelEx(&cfg, dw_tc_kernel, mapH, mapZ, p));
     LNB_CHECK_LAUNCH();
     return LNB_OK;
 }
@@ -651,7 +755,7 @@ extern "C" LNB_API int lnb_test_wide_dw(lnb_ctx *ctx, const void *H, int in_pad,
     LNB_TRY(lnb_arena_reserve(ctx, (size_t)n_part * (in_pad + 1) * out_pad * sizeof(float) + 8192));
     float *partial = (float *)lnb_arena_take(ctx, (size_t)n_part * in_pad * out_pad * sizeof(float));
     float *bpartial = (float *)lnb_arena_take(ctx, (size_t)n_part * out_pad * sizeof(float));
-    LNB_TRY(lnb_wide_dw(ctx, H, in_pad, in_pad, dZ, out_pad, out_pad, rows, partial, db ? bpartial : nullptr, n_part));
+    LNB_TRY(lnb_wide_dw(ctx, H, in_pad, in_pad, dZ, out_pad, out_pad, rows, partial, db ? bpartial : nullptr, n_part, (int)(rows & 1)));
     LNB_CUDA(cudaMemsetAsync(dW, 0, (size_t)in_pad * out_pad * sizeof(float), ctx->stream));
     wide_dw_reduce_kernel<<<(in_pad * out_pad + 127) / 128, 256, 0, ctx->stream>>>(partial, n_part, in_pad, out_pad, in_pad, out_pad, dW, out_pad, 1.0f, nullptr);
     LNB_CHECK_LAUNCH();
@@ -725,8 +829,8 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
     add((size_t)N * 16);                                         // head fp32 [N][4]
     if (rays) { add((size_t)N * c_in * 4); add((size_t)R * S * 4); }
     for (int l = 0; l < L; ++l) { add((size_t)in_pad[l] * out_pad[l] * 2); add((size_t)in_pad[l] * out_pad[l] * 2); add((size_t)out_pad[l] * 4); }
-    add((size_t)n_part * 256 * 256 * 4);
-    add((size_t)n_part * 256 * 4);
+    if (grad)
+        for (int l = 0; l < L; ++l) { add((size_t)n_part * in_pad[l] * out_pad[l] * 4); add((size_t)n_part * out_pad[l] * 4); }
     add((size_t)R * 4 + 16); add((size_t)R * 12 + 16); add(64);
     LNB_TRY(lnb_arena_reserve(ctx, need));
     auto take = [&](size_t bytes) { return lnb_arena_take(ctx, bytes); };
@@ -754,8 +858,11 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
         Wb[l] = (__nv_bfloat16 *)take((size_t)in_pad[l] * out_pad[l] * 2);
         biasP[l] = (float *)take((size_t)out_pad[l] * 4);
     }
-    float *partial = (float *)take((size_t)n_part * 256 * 256 * 4);
-    float *bpartial = (float *)take((size_t)n_part * 256 * 4);
+    float *partial[LNB_MAX_LAYERS], *bpartial[LNB_MAX_LAYERS];
+    for (int l = 0; l < L; ++l) {
+        partial[l] = grad ? (float *)take((size_t)n_part * in_pad[l] * out_pad[l] * 4) : nullptr;
+        bpartial[l] = grad ? (float *)take((size_t)n_part * out_pad[l] * 4) : nullptr;
+    }
     float *ray_sse = (float *)take((size_t)R * 4 + 16);
     float *color = a->color ? a->color : (float *)take((size_t)R * 12 + 16);
     float *loss = a->loss ? a->loss : (float *)take(64);
@@ -774,10 +881,19 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
         LNB_CUDA(cudaMemcpyAsync(biasP[l], a->bs + (size_t)l * mlp->max_out, (size_t)mlp->dims[l + 1] * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     }
 
-    // ---- forward and adjoint chain, slab by slab (unit seed; the seed scales d_ws / d_bs at the end)
+    // ---- forward and adjoint chain, slab by slab (unit seed; the seed scales d_ws / d_bs at the end).
+    // Serpentine order: every GEMM / dW launch walks the samples in the direction opposite to the
+    // launch before it, so it starts on the part of its input that the previous kernel touched last
+    // and that is still in the 126 MB L2 (LNB_WIDE_NO_SERPENTINE=1 turns it off).
+    static const bool serpentine = getenv("LNB_WIDE_NO_SERPENTINE") == nullptr;
+    ReduceJobs jobs{};
+    int blocks = 0;
     for (int r0 = 0; r0 < R; r0 += slab_rays) {
         const int Rs = R - r0 < slab_rays ? R - r0 : slab_rays;
         const long long n0 = (long long)r0 * S, Ns = (long long)Rs * S;
+        const bool whole = Rs == R;
+        int dir = 0;                                             // the conversion kernels write front to back
+        auto next_dir = [&] { dir = serpentine ? !dir : 0; return dir; };
         {
             const long long n = Ns * (in_pad[0] / 8);
             f32_to_bf16_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(X + n0 * c_in, c_in, c_in, Ns, H[0] + n0 * in_pad[0], in_pad[0]);
@@ -786,9 +902,9 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
         for (int l = 0; l < L - 1; ++l)
             LNB_TRY(lnb_wide_gemm(ctx, H[l] + n0 * in_pad[l], in_pad[l], Wf[l], in_pad[l], Ns, out_pad[l], in_pad[l], biasP[l], nullptr,
                                   grad ? bits[l + 1] + n0 * (in_pad[l + 1] / 32) : nullptr, in_pad[l + 1] / 32, H[l + 1] + n0 * out_pad[l], out_pad[l],
-                                  EPI_RELU_BF16, 0));
+                                  EPI_RELU_BF16, 0, next_dir()));
         LNB_TRY(lnb_wide_gemm(ctx, H[L - 1] + n0 * in_pad[L - 1], in_pad[L - 1], Wf[L - 1], in_pad[L - 1], Ns, 16, in_pad[L - 1], biasP[L - 1],
-                              nullptr, nullptr, 0, head + n0 * 4, 4, EPI_HEAD_F32, mlp->head));
+                              nullptr, nullptr, 0, head + n0 * 4, 4, EPI_HEAD_F32, mlp->head, next_dir()));
         LNB_TRY(lnb_launch_composite_fwd(ctx, head + n0 * 4, 4, dists + n0, a->target ? a->target + (size_t)r0 * 3 : nullptr, Rs, S, nullptr, nullptr,
                                          nullptr, nullptr, color + (size_t)r0 * 3, 0, ray_sse + r0));
         if (!grad) continue;
@@ -799,27 +915,37 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
             f32_to_bf16_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dzh + n0 * 4, 4, 4, Ns, dZ[L - 1] + n0 * out_pad[L - 1], out_pad[L - 1]);
             LNB_CHECK_LAUNCH();
         }
-        for (int l = L - 1; l >= 1; --l)   // dZ_{l-1} = (dZ_l W_l^T) where H_l > 0
-            LNB_TRY(lnb_wide_gemm(ctx, dZ[l] + n0 * out_pad[l], out_pad[l], Wb[l], out_pad[l], Ns, in_pad[l], out_pad[l], nullptr,
-                                  bits[l] + n0 * (in_pad[l] / 32), nullptr, in_pad[l] / 32, dZ[l - 1] + n0 * in_pad[l], in_pad[l], EPI_MASK_BF16, 0));
+        dir = 0;
+        for (int l = L - 1; l >= 0; --l) {
+            // whole batch in one slab: the weight gradient of layer l runs right here, between the kernel that
+            // wrote dZ_l and the one that reads it again
+            if (whole) LNB_TRY(lnb_wide_dw(ctx, H[l], in_pad[l], in_pad[l], dZ[l], out_pad[l], out_pad[l], N, partial[l], bpartial[l], n_part, next_dir()));
+            if (l >= 1)   // dZ_{l-1} = (dZ_l W_l^T) where H_l > 0
+                LNB_TRY(lnb_wide_gemm(ctx, dZ[l] + n0 * out_pad[l], out_pad[l], Wb[l], out_pad[l], Ns, in_pad[l], out_pad[l], nullptr,
+                                      bits[l] + n0 * (in_pad[l] / 32), nullptr, in_pad[l] / 32, dZ[l - 1] + n0 * in_pad[l], in_pad[l], EPI_MASK_BF16, 0,
+                                      next_dir()));
+        }
     }
     if (a->target) LNB_TRY(lnb_launch_sum(ctx, ray_sse, R, loss));
     else if (a->loss) LNB_TRY(lnb_launch_fill(ctx, loss, 1, 0.0f));
     if (!grad) return LNB_OK;
 
-    // ---- weight and bias gradients over the whole batch
-    const float *seed_dev = a->seed_mode == LNB_SEED_LOSS ? loss : nullptr;
-    const float seed_val = a->seed_mode == LNB_SEED_LOSS ? 1.0f : a->seed;
+    // ---- weight and bias gradients: per layer one dW kernel (+ column sums) over the whole batch (above, or
+    // here when the chain ran in slabs), then one launch that reduces every layer's partials into d_ws / d_bs
     for (int l = L - 1; l >= 0; --l) {
-        const int in_l = mlp->dims[l], out_l = mlp->dims[l + 1];
-        LNB_TRY(lnb_wide_dw(ctx, H[l], in_pad[l], in_pad[l], dZ[l], out_pad[l], out_pad[l], N, partial, bpartial, n_part));
-        wide_dw_reduce_kernel<<<(in_pad[l] * out_pad[l] + 127) / 128, 256, 0, ctx->stream>>>(partial, n_part, in_pad[l], out_pad[l], in_l, out_l,
-                                                                                            a->d_ws + (size_t)l * mlp->max_in * mlp->max_out,
-                                                                                            mlp->max_out, seed_val, seed_dev);
-        LNB_CHECK_LAUNCH();
-        wide_dw_reduce_kernel<<<(out_pad[l] + 127) / 128, 256, 0, ctx->stream>>>(bpartial, n_part, 1, out_pad[l], 1, out_l,
-                                                                                a->d_bs + (size_t)l * mlp->max_out, mlp->max_out, seed_val, seed_dev);
-        LNB_CHECK_LAUNCH();
+        if (slab_rays < R) LNB_TRY(lnb_wide_dw(ctx, H[l], in_pad[l], in_pad[l], dZ[l], out_pad[l], out_pad[l], N, partial[l], bpartial[l], n_part, 0));
+        ReduceJob &w = jobs.job[jobs.n_jobs++];
+        w = ReduceJob{partial[l], a->d_ws + (size_t)l * mlp->max_in * mlp->max_out, in_pad[l], out_pad[l], mlp->dims[l], mlp->dims[l + 1],
+                      mlp->max_out, blocks};
+        blocks += (in_pad[l] * out_pad[l] + 127) / 128;
+        ReduceJob &bj = jobs.job[jobs.n_jobs++];
+        bj = ReduceJob{bpartial[l], a->d_bs + (size_t)l * mlp->max_out, 1, out_pad[l], 1, mlp->dims[l + 1], mlp->max_out, blocks};
+        blocks += (out_pad[l] + 127) / 128;
     }
+    jobs.n_part = n_part;
+    jobs.seed_value = a->seed_mode == LNB_SEED_LOSS ? 1.0f : a->seed;
+    jobs.seed_dev = a->seed_mode == LNB_SEED_LOSS ? loss : nullptr;
+    wide_reduce_all_kernel<<<blocks, 256, 0, ctx->stream>>>(jobs);
+    LNB_CHECK_LAUNCH();
     return LNB_OK;
 }

@@ -44,9 +44,14 @@ def test_wide_gemm_matches_fp32_product_of_bf16_operands(ctx, torch_cuda, M, N, 
 
 
 def _pack_bits(torch, positive):
-    """[M][N] bool -> [M][N/32] uint32, bit j of word w <-> column 32 w + j (the kernel's ReLU pattern layout)"""
-    packed = np.packbits(positive.cpu().numpy().astype(np.uint8), axis=1, bitorder="little")
-    return torch.as_tensor(np.ascontiguousarray(packed).view(np.int32)).cuda()
+    """[M][N] bool -> [M][N/32] int32 in the kernel's ReLU-pattern layout (wide_tc.cu GemmParams): word w
+    covers columns 32w..32w+31, column 32w + 8g + 2j + p at bit 16p + 4g + j."""
+    pos = positive.cpu().numpy().astype(np.uint64)
+    M, N = pos.shape
+    c = np.arange(32)
+    shift = (16 * (c % 2) + 4 * (c // 8) + (c % 8) // 2).astype(np.uint64)
+    words = (pos.reshape(M, N // 32, 32) << shift).sum(axis=2).astype(np.uint32)
+    return torch.as_tensor(np.ascontiguousarray(words).view(np.int32)).cuda()
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (1000, 256, 256), (4096 + 77, 128, 64), (50000, 256, 256), (777, 192, 128)])
