@@ -152,3 +152,49 @@ def test_wide_path_against_f64_restatement(ctx, torch_cuda, R, S, E, width, laye
                 d_ws=rel_err(o["d_ws"], f["d_ws"]), d_bs=rel_err(o["d_bs"], f["d_bs"]))
     _log("wide R=%d S=%d E=%d w=%d L=%d rays=%s %s" % (R, S, E, width, layers, rays, errs))
     assert max(errs.values()) <= WIDE_TOL, errs
+
+
+def test_trainer_on_a_wide_mlp_follows_numpy_adam(ctx, torch_cuda):
+    """lnb_trainer with a network the fused kernel cannot take (5 layers of 128): the generic step runs
+    the layerwise tensor-core kernels, then Adam (train_nerf.py:133-161); compared with the float64
+    gradients + numpy Adam over 3 steps, features in and rays in."""
+    torch = torch_cuda
+    from loma_nerf_b200 import api
+    R, S, E = 96, 40, 6
+    cases = [O.make_nerf_case(2100 + i, R, S, E=E, width=128, n_layers=5) for i in range(3)]
+    ws0, bs0 = cases[0]["ws"].copy(), cases[0]["bs"].copy()
+    dims = [int(v) for v in cases[0]["dims"]]
+    lr, b1, b2, eps = 5e-4, 0.9, 0.999, 1e-8
+    ws, bs = ws0.astype(np.float64), bs0.astype(np.float64)
+    m = [np.zeros_like(ws), np.zeros_like(bs)]; v = [np.zeros_like(ws), np.zeros_like(bs)]
+    losses = []
+    for t, c in enumerate(cases, start=1):
+        f = O.nerf_f64(c["X"], ws.astype(np.float32), bs.astype(np.float32), c["dims"], c["target"], c["dists"], R, S, g=1.0)
+        losses.append(f["loss"])
+        lr_t = lr * (np.sqrt(1 - b2 ** t) / (1 - b1 ** t))
+        for i, (p_, g_) in enumerate(((ws, f["d_ws"]), (bs, f["d_bs"]))):
+            m[i] = b1 * m[i] + (1 - b1) * g_
+            v[i] = b2 * v[i] + (1 - b2) * g_ ** 2
+            p_ -= lr_t * (m[i] / (1 - b1 ** t)) / (np.sqrt(v[i] / (1 - b2 ** t)) + eps)
+    cv = lambda a: torch.as_tensor(np.ascontiguousarray(a, np.float32)).cuda()  # noqa: E731
+    for mode in ("features", "rays"):
+        tr = api.Trainer(ctx, dims, ws0, bs0, optimizer="adam", lr=lr, beta1=b1, beta2=b2, eps=eps)
+        got = []
+        for i, c in enumerate(cases):
+            if mode == "features":
+                batch = dict(X=cv(c["X"]), dists=cv(c["dists"]), target=cv(c["target"]), path="tc")
+            else:
+                rays = tuple(torch.as_tensor(np.ascontiguousarray(c[k])).cuda() for k in ("rays_o", "rays_d", "t"))
+                batch = dict(rays=rays, pe_bands=E, target=cv(c["target"]), path="tc")
+            if i == 1:
+                tr.grad(**batch); tr.apply()
+            else:
+                tr.step(**batch)
+            got.append(tr.read()[2])
+        w, b, _ = tr.read()
+        tr.close()
+        du, dr = (w - ws0).ravel().astype(np.float64), (ws - ws0).ravel()
+        upd_l2 = float(np.linalg.norm(du - dr) / np.linalg.norm(dr))
+        _log("wide trainer %s: loss err %.3g, update l2 err %.3g" % (mode, rel_err(got, losses), upd_l2))
+        assert rel_err(got, losses) <= WIDE_TOL
+        assert upd_l2 <= 0.2   # Adam turns every entry into ~lr*sign(g): entries below the bf16 noise flip freely
