@@ -98,10 +98,33 @@ def run_reference(args):
     from oracle import cpu_bench
     import multiprocessing as mp
     w = WORKLOADS[args.workload]
-    if args.workload != "c2":
-        print(json.dumps({"impl": "reference", "unavailable": "reference arm is timed on the C2 workload only"}))
-        return 0
     cores = cpu_bench.host_cores()
+    if args.workload == "c5":
+        # paper-size network: the reference program rebuilt with larger static tapes (oracle/_ref/nerf_big.so),
+        # one ray of 192 samples per call, 1.9 GB of stack per process -> at most 8 processes
+        procs = min(cores, 8)
+        if cpu_bench.run_big(1, 0) is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/nerf_big.so was not built"}))
+            return 0
+        tot_s, tot_n, steps = 0.0, 0, min(args.steps, 3)
+        for _ in range(min(args.warmup, 1)):
+            cpu_bench.run_big(procs, 1, S=w["S"])
+        for _ in range(steps):
+            r = cpu_bench.run_big(procs, 1, S=w["S"])
+            tot_s += r["seconds"]
+            tot_n += r["samples"]
+        value = tot_n / tot_s
+        sample = ("each step: %d processes x 1 call pair (forward + grad) x 1 ray x %d samples of the C5 network through "
+                  "oracle/_ref/nerf_big.so; %d steps timed (each ~4 s), wall time of the slowest process" % (procs, w["S"], steps))
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * tot_s / steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": workload_config(args.workload, args.gpus),
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "reference", "sample": sample},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
     chunks = 24   # per core per step: 24 chunks x 256 samples, ~0.25 s of C time
     with mp.get_context("fork").Pool(cores) as pool:
         for _ in range(args.warmup):
@@ -487,7 +510,16 @@ def run_ours(args):
             line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                 "traffic": None, "kernel": "whole step (layerwise fp32 kernels)",
                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "c5":
+            from oracle import cpu_bench
+            procs = min(cpu_bench.host_cores(), 8)
+            r = cpu_bench.run_big(procs, 2, S=S)
+            if r is not None:
+                line["cpu_baseline"] = {"value": r["samples"] / r["seconds"], "unit": UNIT, "cores": procs, "kind": "reference",
+                                        "sample": "%d processes x 2 call pairs x 1 ray x %d samples of this network through the "
+                                                  "reference program rebuilt with larger tapes (oracle/_ref/nerf_big.so, 1.9 GB of "
+                                                  "stack each), forward + grad call, wall time of the slowest process" % (procs, S)}
+        elif world == 1 and not args.no_cpu_baseline:
             from oracle import cpu_bench
             cores = cpu_bench.host_cores()
             r = cpu_bench.run(cores, 40, S=S)

@@ -681,11 +681,7 @@ int lnb_wide_gemm(lnb_ctx *ctx, const void *A, int lda, const void *B, int ldb, 
     p.a_stages = gemm_a_stages(N, K);
     LNB_ARG(p.a_stages >= 2, "wide gemm: shared memory");
     const size_t smem = gemm_smem(N, K, p.a_stages);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        LNB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
+    LNB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: set every time
     const int n_tiles = (int)((M + BM - 1) / BM);
     const int grid = n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count;
     cudaLaunchConfig_t cfg{};
@@ -733,11 +729,7 @@ int lnb_wide_dw(lnb_ctx *ctx, const void *H, int ldh, int in_pad, const void *dZ
     p.l2_hints = l2_hints;
     p.in_pad = in_pad; p.out_pad = out_pad; p.partial = partial; p.colsum = colsum;
     const size_t smem = dw_smem(in_pad, out_pad);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        LNB_CUDA(cudaFuncSetAttribute(dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
+    LNB_CUDA(cudaFuncSetAttribute(dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[1];
     pdl_config(&cfg, attr, n_part, DW_THREADS, smem, ctx->stream);

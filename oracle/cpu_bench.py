@@ -90,6 +90,33 @@ def run(n_procs, chunks_per_proc, S=64, train=True, pool=None):
     return dict(samples=n_procs * chunks_per_proc * rays * S, seconds=max(times), kind=kind, cores=n_procs)
 
 
+def _worker_big(args):
+    """One call pair (forward + grad) of the paper-size reference build oracle/_ref/nerf_big.so on one ray of
+    192 samples through the 63 -> 8 x 256 -> 4 network (its static tapes hold 1.9 GB on the stack)."""
+    seed, n_calls, S = args
+    case = O.make_nerf_case(seed, 1, S, E=10, width=256, n_layers=9)
+    ref = O.load_ref("nerf_big")
+    t0 = time.perf_counter()
+    for _ in range(n_calls):
+        ref.nerf(case["X"], case["ws"], case["bs"], [int(v) for v in case["dims"]], case["target"], case["dists"], 1, S, g="loss")
+    return time.perf_counter() - t0
+
+
+def run_big(n_procs, calls_per_proc=1, S=192):
+    """Paper-size (BASELINE config 5) CPU baseline; needs oracle/_ref/nerf_big.so.  The time includes the
+    zero-copy marshalling of the call (microseconds against seconds in the C code).  Returns None when the
+    reference build is absent."""
+    if not O.have_ref("nerf_big"):
+        return None
+    jobs = [(3000 + p, calls_per_proc, S) for p in range(n_procs)]
+    if n_procs == 1:
+        times = [_worker_big(jobs[0])]
+    else:
+        with mp.get_context("fork").Pool(n_procs) as pl:
+            times = pl.map(_worker_big, jobs)
+    return dict(samples=n_procs * calls_per_proc * S, seconds=max(times), kind="reference", cores=n_procs)
+
+
 def host_cores():
     try:
         return max(1, len(os.sched_getaffinity(0)))
