@@ -763,11 +763,12 @@ extern "C" LNB_API int lnb_test_wide_dw(lnb_ctx *ctx, const void *H, int in_pad,
 // The wide-MLP step: layerwise on the tensor cores (see the header of this file).  Produces what
 // the fused kernel produces: loss, colour, d_ws, d_bs.  Returns LNB_ERR_UNSUPPORTED otherwise.
 //
-// The forward and the adjoint chain run over SLABS of whole rays small enough that a layer's
-// activations (slab x 256 bf16) are still in the 126 MB L2 when the next layer reads them, so HBM
-// sees each activation / adjoint tensor written once (they are kept: the weight gradient needs
-// H_l and dZ_l of every layer) instead of written and read back.  The weight gradients then run
-// once per layer over the whole batch, which keeps their per-CTA TMEM accumulation long.
+// The whole batch normally goes through each kernel in one launch.  LNB_WIDE_SLAB_WAVES=k splits it
+// into slabs of whole rays (k waves of tiles over the SMs) that run forward, adjoint chain and weight
+// gradients one after another, each slab with its own set of per-CTA partials: an experiment in
+// keeping a layer's activations in L2 for the next layer.  Measured slower at every size (C5: 3.33 ms
+// whole, 3.50 / 3.70 / 3.88 ms for 2 / 3 / 4 slabs: every extra launch costs ~4.5 us of weight reload,
+// pipeline fill and tail), so the default is one slab.
 // ---------------------------------------------------------------------------------------------
 static int pad64(int v) { return (v + 63) / 64 * 64; }
 
@@ -806,6 +807,7 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
         const long long r = (long long)slab_waves * ctx->sm_count * BM / S;
         slab_rays = (int)(r < 1 ? 1 : (r > R ? R : r));
     }
+    const int n_slabs = R > 0 ? (R + slab_rays - 1) / slab_rays : 1;
 
     // ---- arena plan
     size_t need = 1 << 16;
@@ -822,7 +824,7 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
     if (rays) { add((size_t)N * c_in * 4); add((size_t)R * S * 4); }
     for (int l = 0; l < L; ++l) { add((size_t)in_pad[l] * out_pad[l] * 2); add((size_t)in_pad[l] * out_pad[l] * 2); add((size_t)out_pad[l] * 4); }
     if (grad)
-        for (int l = 0; l < L; ++l) { add((size_t)n_part * in_pad[l] * out_pad[l] * 4); add((size_t)n_part * out_pad[l] * 4); }
+        for (int l = 0; l < L; ++l) { add((size_t)n_slabs * n_part * in_pad[l] * out_pad[l] * 4); add((size_t)n_slabs * n_part * out_pad[l] * 4); }
     add((size_t)R * 4 + 16); add((size_t)R * 12 + 16); add(64);
     LNB_TRY(lnb_arena_reserve(ctx, need));
     auto take = [&](size_t bytes) { return lnb_arena_take(ctx, bytes); };
@@ -852,8 +854,8 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
     }
     float *partial[LNB_MAX_LAYERS], *bpartial[LNB_MAX_LAYERS];
     for (int l = 0; l < L; ++l) {
-        partial[l] = grad ? (float *)take((size_t)n_part * in_pad[l] * out_pad[l] * 4) : nullptr;
-        bpartial[l] = grad ? (float *)take((size_t)n_part * out_pad[l] * 4) : nullptr;
+        partial[l] = grad ? (float *)take((size_t)n_slabs * n_part * in_pad[l] * out_pad[l] * 4) : nullptr;
+        bpartial[l] = grad ? (float *)take((size_t)n_slabs * n_part * out_pad[l] * 4) : nullptr;
     }
     float *ray_sse = (float *)take((size_t)R * 4 + 16);
     float *color = a->color ? a->color : (float *)take((size_t)R * 12 + 16);
@@ -883,7 +885,7 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
     for (int r0 = 0; r0 < R; r0 += slab_rays) {
         const int Rs = R - r0 < slab_rays ? R - r0 : slab_rays;
         const long long n0 = (long long)r0 * S, Ns = (long long)Rs * S;
-        const bool whole = Rs == R;
+        const int slab = r0 / slab_rays;
         int dir = 0;                                             // the conversion kernels write front to back
         auto next_dir = [&] { dir = serpentine ? !dir : 0; return dir; };
         {
@@ -909,9 +911,11 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
         }
         dir = 0;
         for (int l = L - 1; l >= 0; --l) {
-            // whole batch in one slab: the weight gradient of layer l runs right here, between the kernel that
-            // wrote dZ_l and the one that reads it again
-            if (whole) LNB_TRY(lnb_wide_dw(ctx, H[l], in_pad[l], in_pad[l], dZ[l], out_pad[l], out_pad[l], N, partial[l], bpartial[l], n_part, next_dir()));
+            // the weight gradient of layer l (this slab's share: its own set of per-CTA partials) runs right here,
+            // between the kernel that wrote dZ_l and the one that reads it again
+            LNB_TRY(lnb_wide_dw(ctx, H[l] + n0 * in_pad[l], in_pad[l], in_pad[l], dZ[l] + n0 * out_pad[l], out_pad[l], out_pad[l], Ns,
+                                partial[l] + (size_t)slab * n_part * in_pad[l] * out_pad[l], bpartial[l] + (size_t)slab * n_part * out_pad[l], n_part,
+                                next_dir()));
             if (l >= 1)   // dZ_{l-1} = (dZ_l W_l^T) where H_l > 0
                 LNB_TRY(lnb_wide_gemm(ctx, dZ[l] + n0 * out_pad[l], out_pad[l], Wb[l], out_pad[l], Ns, in_pad[l], out_pad[l], nullptr,
                                       bits[l] + n0 * (in_pad[l] / 32), nullptr, in_pad[l] / 32, dZ[l - 1] + n0 * in_pad[l], in_pad[l], EPI_MASK_BF16, 0,
@@ -925,7 +929,6 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
     // ---- weight and bias gradients: per layer one dW kernel (+ column sums) over the whole batch (above, or
     // here when the chain ran in slabs), then one launch that reduces every layer's partials into d_ws / d_bs
     for (int l = L - 1; l >= 0; --l) {
-        if (slab_rays < R) LNB_TRY(lnb_wide_dw(ctx, H[l], in_pad[l], in_pad[l], dZ[l], out_pad[l], out_pad[l], N, partial[l], bpartial[l], n_part, 0));
         ReduceJob &w = jobs.job[jobs.n_jobs++];
         w = ReduceJob{partial[l], a->d_ws + (size_t)l * mlp->max_in * mlp->max_out, in_pad[l], out_pad[l], mlp->dims[l], mlp->dims[l + 1],
                       mlp->max_out, blocks};
@@ -934,7 +937,7 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
         bj = ReduceJob{bpartial[l], a->d_bs + (size_t)l * mlp->max_out, 1, out_pad[l], 1, mlp->dims[l + 1], mlp->max_out, blocks};
         blocks += (out_pad[l] + 127) / 128;
     }
-    jobs.n_part = n_part;
+    jobs.n_part = n_part * n_slabs;
     jobs.seed_value = a->seed_mode == LNB_SEED_LOSS ? 1.0f : a->seed;
     jobs.seed_dev = a->seed_mode == LNB_SEED_LOSS ? loss : nullptr;
     wide_reduce_all_kernel<<<blocks, 256, 0, ctx->stream>>>(jobs);
