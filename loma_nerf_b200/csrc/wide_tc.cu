@@ -35,10 +35,18 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm vo
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t done = 0;
+    unsigned long long t0 = 0;
     for (uint32_t it = 0; !done; ++it) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(bar), "r"(parity), "r"(100000u) : "memory");
-        if (it > (1u << 22)) __trap(); // a lost arrival must fail loudly, not hang the GPU
+        if (!done && (it & 0xFFFu) == 0xFFFu) {
+            // a lost arrival must fail loudly, not hang the GPU: 20 s by the global timer (a kernel started early by
+            // programmatic dependent launch legitimately spins here for as long as its predecessor runs)
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 20000000000ull) __trap();
+        }
     }
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
@@ -347,6 +355,270 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (warp == 1) tmem_dealloc(tmem, 2 * acc_cols);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Chain of layers in ONE persistent launch.  Tile t of layer l+1 needs only tile t of layer l (the
+// same 128 samples, all columns), and the tile -> CTA map is the same for every layer, so the
+// dependency is CTA-local: a CTA takes a block of G of its tiles through ALL layers of the chain
+// before it moves to its next block.  What layer l wrote for those G tiles (G x 64 KB per CTA,
+// G x 9.5 MB over the chip, stored evict-last) is still in L2 when layer l+1 reads it a few
+// microseconds later, so HBM sees every activation tensor written once and never read back; the
+// weights are reloaded from L2 once per layer per block (128 KB / G tiles), chunk by chunk as the
+// previous layer's last MMAs release them.  Same warp roles, rings and epilogues as gemm_tc_kernel.
+// ---------------------------------------------------------------------------------------------
+#ifdef LNB_WIDE_CLK
+// debug build (LNB_WIDE_CLK=1 python -m loma_nerf_b200.build): where the chain kernel's MMA and epilogue warps wait
+__device__ unsigned long long g_wide_clk[8];
+#define WCLK_T0() const long long _t0 = clock64()
+#define WCLK_ADD(i) atomicAdd(&g_wide_clk[i], (unsigned long long)(clock64() - _t0))
+#else
+#define WCLK_T0()
+#define WCLK_ADD(i)
+#endif
+constexpr int CHAIN_MAX_G = 8;
+constexpr int CHAIN_THREADS = 576;   // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue: the epilogue is the long pole of the chain
+struct ChainLayer {
+    const float *bias;         // [N] or NULL
+    const uint32_t *bits_in;   // EPI_MASK_BF16
+    uint32_t *bits_out;        // EPI_RELU_BF16 (optional)
+    float *head_out;           // EPI_HEAD_F32: [M][4]
+    int ldbits, N, K, epi;
+};
+struct ChainParams {
+    int M, n_layers, G, a_stages, head, l2_hints, b_region;
+    ChainLayer layer[LNB_MAX_LAYERS];
+};
+struct ChainMaps { CUtensorMap A[LNB_MAX_LAYERS], B[LNB_MAX_LAYERS], C[LNB_MAX_LAYERS]; };
+
+__device__ __forceinline__ void bulk_wait_group_n(int n)
+{
+    if (n >= 2) asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
+    else if (n == 1) asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(CHAIN_THREADS, 1)
+chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = (p.M + BM - 1) / BM;
+    const int n_my = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int AS = p.a_stages;
+    uint8_t *sB = smem, *sA = smem + p.b_region;
+    uint8_t *sC = sA + AS * A_STAGE_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sC + 16 * 2048);   // 16 epilogue warps x one 32-row x 64-byte staging box
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + 8), tfull0 = smem_u32(bars + 16), tempty0 = smem_u32(bars + 18),
+                   bfull0 = smem_u32(bars + 20), bempty0 = smem_u32(bars + 24), done0 = smem_u32(bars + 28);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 28 + CHAIN_MAX_G);
+    float *sBias = reinterpret_cast<float *>(bars + 28 + CHAIN_MAX_G + 2);
+    constexpr uint32_t acc_cols = 256;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < AS; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 512); }
+        for (int k = 0; k < 4; ++k) { mbar_init(bfull0 + 8 * k, 1); mbar_init(bempty0 + 8 * k, 1); }
+        for (int j = 0; j < CHAIN_MAX_G; ++j) mbar_init(done0 + 8 * j, 16);     // one arrival per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * acc_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ---- TMA producer
+        if (lane == 0) {
+            pdl_wait();
+            pdl_trigger();
+            uint32_t stage = 0, phase = 0, round = 0;
+            for (int blk = 0, bi = 0; blk < n_my; blk += p.G, ++bi) {
+                const int g_cnt = n_my - blk < p.G ? n_my - blk : p.G;
+                for (int li = 0; li < p.n_layers; ++li, ++round) {
+                    // weight chunk kb always sits at kb * 32 KB whatever the layer's N, so "chunk kb released" means the same
+                    // bytes for every layer
+                    const int kb_count = p.layer[li].K / BK, b_bytes = p.layer[li].N * BK * 2, b_stride = 256 * BK * 2;
+                    for (int kb = 0; kb < 4; ++kb) {
+                        if (kb < kb_count) {
+                            if (round > 0) mbar_wait(bempty0 + 8 * kb, (round - 1) & 1);   // last round's MMAs on this chunk retired
+                            mbar_expect_tx(bfull0 + 8 * kb, (uint32_t)b_bytes);
+                            tma_load_2d(smem_u32(sB + kb * b_stride), &maps.B[li], kb * BK, 0, bfull0 + 8 * kb);
+                        } else {
+                            mbar_arrive(bfull0 + 8 * kb);                                   // keep the phases of unused chunks in step
+                        }
+                    }
+                    for (int j = 0; j < g_cnt; ++j) {
+                        const int tile = (int)blockIdx.x + (blk + j) * (int)gridDim.x;
+                        if (li > 0) {   // this tile's output of the previous layer has fully left the SM (see the epilogue)
+                            mbar_wait(done0 + 8 * j, (uint32_t)(bi * (p.n_layers - 1) + li - 1) & 1u);
+                            asm volatile("fence.proxy.async.global;" ::: "memory");
+                        }
+                        for (int kb = 0; kb < kb_count; ++kb) {
+                            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                            mbar_expect_tx(full0 + 8 * stage, (uint32_t)A_STAGE_BYTES);
+                            if (p.l2_hints & 1) tma_load_2d_hint(smem_u32(sA + stage * A_STAGE_BYTES), &maps.A[li], kb * BK, tile * BM, full0 + 8 * stage, L2_EVICT_FIRST);
+                            else tma_load_2d(smem_u32(sA + stage * A_STAGE_BYTES), &maps.A[li], kb * BK, tile * BM, full0 + 8 * stage);
+                            if (++stage == (uint32_t)AS) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, round = 0;
+#ifdef LNB_WIDE_CLK
+            const long long t_begin = clock64();
+#endif
+            for (int blk = 0; blk < n_my; blk += p.G) {
+                const int g_cnt = n_my - blk < p.G ? n_my - blk : p.G;
+                for (int li = 0; li < p.n_layers; ++li, ++round) {
+                    const int kb_count = p.layer[li].K / BK, b_stride = 256 * BK * 2;
+                    const uint32_t idesc = instr_desc(128, p.layer[li].N, 0, 0);
+                    for (int j = 0; j < g_cnt; ++j) {
+                        { WCLK_T0(); mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1); WCLK_ADD(0); }
+                        tc_fence_after();
+                        for (int kb = 0; kb < kb_count; ++kb) {
+                            if (j == 0) { WCLK_T0(); mbar_wait(bfull0 + 8 * kb, round & 1); WCLK_ADD(1); }
+                            { WCLK_T0(); mbar_wait(full0 + 8 * stage, phase); WCLK_ADD(2); }
+                            tc_fence_after();
+                            const uint32_t a0 = smem_u32(sA + stage * A_STAGE_BYTES), b0 = smem_u32(sB + kb * b_stride);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k)
+                                umma_bf16(tmem + acc * acc_cols, sw128_desc(a0 + k * 32, 16, 1024), sw128_desc(b0 + k * 32, 16, 1024), idesc,
+                                          (kb > 0 || k > 0) ? 1u : 0u);
+                            umma_commit(empty0 + 8 * stage);
+                            if (j == g_cnt - 1) umma_commit(bempty0 + 8 * kb);     // this round is done with weight chunk kb
+                            if (++stage == (uint32_t)AS) { stage = 0; phase ^= 1; }
+                        }
+                        if (j == g_cnt - 1)
+                            for (int kb = kb_count; kb < 4; ++kb) umma_commit(bempty0 + 8 * kb);
+                        umma_commit(tfull0 + 8 * acc);
+                        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                    }
+                }
+            }
+#ifdef LNB_WIDE_CLK
+            atomicAdd(&g_wide_clk[3], (unsigned long long)(clock64() - t_begin));
+#endif
+        }
+    } else {
+        // ---- epilogue warps 2..17: four per TMEM lane quadrant (warp w may touch lanes 32*(w%4) .. +31), warp k of a
+        // quadrant owns the 64-column chunk k of every tile and handles it as two 32-column halves: registers -> its
+        // 32-row x 64-byte staging box (64-byte swizzle) -> TMA store
+        const int q = warp & 3, k = (warp - 2) >> 2, et = threadIdx.x - 64;
+        uint32_t acc = 0, acc_phase = 0;
+        uint8_t *buf = sC + (warp - 2) * 2048;
+        pdl_wait();
+        for (int blk = 0; blk < n_my; blk += p.G) {
+            const int g_cnt = n_my - blk < p.G ? n_my - blk : p.G;
+            for (int li = 0; li < p.n_layers; ++li) {
+                const ChainLayer &Ly = p.layer[li];
+                const int N = Ly.N, epi = Ly.epi, c0 = k * 64;
+                const bool signal = li < p.n_layers - 1;
+                const int n_groups = (epi != EPI_HEAD_F32 && c0 < N) ? 2 : 0;   // TMA stores this warp issues per tile
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                if (et < N) sBias[et] = Ly.bias ? __ldg(Ly.bias + et) : 0.0f;
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                for (int j = 0; j < g_cnt; ++j) {
+                    const int tile = (int)blockIdx.x + (blk + j) * (int)gridDim.x;
+                    const long long row = (long long)tile * BM + q * 32 + lane;
+                    const bool live = row < p.M;
+                    uint2 mw = make_uint2(0u, 0u);
+                    if (epi == EPI_MASK_BF16 && live && c0 < N) mw = __ldg(reinterpret_cast<const uint2 *>(Ly.bits_in + row * Ly.ldbits + (c0 >> 5)));
+                    { WCLK_T0(); mbar_wait(tfull0 + 8 * acc, acc_phase); if (threadIdx.x == 64) WCLK_ADD(4); }
+                    tc_fence_after();
+#ifdef LNB_WIDE_CLK
+                    const long long t_epi = clock64();
+#endif
+                    const uint32_t tbase = tmem + acc * acc_cols + ((uint32_t)(q * 32) << 16);
+                    if (epi == EPI_HEAD_F32) {
+                        if (k == 0) {
+                            uint32_t v[16];
+                            tmem_ld16(tbase, v);
+                            tmem_ld_wait();
+                            if (live) {
+                                float z[4];
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) z[c] = __uint_as_float(v[c]) + sBias[c];
+                                float4 o;
+                                o.x = 1.0f / (1.0f + __expf(-z[0])); o.y = 1.0f / (1.0f + __expf(-z[1])); o.z = 1.0f / (1.0f + __expf(-z[2]));
+                                o.w = p.head == LNB_HEAD_NERF ? fmaxf(z[3], 0.0f) : 1.0f / (1.0f + __expf(-z[3]));
+                                reinterpret_cast<float4 *>(Ly.head_out)[row] = o;
+                            }
+                        }
+                    } else if (c0 < N) {
+                        uint32_t words[2] = {0u, 0u};
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            uint32_t v[32];
+                            tmem_ld32(tbase + c0 + h * 32, v);
+                            tmem_ld_wait();
+                            tma_store_wait_read0();          // this warp's previous store has left the box
+                            __syncwarp();
+                            const uint32_t wsel = h == 0 ? mw.x : mw.y;
+                            uint32_t wout = 0;
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {   // four 16-byte pieces of this 64-byte row
+                                uint4 *slot = reinterpret_cast<uint4 *>(buf + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4));
+                                uint32_t pk[4];
+                                if (epi == EPI_RELU_BF16) {
+                                    uint32_t b8 = 0;
+                                    const float4 bA = *reinterpret_cast<const float4 *>(sBias + c0 + h * 32 + g * 8), bB = *reinterpret_cast<const float4 *>(sBias + c0 + h * 32 + g * 8 + 4);
+                                    const float bv[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+#pragma unroll
+                                    for (int c = 0; c < 4; ++c) {
+                                        const float r0 = fmaxf(__uint_as_float(v[g * 8 + 2 * c]) + bv[2 * c], 0.0f);
+                                        const float r1 = fmaxf(__uint_as_float(v[g * 8 + 2 * c + 1]) + bv[2 * c + 1], 0.0f);
+                                        pk[c] = pack_bf16(r0, r1);
+                                        b8 |= ((((pk[c] & 0x7FFF7FFFu) + 0x7FFF7FFFu) >> (15 - c)) & (0x00010001u << c));
+                                    }
+                                    wout |= b8 << (g * 4);
+                                } else {
+                                    const uint32_t b8 = wsel >> (g * 4);
+#pragma unroll
+                                    for (int c = 0; c < 4; ++c)
+                                        pk[c] = pack_bf16(__uint_as_float(v[g * 8 + 2 * c]), __uint_as_float(v[g * 8 + 2 * c + 1])) &
+                                                (((b8 >> c) & 0x00010001u) * 0xFFFFu);
+                                }
+                                *slot = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            }
+                            words[h] = wout;
+                            fence_async_smem();
+                            __syncwarp();
+                            if (lane == 0) {
+                                if (p.l2_hints & 2) tma_store_2d_hint(&maps.C[li], smem_u32(buf), c0 + h * 32, (int)(tile * BM + q * 32), L2_EVICT_LAST);
+                                else tma_store_2d(&maps.C[li], smem_u32(buf), c0 + h * 32, (int)(tile * BM + q * 32));
+                            }
+                        }
+                        if (epi == EPI_RELU_BF16 && Ly.bits_out && live)
+                            *reinterpret_cast<uint2 *>(Ly.bits_out + row * Ly.ldbits + (c0 >> 5)) = make_uint2(words[0], words[1]);
+                    }
+                    tc_fence_before();
+                    mbar_arrive(tempty0 + 8 * acc);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+#ifdef LNB_WIDE_CLK
+                    if (threadIdx.x == 64) atomicAdd(&g_wide_clk[5], (unsigned long long)(clock64() - t_epi));
+#endif
+                    // tell the producer when a tile's output is complete in memory: one tile late, so the wait
+                    // is for stores issued a whole tile ago; the block's last tile is waited for outright
+                    if (signal && lane == 0) {
+                        WCLK_T0();
+                        if (j > 0) { bulk_wait_group_n(n_groups); mbar_arrive(done0 + 8 * (j - 1)); }
+                        if (j == g_cnt - 1) { bulk_wait_group_n(0); mbar_arrive(done0 + 8 * j); }
+                        if (threadIdx.x == 64) WCLK_ADD(6);
+                    }
+                }
+            }
+        }
+    }
+    if (warp >= 2) tma_store_wait_all();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 2 * acc_cols);
+}
+
 // ---- host helpers ------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -364,19 +636,29 @@ EncodeTiledFn get_encode()
 }
 
 // 2-D bf16 row-major [rows][cols] (cols contiguous, row pitch ld elements), box {64 cols, box_rows}, 128B swizzle
-int make_map(lnb_ctx *ctx, CUtensorMap *m, const void *base, long long rows, int cols, int ld, int box_rows)
+int make_map(lnb_ctx *ctx, CUtensorMap *m, const void *base, long long rows, int cols, int ld, int box_rows, int box_cols = 64)
 {
     EncodeTiledFn enc = get_encode();
     if (!enc) { ctx->err = "cuTensorMapEncodeTiled is not available"; return LNB_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};   // 64 columns: 128-byte swizzle; 32 columns: 64-byte swizzle
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { ctx->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; return LNB_ERR_CUDA; }
     return LNB_OK;
+}
+
+// launch configuration with programmatic stream serialization (LNB_WIDE_NO_PDL=1 turns it off)
+void pdl_config(cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attr, int grid, int block, size_t smem, cudaStream_t stream)
+{
+    static const bool use_pdl = getenv("LNB_WIDE_NO_PDL") == nullptr;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg->gridDim = dim3((unsigned)grid); cfg->blockDim = dim3((unsigned)block); cfg->dynamicSmemBytes = smem; cfg->stream = stream;
+    cfg->attrs = attr; cfg->numAttrs = use_pdl ? 1 : 0;
 }
 
 int gemm_a_stages(int N, int K)
@@ -637,16 +919,6 @@ __global__ void wide_prep_kernel(const float *__restrict__ w, int ldw, int in_di
     Wf[(size_t)j * in_pad + k] = __float2bfloat16_rn(v);
 }
 
-// launch configuration with programmatic stream serialization (LNB_WIDE_NO_PDL=1 turns it off)
-void pdl_config(cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attr, int grid, int block, size_t smem, cudaStream_t stream)
-{
-    static const bool use_pdl = getenv("LNB_WIDE_NO_PDL") == nullptr;
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg->gridDim = dim3((unsigned)grid); cfg->blockDim = dim3((unsigned)block); cfg->dynamicSmemBytes = smem; cfg->stream = stream;
-    cfg->attrs = attr; cfg->numAttrs = use_pdl ? 1 : 0;
-}
-
 size_t dw_smem(int in_pad, int out_pad)
 {
     return (size_t)DW_STAGES * ((in_pad / 64) + (out_pad / 64)) * 8192 + (2 * DW_STAGES + 4) * 8 + 16;
@@ -689,6 +961,68 @@ int lnb_wide_gemm(lnb_ctx *ctx, const void *A, int lda, const void *B, int ldb, 
     pdl_config(&cfg, attr, grid, GEMM_THREADS, smem, ctx->stream);
     lnb_prof_begin(ctx, "gemm_tc_kernel");
     LNB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel, mapA, mapB, mapC, p));
+    lnb_prof_end(ctx);
+    LNB_CHECK_LAUNCH();
+    return LNB_OK;
+}
+
+// One launch for a chain of layers (chain_tc_kernel): layer i computes epilogue_i(A_i B_i^T) where A_{i+1}
+// is the bf16 tensor layer i wrote.  All layers share M; K, N multiples of 64 (the last may have N = 16
+// with the head epilogue).
+struct ChainDesc {
+    const void *A; int lda;
+    const void *B; int ldb;
+    int N, K;
+    const float *bias;
+    const uint32_t *bits_in; uint32_t *bits_out; int ldbits;
+    void *C; int ldc;
+    int epi;
+};
+
+int lnb_wide_chain(lnb_ctx *ctx, const ChainDesc *d, int n, long long M, int head)
+{
+    LNB_ARG(n >= 1 && n <= LNB_MAX_LAYERS && M >= 0, "wide chain: layers");
+    if (M == 0) return LNB_OK;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
+    ChainMaps maps;              // 6 KB, passed by value at launch
+    ChainParams p{};
+    size_t b_region = 0;
+    for (int i = 0; i < n; ++i) {
+        const ChainDesc &c = d[i];
+        LNB_ARG(c.N >= 16 && c.N <= 256 && c.N % 16 == 0 && c.K >= 64 && c.K <= 256 && c.K % 64 == 0 && c.lda % 8 == 0 && c.ldb % 8 == 0, "wide chain: shape");
+        LNB_TRY(make_map(ctx, &maps.A[i], c.A, M, c.K, c.lda, BM));
+        LNB_TRY(make_map(ctx, &maps.B[i], c.B, c.N, c.K, c.ldb, c.N));
+        maps.C[i] = maps.A[i];
+        if (c.epi == EPI_RELU_BF16 || c.epi == EPI_MASK_BF16) {
+            LNB_ARG(c.N % 64 == 0 && c.ldc % 8 == 0 && c.ldc >= c.N, "wide chain: bf16 layers are multiples of 64 wide");
+            LNB_ARG((c.epi != EPI_MASK_BF16 || c.bits_in) && (!(c.bits_in || c.bits_out) || (c.ldbits * 32 >= c.N && c.ldbits <= 8)), "wide chain: ReLU bits");
+            LNB_TRY(make_map(ctx, &maps.C[i], c.C, M, c.N, c.ldc, 32, 32));
+        } else {
+            LNB_ARG(c.epi == EPI_HEAD_F32 && i == n - 1, "wide chain: only the last layer may be the head");
+        }
+        ChainLayer &l = p.layer[i];
+        l.bias = c.bias; l.bits_in = c.bits_in; l.bits_out = c.bits_out; l.head_out = c.epi == EPI_HEAD_F32 ? (float *)c.C : nullptr;
+        l.ldbits = c.ldbits; l.N = c.N; l.K = c.K; l.epi = c.epi;
+        const size_t need = (size_t)(c.K / BK - 1) * (256 * BK * 2) + (((size_t)c.N * BK * 2 + 1023) / 1024 * 1024);   // chunks 32 KB apart
+        b_region = need > b_region ? need : b_region;
+    }
+    static const int G = [] { const char *e = getenv("LNB_WIDE_CHAIN_G"); const int g = e ? atoi(e) : 6; return g < 2 ? 2 : (g > CHAIN_MAX_G ? CHAIN_MAX_G : g); }();   // 2..8 (1 hangs: open)
+    // chain: what a layer reads is dead in L2 once read (evict-first); measured 3.04 ms per C5 step against 3.08 with
+    // evict-last stores only
+    static const int l2_hints = [] { const char *e = getenv("LNB_WIDE_L2_HINTS"); return e ? atoi(e) : 1; }();
+    p.M = (int)M; p.n_layers = n; p.G = G; p.head = head; p.l2_hints = l2_hints; p.b_region = (int)b_region;
+    long long st = (232448LL - 2048 - 16 * 2048 - (long long)b_region) / A_STAGE_BYTES;
+    p.a_stages = (int)(st > MAX_A_STAGES ? MAX_A_STAGES : st);
+    LNB_ARG(p.a_stages >= 2, "wide chain: shared memory");
+    const size_t smem = b_region + (size_t)p.a_stages * A_STAGE_BYTES + 16 * 2048 + (28 + CHAIN_MAX_G + 2) * 8 + 1024 + 16;
+    LNB_CUDA(cudaFuncSetAttribute(chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int n_tiles = (int)((M + BM - 1) / BM);
+    const int grid = n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count;
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    pdl_config(&cfg, attr, grid, CHAIN_THREADS, smem, ctx->stream);
+    lnb_prof_begin(ctx, "chain_tc_kernel");
+    LNB_CUDA(cudaLaunchKernelEx(&cfg, chain_tc_kernel, maps, p));
     lnb_prof_end(ctx);
     LNB_CHECK_LAUNCH();
     return LNB_OK;
@@ -880,6 +1214,10 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
     // launch before it, so it starts on the part of its input that the previous kernel touched last
     // and that is still in the 126 MB L2 (LNB_WIDE_NO_SERPENTINE=1 turns it off).
     static const bool serpentine = getenv("LNB_WIDE_NO_SERPENTINE") == nullptr;
+    // one persistent launch per chain of layers (chain_tc_kernel) when the batch is one slab and every hidden width
+    // is a multiple of 64 after padding (always); LNB_WIDE_NO_CHAIN=1 keeps one launch per layer
+    static const bool chain_on = getenv("LNB_WIDE_NO_CHAIN") == nullptr;
+    const bool chain = chain_on && n_slabs == 1;
     ReduceJobs jobs{};
     int blocks = 0;
     for (int r0 = 0; r0 < R; r0 += slab_rays) {
@@ -893,12 +1231,21 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
             f32_to_bf16_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(X + n0 * c_in, c_in, c_in, Ns, H[0] + n0 * in_pad[0], in_pad[0]);
             LNB_CHECK_LAUNCH();
         }
+        if (chain) {
+            ChainDesc cd[LNB_MAX_LAYERS];
+            for (int l = 0; l < L - 1; ++l)
+                cd[l] = ChainDesc{H[l], in_pad[l], Wf[l], in_pad[l], out_pad[l], in_pad[l], biasP[l], nullptr, grad ? bits[l + 1] : nullptr, in_pad[l + 1] / 32,
+                                  H[l + 1], out_pad[l], EPI_RELU_BF16};
+            cd[L - 1] = ChainDesc{H[L - 1], in_pad[L - 1], Wf[L - 1], in_pad[L - 1], 16, in_pad[L - 1], biasP[L - 1], nullptr, nullptr, 0, head, 4, EPI_HEAD_F32};
+            LNB_TRY(lnb_wide_chain(ctx, cd, L, N, mlp->head));
+        } else {
         for (int l = 0; l < L - 1; ++l)
             LNB_TRY(lnb_wide_gemm(ctx, H[l] + n0 * in_pad[l], in_pad[l], Wf[l], in_pad[l], Ns, out_pad[l], in_pad[l], biasP[l], nullptr,
                                   grad ? bits[l + 1] + n0 * (in_pad[l + 1] / 32) : nullptr, in_pad[l + 1] / 32, H[l + 1] + n0 * out_pad[l], out_pad[l],
                                   EPI_RELU_BF16, 0, next_dir()));
         LNB_TRY(lnb_wide_gemm(ctx, H[L - 1] + n0 * in_pad[L - 1], in_pad[L - 1], Wf[L - 1], in_pad[L - 1], Ns, 16, in_pad[L - 1], biasP[L - 1],
                               nullptr, nullptr, 0, head + n0 * 4, 4, EPI_HEAD_F32, mlp->head, next_dir()));
+        }
         LNB_TRY(lnb_launch_composite_fwd(ctx, head + n0 * 4, 4, dists + n0, a->target ? a->target + (size_t)r0 * 3 : nullptr, Rs, S, nullptr, nullptr,
                                          nullptr, nullptr, color + (size_t)r0 * 3, 0, ray_sse + r0));
         if (!grad) continue;
@@ -910,6 +1257,18 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
             LNB_CHECK_LAUNCH();
         }
         dir = 0;
+        if (chain) {
+            // the adjoint chain dZ_{L-1} -> ... -> dZ_0 in one launch, then the weight gradients, first the layers whose
+            // adjoints were written last
+            ChainDesc cd[LNB_MAX_LAYERS];
+            int n = 0;
+            for (int l = L - 1; l >= 1; --l)
+                cd[n++] = ChainDesc{dZ[l], out_pad[l], Wb[l], out_pad[l], in_pad[l], out_pad[l], nullptr, bits[l], nullptr, in_pad[l] / 32, dZ[l - 1], in_pad[l],
+                                    EPI_MASK_BF16};
+            if (n) LNB_TRY(lnb_wide_chain(ctx, cd, n, N, 0));
+            for (int l = 0; l < L; ++l)
+                LNB_TRY(lnb_wide_dw(ctx, H[l], in_pad[l], in_pad[l], dZ[l], out_pad[l], out_pad[l], N, partial[l], bpartial[l], n_part, next_dir()));
+        } else
         for (int l = L - 1; l >= 0; --l) {
             // the weight gradient of layer l (this slab's share: its own set of per-CTA partials) runs right here,
             // between the kernel that wrote dZ_l and the one that reads it again
@@ -944,3 +1303,12 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
     LNB_CHECK_LAUNCH();
     return LNB_OK;
 }
+
+#ifdef LNB_WIDE_CLK
+extern "C" LNB_API int lnb_test_wide_clk(unsigned long long *out8, int reset)
+{
+    if (out8 && cudaMemcpyFromSymbol(out8, g_wide_clk, sizeof(unsigned long long) * 8) != cudaSuccess) return LNB_ERR_CUDA;
+    if (reset) { unsigned long long z[8] = {0}; if (cudaMemcpyToSymbol(g_wide_clk, z, sizeof(z)) != cudaSuccess) return LNB_ERR_CUDA; }
+    return LNB_OK;
+}
+#endif
