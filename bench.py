@@ -432,7 +432,43 @@ def run_ours(args):
                                                     "memory, sample positions and positional encoding on the device"}}
         fl = flops_per_sample(dims)
         alg_bytes = (N * 8 + R * 60) if use_rays else (N * (c_in * 4 + 4) + R * 12)
-        if prof and prof["kernel"] == "gemm_tc_kernel":
+        if prof and prof["kernel"] == "chain_tc_kernel":
+            # wide MLP, chained layers (wide_tc.cu chain_tc_kernel): two launches per step, the forward chain (all L
+            # layers) and the adjoint chain (L-1 layers).  Activations are re-read from L2, so the launch is bound by
+            # the tensor pipe and what feeds it (shared-memory bandwidth), not by HBM: SURVEY 8d's FLOPs per sample
+            # (forward 2*sum(in*out); adjoint the same without layer 0) x samples / launch time against the bf16 peak.
+            sec = prof["ms_per_launch"] * 1e-3
+            f_fwd = 2.0 * sum(dims[l] * dims[l + 1] for l in range(len(dims) - 1))
+            f_adj = 2.0 * sum(dims[l] * dims[l + 1] for l in range(1, len(dims) - 1))
+            flops_launch = N * (f_fwd + f_adj) / 2
+            tpeak = peaks.get("bf16_tflops_sustained", 1389.4)
+            ach = flops_launch / sec / 1e12
+            traffic, traffic_src = None, None
+            prof_csv = os.path.join(ROOT, "profiles", "r01_wide_chain_ncu_full_per_launch.csv")
+            if args.workload == "c5" and os.path.exists(prof_csv):
+                try:
+                    import csv as _csv
+                    rows = [r for r in _csv.reader(open(prof_csv))][1:]
+                    g = [float(r[4]) + float(r[5]) for r in rows if r[2] == "chain_tc_kernel"]   # bytes read + written
+                    if g:
+                        traffic, traffic_src = sum(g) / len(g), "profiles/r01_wide_chain_ncu_full_per_launch.csv (mean of the forward and the adjoint chain)"
+                except Exception:
+                    pass
+            pad = lambda v: (v + 63) // 64 * 64  # noqa: E731
+            Lw = len(dims) - 1
+            b_fwd = N * (pad(dims[0]) * 2 + sum(pad(dims[l + 1]) * 2 + pad(dims[l + 1]) // 8 for l in range(Lw - 1)) + 16)
+            b_adj = N * (pad(dims[Lw]) * 2 + sum(pad(dims[l]) * 2 + pad(dims[l]) // 8 for l in range(1, Lw)))
+            line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
+                                "traffic": traffic, "traffic_source": traffic_src, "kernel": prof["kernel"], "us_per_launch": sec * 1e6,
+                                "launches_timed": prof["launches"], "launches_per_step": 2,
+                                "algorithmic_flops_per_launch": flops_launch, "algorithmic_bytes_per_launch": (b_fwd + b_adj) / 2,
+                                "hbm_gbs": (b_fwd + b_adj) / 2 / sec / 1e9,
+                                "step_tflops": N * fl / (ms / args.steps * 1e-3) / 1e12,
+                                "step_tensor_frac": N * fl / (ms / args.steps * 1e-3) / 1e12 / tpeak,
+                                "note": "the rest of the step is the HBM-bound weight-gradient kernels (dw_tc_kernel, 8 launches); "
+                                        "step_tensor_frac is SURVEY 8d's F_train x samples / step time against the sustained bf16 peak",
+                                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside the step)" if peaks else "fallback 1389 TFLOP/s"}
+        elif prof and prof["kernel"] == "gemm_tc_kernel":
             # wide MLP: layerwise tensor-core GEMMs with bf16 activations in HBM (wide_tc.cu).  Per launch the
             # kernel reads A (rows x K bf16) [+ 32 B/row of ReLU bits when masked] and writes rows x 256 bf16
             # [+ 32 B/row of bits] (the head writes 16 B/row): summed over the step's launches below.
