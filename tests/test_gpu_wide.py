@@ -198,3 +198,23 @@ def test_trainer_on_a_wide_mlp_follows_numpy_adam(ctx, torch_cuda):
         _log("wide trainer %s: loss err %.3g, update l2 err %.3g" % (mode, rel_err(got, losses), upd_l2))
         assert rel_err(got, losses) <= WIDE_TOL
         assert upd_l2 <= 0.2   # Adam turns every entry into ~lr*sign(g): entries below the bf16 noise flip freely
+
+
+def test_chain_kernel_equals_one_launch_per_layer_bit_for_bit():
+    """chain_tc_kernel (all layers of a pass in one launch, activations handed over through L2) runs the very
+    same MMAs and epilogues as one gemm_tc_kernel launch per layer: loss, colour and gradient checksums of a
+    337 500-sample step must agree to the last bit, run after run (a lost hand-over would show up here).
+    The switch is an environment variable read once per process, hence the subprocesses."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def run(env_extra):
+        env = dict(os.environ, **env_extra)
+        out = subprocess.run([sys.executable, os.path.join(root, "tools", "t_chain.py"), "1800"], cwd=root, env=env, capture_output=True,
+                             text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        lines = [l for l in out.stdout.splitlines() if l.startswith("loss ")]
+        assert len(lines) == 3 and len(set(lines)) == 1, lines      # three repetitions, identical
+        return lines[0]
+
+    assert run({}) == run({"LNB_WIDE_NO_CHAIN": "1"}) == run({"LNB_WIDE_CHAIN_G": "3"})
