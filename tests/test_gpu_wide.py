@@ -200,11 +200,12 @@ def test_trainer_on_a_wide_mlp_follows_numpy_adam(ctx, torch_cuda):
         assert upd_l2 <= 0.2   # Adam turns every entry into ~lr*sign(g): entries below the bf16 noise flip freely
 
 
-def test_chain_kernel_equals_one_launch_per_layer_bit_for_bit():
+def test_chain_kernel_equals_one_launch_per_layer():
     """chain_tc_kernel (all layers of a pass in one launch, activations handed over through L2) runs the very
-    same MMAs and epilogues as one gemm_tc_kernel launch per layer: loss, colour and gradient checksums of a
-    337 500-sample step must agree to the last bit, run after run (a lost hand-over would show up here).
-    The switch is an environment variable read once per process, hence the subprocesses."""
+    same MMAs and epilogues as one gemm_tc_kernel launch per layer: loss and colour of a 345 600-sample step
+    must agree to the last printed digit, run after run (a lost hand-over would show up here); the gradients
+    go through differently ordered fp32 partial sums, so they are compared to 1e-5.  The switch is an
+    environment variable read once per process, hence the subprocesses."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -213,8 +214,11 @@ def test_chain_kernel_equals_one_launch_per_layer_bit_for_bit():
         out = subprocess.run([sys.executable, os.path.join(root, "tools", "t_chain.py"), "1800"], cwd=root, env=env, capture_output=True,
                              text=True, timeout=300)
         assert out.returncode == 0, out.stderr[-2000:]
-        lines = [l for l in out.stdout.splitlines() if l.startswith("loss ")]
+        lines = [ln for ln in out.stdout.splitlines() if ln.startswith("loss ")]
         assert len(lines) == 3 and len(set(lines)) == 1, lines      # three repetitions, identical
-        return lines[0]
+        tok = lines[0].split()
+        return tok[1], tok[3], np.array([float(tok[5]), float(tok[7]), float(tok[9])])
 
-    assert run({}) == run({"LNB_WIDE_NO_CHAIN": "1"}) == run({"LNB_WIDE_CHAIN_G": "3"})
+    a, b, c = run({}), run({"LNB_WIDE_NO_CHAIN": "1"}), run({"LNB_WIDE_CHAIN_G": "3"})
+    assert a[0] == b[0] == c[0] and a[1] == b[1] == c[1], (a, b, c)
+    assert np.allclose(a[2], b[2], rtol=1e-5) and np.allclose(a[2], c[2], rtol=1e-5), (a, b, c)
