@@ -481,8 +481,11 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                     // bytes for every layer
                     const int kb_count = p.layer[li].K / BK, b_rows = PAIR ? p.layer[li].N / 2 : p.layer[li].N, b_bytes = b_rows * BK * 2;
                     for (int kb = 0; kb < 4; ++kb) {
+                        // last round's MMAs on this chunk have retired.  Also for a chunk this layer does not use: its
+                        // "full" barrier is advanced by a plain arrive below, and that must not overtake the MMA
+                        // thread's wait for the previous phase (it can when a round has a single tile)
+                        if (round > 0) mbar_wait(bempty0 + 8 * kb, (round - 1) & 1);
                         if (kb < kb_count) {
-                            if (round > 0) mbar_wait(bempty0 + 8 * kb, (round - 1) & 1);   // last round's MMAs on this chunk retired
                             if (PAIR) {
                                 if (leader) mbar_expect_tx(bfull0 + 8 * kb, (uint32_t)(2 * b_bytes));   // both CTAs' halves land on this barrier
                                 tma_load_2d_2sm(smem_u32(sB + kb * B_CHUNK), &maps.B[li], kb * BK, (int)rank * b_rows, bfull0 + 8 * kb);
@@ -1071,7 +1074,7 @@ int lnb_wide_chain(lnb_ctx *ctx, const ChainDesc *d, int n, long long M, int hea
         const size_t need = (size_t)(c.K / BK - 1) * chunk + ((rows * BK * 2 + 1023) / 1024 * 1024);
         b_region = need > b_region ? need : b_region;
     }
-    static const int G = [] { const char *e = getenv("LNB_WIDE_CHAIN_G"); const int g = e ? atoi(e) : 6; return g < 2 ? 2 : (g > CHAIN_MAX_G ? CHAIN_MAX_G : g); }();   // 2..8 (1 hangs: open)
+    static const int G = [] { const char *e = getenv("LNB_WIDE_CHAIN_G"); const int g = e ? atoi(e) : 6; return g < 1 ? 1 : (g > CHAIN_MAX_G ? CHAIN_MAX_G : g); }();
     // chain: what a layer reads is dead in L2 once read (evict-first); measured 3.04 ms per C5 step against 3.08 with
     // evict-last stores only
     static const int l2_hints = [] { const char *e = getenv("LNB_WIDE_L2_HINTS"); return e ? atoi(e) : 1; }();
