@@ -3,6 +3,8 @@
 // feature index = slot*F + coord) and train_nerf.py:289-311 (pts = o + d t, dists, last = 1e8).
 // The exact variants here compute in float64 like the reference; the fused tensor-core path has
 // its own fp32 prologue (fused_tc.cu) with the error bound stated in DESIGN.md.
+#include <cuda_bf16.h>
+
 #include "lnb_internal.h"
 
 namespace {
@@ -32,7 +34,7 @@ __global__ void pos_encoding_kernel(const double *__restrict__ x, long long n, i
 template <typename T>
 __global__ void sample_encode_kernel(const T *__restrict__ o, const T *__restrict__ d,
                                      const T *__restrict__ t, int R, int S, int E,
-                                     float *__restrict__ X, float *__restrict__ dists)
+                                     float *__restrict__ X, float *__restrict__ dists, __nv_bfloat16 *__restrict__ Xb, int ldb)
 {
     long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (long long)R * S * 3) return;
@@ -42,6 +44,23 @@ __global__ void sample_encode_kernel(const T *__restrict__ o, const T *__restric
     const int C = 3 * (1 + 2 * E);
     double tt = (double)t[smp];
     double v = (double)o[r * 3 + f] + (double)d[r * 3 + f] * tt;
+    if (Xb) {
+        // the wide tensor-core path's operand layout: bf16 rows of ldb columns, the float value rounded once more
+        __nv_bfloat16 *x = Xb + smp * ldb;
+        x[f] = __float2bfloat16_rn((float)v);
+        double freq = 1.0;
+        for (int i = 0; i < E; ++i) {
+            // the argument is formed in double and rounded once (error <= 2^-24 * |arg|, far below the bf16 step of
+            // the result); fp32 sincosf with full range reduction instead of the double one: B200's fp64 rate is low
+            float sn, cs;
+            sincosf((float)(freq * v), &sn, &cs);
+            x[(2 * i + 1) * 3 + f] = __float2bfloat16_rn(sn);
+            x[(2 * i + 2) * 3 + f] = __float2bfloat16_rn(cs);
+            freq *= 2.0;
+        }
+        if (f == 0)
+            for (int c = C; c < ldb; ++c) x[c] = __float2bfloat16_rn(0.0f);
+    } else {
     float *x = X + smp * C;
     x[f] = (float)v;
     double freq = 1.0;
@@ -51,6 +70,7 @@ __global__ void sample_encode_kernel(const T *__restrict__ o, const T *__restric
         x[(2 * i + 1) * 3 + f] = (float)sn;
         x[(2 * i + 2) * 3 + f] = (float)cs;
         freq *= 2.0;
+    }
     }
     if (f == 0 && dists) dists[smp] = (s + 1 < S) ? (float)((double)t[smp + 1] - tt) : (float)1e8;
 }
@@ -69,13 +89,20 @@ int lnb_launch_pos_encoding(lnb_ctx *ctx, const double *x, long long n, int F, i
 int lnb_launch_sample_encode(lnb_ctx *ctx, const void *o, const void *d, const void *t, int f64,
                              int R, int S, int E, float *X, float *dists)
 {
+    return lnb_launch_sample_encode_bf16(ctx, o, d, t, f64, R, S, E, X, dists, nullptr, 0);
+}
+
+// the same, writing either fp32 features X [N][3+6E] or (Xb != NULL) bf16 rows Xb [N][ldb], zero beyond 3+6E
+int lnb_launch_sample_encode_bf16(lnb_ctx *ctx, const void *o, const void *d, const void *t, int f64,
+                                  int R, int S, int E, float *X, float *dists, void *Xb, int ldb)
+{
     long long tot = (long long)R * S * 3;
     if (tot <= 0) return LNB_OK;
     const unsigned blocks = (unsigned)((tot + 255) / 256);
     if (f64)
-        sample_encode_kernel<double><<<blocks, 256, 0, ctx->stream>>>((const double *)o, (const double *)d, (const double *)t, R, S, E, X, dists);
+        sample_encode_kernel<double><<<blocks, 256, 0, ctx->stream>>>((const double *)o, (const double *)d, (const double *)t, R, S, E, X, dists, (__nv_bfloat16 *)Xb, ldb);
     else
-        sample_encode_kernel<float><<<blocks, 256, 0, ctx->stream>>>((const float *)o, (const float *)d, (const float *)t, R, S, E, X, dists);
+        sample_encode_kernel<float><<<blocks, 256, 0, ctx->stream>>>((const float *)o, (const float *)d, (const float *)t, R, S, E, X, dists, (__nv_bfloat16 *)Xb, ldb);
     LNB_CHECK_LAUNCH();
     return LNB_OK;
 }

@@ -1232,7 +1232,7 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
     if (!grad) { add((size_t)N * max_pad * 2); add((size_t)N * max_pad * 2); }   // render: two buffers in turn
     if (grad) add((size_t)N * 16);                               // head adjoint fp32 [N][4]
     add((size_t)N * 16);                                         // head fp32 [N][4]
-    if (rays) { add((size_t)N * c_in * 4); add((size_t)R * S * 4); }
+    if (rays) add((size_t)R * S * 4);
     for (int l = 0; l < L; ++l) { add((size_t)in_pad[l] * out_pad[l] * 2); add((size_t)in_pad[l] * out_pad[l] * 2); add((size_t)out_pad[l] * 4); }
     if (grad)
         for (int l = 0; l < L; ++l) { add((size_t)n_slabs * n_part * in_pad[l] * out_pad[l] * 4); add((size_t)n_slabs * n_part * out_pad[l] * 4); }
@@ -1251,10 +1251,12 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
     float *dzh = grad ? (float *)take((size_t)N * 16) : nullptr;
     float *head = (float *)take((size_t)N * 16);
     const float *X = a->X, *dists = a->dists;
-    if (rays) {
-        float *Xe = (float *)take((size_t)N * c_in * 4), *de = (float *)take((size_t)R * S * 4);
-        if (N > 0) LNB_TRY(lnb_launch_sample_encode(ctx, a->rays_o, a->rays_d, a->t, a->ray_dtype == LNB_RAY_F64, R, S, a->pe_bands, Xe, de));
-        X = Xe; dists = de;
+    if (rays) {   // sample positions and positional encoding straight into the bf16 operand of layer 0
+        float *de = (float *)take((size_t)R * S * 4);
+        if (N > 0)
+            LNB_TRY(lnb_launch_sample_encode_bf16(ctx, a->rays_o, a->rays_d, a->t, a->ray_dtype == LNB_RAY_F64, R, S, a->pe_bands, nullptr, de, H[0],
+                                                  in_pad[0]));
+        dists = de;
     }
     __nv_bfloat16 *Wf[LNB_MAX_LAYERS], *Wb[LNB_MAX_LAYERS];
     float *biasP[LNB_MAX_LAYERS];
@@ -1303,7 +1305,7 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
         const int slab = r0 / slab_rays;
         int dir = 0;                                             // the conversion kernels write front to back
         auto next_dir = [&] { dir = serpentine ? !dir : 0; return dir; };
-        {
+        if (!rays) {
             const long long n = Ns * (in_pad[0] / 8);
             f32_to_bf16_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(X + n0 * c_in, c_in, c_in, Ns, H[0] + n0 * in_pad[0], in_pad[0]);
             LNB_CHECK_LAUNCH();
