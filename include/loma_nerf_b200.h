@@ -98,6 +98,12 @@ LNB_API void grad_mlp_fit(float **layer_input, float **d_layer_input, int layer_
  * c[i][j] += sum_k a[i][k] * b[k][j]. */
 LNB_API void mult_a_b(float **a, int a_h, int a_w, float **b, int b_h, int b_w, float **c);
 
+/* replaces: the forward-mode pair constructor the loma compiler emits into every library (autodiff.py:199-208;
+ * `_dfloat make__dfloat(float val, float dval)` in the generated C).  Neither host script calls it; it is exported
+ * so that the symbol table of the drop-in matches the generated one. */
+typedef struct { float val; float dval; } _dfloat;
+LNB_API _dfloat make__dfloat(float val, float dval);
+
 /* ------------------------------------------------------------------------------------------
  * (2) FLAT API
  * ------------------------------------------------------------------------------------------ */

@@ -340,3 +340,12 @@ extern "C" void mult_a_b(float **a, int a_h, int a_w, float **b, int b_h, int b_
     if (!ok) { cudaGetLastError(); fail(); return; }
     for (int i = 0; i < a_h; ++i) memcpy(c[i], &h[na + nb + (size_t)i * b_w], b_w * sizeof(float));
 }
+
+// autodiff.py:199-208: value / tangent pair constructor present in every loma-generated library
+extern "C" LNB_API _dfloat make__dfloat(float val, float dval)
+{
+    _dfloat r;
+    r.val = val;
+    r.dval = dval;
+    return r;
+}

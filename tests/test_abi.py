@@ -37,6 +37,17 @@ def test_library_exports_every_declared_symbol(lib):
         assert hasattr(lib, s), s
 
 
+def test_make_dfloat_pair_constructor(lib):
+    """autodiff.py:199-208: the (value, tangent) struct constructor every loma-generated library carries."""
+    class DFloat(ctypes.Structure):
+        _fields_ = [("val", ctypes.c_float), ("dval", ctypes.c_float)]
+    assert "make__dfloat" in declared_symbols()
+    lib.make__dfloat.restype = DFloat
+    lib.make__dfloat.argtypes = [ctypes.c_float, ctypes.c_float]
+    r = lib.make__dfloat(1.5, -2.25)
+    assert (r.val, r.dval) == (1.5, -2.25)
+
+
 def test_struct_mirror_matches_c_layout(lib):
     from loma_nerf_b200 import _lib as L
     out = (ctypes.c_int * 16)()
