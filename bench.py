@@ -29,11 +29,22 @@ WORKLOADS = {
     # name: (E bands, width, layers, rays per batch, samples per ray)
     "c2": dict(E=5, width=30, layers=3, R=4096, S=64),
     "c5": dict(E=10, width=256, layers=9, R=4096, S=192),
+    # BASELINE config 1: the 2-D image fit of fit_img.py (mlp_fit: 22 -> 16 -> 16 -> 3, sigmoid head, SSE loss, SGD
+    # 1e-4, fit_img.py:379-421,512-513); one step = one pass over a synthetic 256 x 256 image
+    "c1": dict(fit=True, E=5, width=16, layers=3, R=65536, S=1),
 }
 
 
 def workload_config(name, n_gpus, extra=None):
     w = WORKLOADS[name]
+    if w.get("fit"):
+        c_in = 2 + 4 * w["E"]
+        cfg = {"workload": "mlp-fit %s: MLP %d->%s->3 (fit_img.py), %d pixels per GPU per step" % (
+            name.upper(), c_in, "x".join([str(w["width"])] * (w["layers"] - 1)), w["R"]),
+            "pixels_per_gpu": w["R"], "global_pixels": w["R"] * n_gpus,
+            "sharding": "pixels across %d GPU(s), gradient all-reduce" % n_gpus if n_gpus > 1 else "single GPU"}
+        cfg.update(extra or {})
+        return cfg
     c_in = 3 + 6 * w["E"]
     cfg = {"workload": "nerf-train %s: MLP %d->%s->4, %d rays x %d samples per GPU per step" % (
         name.upper(), c_in, "x".join([str(w["width"])] * (w["layers"] - 1)), w["R"], w["S"]),
@@ -126,18 +137,24 @@ def run_reference(args):
         print(json.dumps(line))
         return 0
     chunks = 24   # per core per step: 24 chunks x 256 samples, ~0.25 s of C time
+    fit = bool(w.get("fit"))
     with mp.get_context("fork").Pool(cores) as pool:
+        run = (lambda n: cpu_bench.run_fit(cores, n, pool=pool)) if fit else (lambda n: cpu_bench.run(cores, n, S=w["S"], pool=pool))
         for _ in range(args.warmup):
-            cpu_bench.run(cores, 2, S=w["S"], pool=pool)
+            run(2)
         tot_s, tot_n = 0.0, 0
         for _ in range(args.steps):
-            r = cpu_bench.run(cores, chunks, S=w["S"], pool=pool)
+            r = run(chunks)
             tot_s += r["seconds"]
             tot_n += r["samples"]
     value = tot_n / tot_s
-    sample = ("each step: %d cores x %d chunks x 256 samples (4 rays x 64) of the C2 workload, forward call + grad call "
-              "per chunk as train_nerf.py does, time inside the C calls only" % (cores, chunks))
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+    if fit:
+        sample = ("each step: %d cores x %d chunks x 256 pixels of the C1 workload through mlp_fit / grad_mlp_fit, forward call + grad "
+                  "call per chunk as fit_img.py does (zero-copy marshalling included, microseconds per call)" % (cores, chunks))
+    else:
+        sample = ("each step: %d cores x %d chunks x 256 samples (4 rays x 64) of the C2 workload, forward call + grad call "
+                  "per chunk as train_nerf.py does, time inside the C calls only" % (cores, chunks))
+    line = {"impl": "reference", "metric": "mlp_fit_train_samples_per_s" if fit else METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args.workload, args.gpus),
@@ -177,11 +194,12 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     w = WORKLOADS[args.workload]
     E, R, S = w["E"], w["R"], w["S"]
-    c_in = 3 + 6 * E
-    dims = synthetic.mlp_dims(c_in, w["width"], w["layers"], 4)
+    fit = bool(w.get("fit"))
+    c_in = 2 + 4 * E if fit else 3 + 6 * E
+    dims = synthetic.mlp_dims(c_in, w["width"], w["layers"], 3 if fit else 4)
     N = R * S
     path = args.path
-    use_rays = args.input == "rays"
+    use_rays = args.input == "rays" and not fit
 
     ctx = api.Context(local)
     stream = torch.cuda.current_stream(device)
@@ -192,10 +210,19 @@ def run_ours(args):
     if use_rays:
         bytes_per_batch = R * 3 * 8 * 2 + N * 8 + R * 12
     else:
-        bytes_per_batch = N * c_in * 4 + N * 4 + R * 12
+        bytes_per_batch = N * c_in * 4 + (0 if fit else N * 4) + R * 12
     n_pool = max(2, int(np.ceil(160e6 / bytes_per_batch)) + 1)
     batches, host_batches = [], []
-    for b in range(n_pool):
+    for b in range(n_pool if fit else 0):
+        # pixel coordinates in [0,1)^2, 5-band positional encoding (pos_encoding.py:4-36), a smooth synthetic image
+        xy = rng.uniform(0, 1, (N, 2))
+        target = (0.5 + 0.4 * np.sin(6 * xy[:, :1] + np.array([0.0, 1.0, 2.0])) * np.cos(4 * xy[:, 1:])).clip(0, 1).astype(np.float32)
+        X = ctx.pos_encoding(torch.as_tensor(xy, device=device), E)
+        tgd = torch.as_tensor(target, device=device)
+        batches.append(dict(X=X, target=tgd, path=path))
+        if b < 2:
+            host_batches.append(dict(features=dict(X=X.cpu().pin_memory(), target=tgd.cpu().pin_memory(), path=path)))
+    for b in range(0 if fit else n_pool):
         o, d = synthetic.random_rays(rng, R)
         t = synthetic.stratified_t(rng, R, S)
         target = rng.uniform(0, 1, (R, 3)).astype(np.float32)
@@ -215,7 +242,10 @@ def run_ours(args):
     _dbg("inputs ready")
     ws_np, bs_np = synthetic.init_mlp(np.random.default_rng(216), dims)   # same weights on every rank
     nP = ws_np.size + bs_np.size
-    trainer = api.Trainer(ctx, dims, ws_np, bs_np, optimizer="adam", lr=5e-4)
+    if fit:
+        trainer = api.Trainer(ctx, dims, ws_np, bs_np, head=api.L.HEAD_SIGMOID, optimizer="sgd", lr=1e-4)
+    else:
+        trainer = api.Trainer(ctx, dims, ws_np, bs_np, optimizer="adam", lr=5e-4)
     grads = trainer.grad_buffer()                           # [d_ws | d_bs | loss] on the device
     collective = "none"
     if world > 1:
@@ -369,7 +399,7 @@ def run_ours(args):
     # ---- render (BASELINE config 4 shape): forward-only 800x800 frames, 64 samples per ray, rays mode;
     # frames are disjoint across ranks (no collective)
     render = None
-    if not args.no_render:
+    if not args.no_render and not fit:
         Hh = 800
         frames = []
         for _ in range(2):
@@ -400,8 +430,8 @@ def run_ours(args):
         del frames, col
     _dbg("render done")
     e2e_feat, e2e_n = e2e("features")
-    e2e_rays, _ = e2e("rays")
-    h2d_feat = (N * c_in + N + R * 3) * 4
+    e2e_rays = None if fit else e2e("rays")[0]
+    h2d_feat = (N * c_in + (0 if fit else N) + R * 3) * 4
     h2d_rays = R * 3 * 8 * 2 + N * 8 + R * 12
     clk = clocks.stop() if rank == 0 else None
     _dbg("e2e done")
@@ -431,7 +461,11 @@ def run_ours(args):
                              "steps": e2e_n, "api": "lnb_trainer_step_host, rays mode: float64 rays + depths from pinned host "
                                                     "memory, sample positions and positional encoding on the device"}}
         fl = flops_per_sample(dims)
-        alg_bytes = (N * 8 + R * 60) if use_rays else (N * (c_in * 4 + 4) + R * 12)
+        alg_bytes = (N * 8 + R * 60) if use_rays else (N * (c_in * 4 + (0 if fit else 4)) + R * 12)
+        if fit:
+            line["metric"] = "mlp_fit_train_samples_per_s"
+            line["config"]["optimizer"] = "SGD, step 1e-4 (fit_img.py:417,512-513) inside the step"
+            line["e2e_rays"] = None
         if prof and prof["kernel"] == "chain_tc_kernel":
             # wide MLP, chained layers (wide_tc.cu chain_tc_kernel): two launches per step, the forward chain (all L
             # layers) and the adjoint chain (L-1 layers).  Activations are re-read from L2, so the launch is bound by
@@ -555,6 +589,12 @@ def run_ours(args):
                                         "sample": "%d processes x 2 call pairs x 1 ray x %d samples of this network through the "
                                                   "reference program rebuilt with larger tapes (oracle/_ref/nerf_big.so, 1.9 GB of "
                                                   "stack each), forward + grad call, wall time of the slowest process" % (procs, S)}
+        elif world == 1 and not args.no_cpu_baseline and fit:
+            from oracle import cpu_bench
+            cores = cpu_bench.host_cores()
+            r = cpu_bench.run_fit(cores, 40)
+            line["cpu_baseline"] = {"value": r["samples"] / r["seconds"], "unit": UNIT, "cores": cores, "kind": r["kind"],
+                                    "sample": "%d cores x 40 chunks x 256 pixels, mlp_fit + grad_mlp_fit per chunk (fit_img.py:423-532)" % cores}
         elif world == 1 and not args.no_cpu_baseline:
             from oracle import cpu_bench
             cores = cpu_bench.host_cores()

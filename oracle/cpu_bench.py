@@ -117,6 +117,47 @@ def run_big(n_procs, calls_per_proc=1, S=192):
     return dict(samples=n_procs * calls_per_proc * S, seconds=max(times), kind="reference", cores=n_procs)
 
 
+def _worker_fit(args):
+    """The 2-D fit protocol of fit_img.py:423-532: chunks of 256 pixels, forward call then grad call."""
+    kind, seed, n_chunks = args
+    case = O.make_fit_case(seed, 256)
+    X, ws, bs, dims, target = case["X"], case["ws"], case["bs"], [int(v) for v in case["dims"]], case["target"]
+    box = {}
+    if kind == "reference":
+        ref = O.CompatCaller(ctypes.CDLL(os.path.join(O.REF_DIR, "mlp_fit.so")), big_stack=False)
+
+        def body():
+            t0 = time.perf_counter()
+            for _ in range(n_chunks):
+                ref.mlp_fit(X, ws, bs, dims, target, g="loss")
+            box["t"] = time.perf_counter() - t0
+        O.run_big_stack(body, 256 << 20)     # grad_mlp_fit keeps 14.7 MB of tape on the stack
+        return box["t"]
+    co = O.COracle()
+    t0 = time.perf_counter()
+    for _ in range(n_chunks):
+        f = co.mlp_fit_forward(X, ws, bs, dims, target, rows=256)
+        co.mlp_fit_backward(X, ws, bs, dims, target, float(f["loss"]), rows=256)
+    return time.perf_counter() - t0
+
+
+def run_fit(n_procs, chunks_per_proc, pool=None):
+    """BASELINE config 1 on the host cores: every process runs `chunks_per_proc` chunks of 256 pixels through
+    oracle/_ref/mlp_fit.so (or the C port).  The time includes the zero-copy marshalling of the calls."""
+    kind = "reference" if O.have_ref("mlp_fit") else "port"
+    if kind == "port":
+        O.build_c_oracle()
+    jobs = [(kind, 2000 + p, chunks_per_proc) for p in range(n_procs)]
+    if pool is not None:
+        times = pool.map(_worker_fit, jobs)
+    elif n_procs == 1:
+        times = [_worker_fit(jobs[0])]
+    else:
+        with mp.get_context("fork").Pool(n_procs) as pl:
+            times = pl.map(_worker_fit, jobs)
+    return dict(samples=n_procs * chunks_per_proc * 256, seconds=max(times), kind=kind, cores=n_procs)
+
+
 def host_cores():
     try:
         return max(1, len(os.sched_getaffinity(0)))
