@@ -1190,7 +1190,8 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
         return LNB_ERR_UNSUPPORTED;
     };
     const int L = mlp->n_layers;
-    if (!nerf) return unsupported("mlp_fit runs on the fused kernel or the fp32 path");
+    if (!nerf && (a->S != 1 || a->target_w < 1 || a->target_w > 4 || a->target_w > mlp->dims[L] || (!a->X)))
+        return unsupported("mlp_fit needs features, one sample per row and at most 4 output channels");
     if (L < 2 || L > LNB_MAX_LAYERS) return unsupported("needs 2..16 layers");
     for (int l = 0; l <= L; ++l)
         if (mlp->dims[l] > 256) return unsupported("layer widths above 256");
@@ -1325,11 +1326,18 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
         LNB_TRY(lnb_wide_gemm(ctx, H[L - 1] + n0 * in_pad[L - 1], in_pad[L - 1], Wf[L - 1], in_pad[L - 1], Ns, 16, in_pad[L - 1], biasP[L - 1],
                               nullptr, nullptr, 0, head + n0 * 4, 4, EPI_HEAD_F32, mlp->head, next_dir()));
         }
-        LNB_TRY(lnb_launch_composite_fwd(ctx, head + n0 * 4, 4, dists + n0, a->target ? a->target + (size_t)r0 * 3 : nullptr, Rs, S, nullptr, nullptr,
-                                         nullptr, nullptr, color + (size_t)r0 * 3, 0, ray_sse + r0));
+        if (nerf) {
+            LNB_TRY(lnb_launch_composite_fwd(ctx, head + n0 * 4, 4, dists + n0, a->target ? a->target + (size_t)r0 * 3 : nullptr, Rs, S, nullptr, nullptr,
+                                             nullptr, nullptr, color + (size_t)r0 * 3, 0, ray_sse + r0));
+        } else if (a->target) {   // mlp_fit: the prediction is the sigmoid head itself, SSE over target_w channels (mlp_fit.py:140-145)
+            LNB_TRY(lnb_launch_fit_loss(ctx, head + n0 * 4, 4, a->target + (size_t)r0 * a->target_w, Rs, a->target_w, ray_sse + r0));
+        }
         if (!grad) continue;
-        LNB_TRY(lnb_launch_composite_bwd(ctx, head + n0 * 4, 4, dists + n0, a->target + (size_t)r0 * 3, color + (size_t)r0 * 3, Rs, S, dzh + n0 * 4, 4, 4,
-                                         nullptr, nullptr));
+        if (nerf)
+            LNB_TRY(lnb_launch_composite_bwd(ctx, head + n0 * 4, 4, dists + n0, a->target + (size_t)r0 * 3, color + (size_t)r0 * 3, Rs, S, dzh + n0 * 4, 4, 4,
+                                             nullptr, nullptr));
+        else
+            LNB_TRY(lnb_launch_fit_head_bwd(ctx, head + n0 * 4, 4, a->target + (size_t)r0 * a->target_w, Rs, a->target_w, Rs, 4, dzh + n0 * 4, 4, nullptr));
         {
             const long long n = Ns * (out_pad[L - 1] / 8);
             f32_to_bf16_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dzh + n0 * 4, 4, 4, Ns, dZ[L - 1] + n0 * out_pad[L - 1], out_pad[L - 1]);

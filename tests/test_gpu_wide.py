@@ -223,3 +223,20 @@ def test_chain_kernel_equals_one_launch_per_layer():
     d = run({"LNB_WIDE_CTA_PAIR": "1", "LNB_WIDE_CHAIN_G": "1"})      # CTA pairs (tcgen05.mma.cta_group::2), single-tile blocks
     assert a[0] == b[0] == c[0] == d[0] and a[1] == b[1] == c[1] == d[1], (a, b, c, d)
     assert np.allclose(a[2], b[2], rtol=1e-5) and np.allclose(a[2], c[2], rtol=1e-5) and np.allclose(a[2], d[2], rtol=1e-5), (a, b, c, d)
+
+
+@pytest.mark.parametrize("N,width,layers", [(5000, 128, 5), (20000, 256, 9), (300, 70, 3)])
+def test_wide_path_mlp_fit_against_f64_restatement(ctx, torch_cuda, N, width, layers):
+    """mlp_fit (scripts/mlp_fit.py:39-147: sigmoid head, SSE over the 3 colour channels) with a network too wide for
+    the fused kernel: the layerwise tensor-core kernels with the fit head, against the float64 restatement."""
+    torch = torch_cuda
+    case = O.make_fit_case(3100 + width, N, E=5, width=width, n_layers=layers)
+    cv = lambda a: torch.as_tensor(np.ascontiguousarray(a, np.float32)).cuda()  # noqa: E731
+    dims = [int(v) for v in case["dims"]]
+    out = ctx.fit_step(dims, cv(case["X"]), cv(case["ws"]), cv(case["bs"]), cv(case["target"]), grad=True, seed=1.0, outputs=("loss",), path="tc")
+    ctx.synchronize()
+    f = O.mlp_fit_f64(case["X"], case["ws"], case["bs"], case["dims"], case["target"], g=1.0)
+    errs = dict(loss=rel_err(out["loss"].cpu().numpy()[0], f["loss"]), d_ws=rel_err(out["d_ws"].cpu().numpy(), f["d_ws"]),
+                d_bs=rel_err(out["d_bs"].cpu().numpy(), f["d_bs"]))
+    _log("wide fit N=%d w=%d L=%d %s" % (N, width, layers, errs))
+    assert max(errs.values()) <= WIDE_TOL, errs
