@@ -5,6 +5,8 @@
 // cumprod_alpha, weights_samples back) and what the fused tensor-core kernel (fused_tc.cu) is
 // checked against on the device.  Reference: /root/reference/scripts/nerf.py:67-304,
 // scripts/mlp_fit.py:39-147 and their reverse (loma_public/reverse_diff.py:576-951).
+#include <stdint.h>
+
 #include "lnb_internal.h"
 
 namespace {
@@ -153,6 +155,182 @@ dw_partials_kernel(const float *__restrict__ H, int ldh, const float *__restrict
             if (j < out_dim) out[(size_t)k * out_dim + j] = acc[a][b];
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Wide layers (e.g. the paper-size 256-wide MLP): classic register-blocked fp32 GEMMs.  128 x 128
+// block tile, K slab of 16, 256 threads, 8 x 8 outputs per thread as 2 x 2 groups of 4 x 4 (so the
+// shared-memory reads are float4: the A reads broadcast, the B reads are contiguous), the next slab
+// prefetched into registers while the current one is multiplied (one barrier per slab).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sgemm128_kernel(lnb_gemm_args g)
+{
+    constexpr int BM = 128, BN = 128, BK = 16;
+    __shared__ __align__(16) float As[2][BK][BM + 4];   // k-major: As[k][row]
+    __shared__ __align__(16) float Bs[2][BK][BN + 4];
+    const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+    const long long row0 = (long long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const int ar = t >> 2, ak = (t & 3) * 4;            // A loader: rows ar, ar + 64; columns ak .. ak + 3 of the slab
+    const bool b_n_fast = g.sbn == 1;                   // B loader walks the contiguous direction of B
+    float4 pa[2];
+    float pb[8];
+    auto load = [&](int k0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const long long r = row0 + ar + 64 * h;
+            pa[h] = r < g.a_rows ? __ldg(reinterpret_cast<const float4 *>(g.A + r * g.lda + k0 + ak)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int e = t + 256 * i;
+            const int kk = b_n_fast ? e >> 7 : e & 15, n = b_n_fast ? e & 127 : e >> 4;
+            pb[i] = n0 + n < g.n_dim ? __ldg(g.B + (long long)(k0 + kk) * g.sbk + (long long)(n0 + n) * g.sbn) : 0.0f;
+        }
+    };
+    auto store = [&](int buf) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            As[buf][ak + 0][ar + 64 * h] = pa[h].x; As[buf][ak + 1][ar + 64 * h] = pa[h].y;
+            As[buf][ak + 2][ar + 64 * h] = pa[h].z; As[buf][ak + 3][ar + 64 * h] = pa[h].w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int e = t + 256 * i;
+            const int kk = b_n_fast ? e >> 7 : e & 15, n = b_n_fast ? e & 127 : e >> 4;
+            Bs[buf][kk][n] = pb[i];
+        }
+    };
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+    load(0);
+    store(0);
+    __syncthreads();
+    const int n_slabs = g.k_dim / BK;
+    for (int sl = 0; sl < n_slabs; ++sl) {
+        const int buf = sl & 1;
+        if (sl + 1 < n_slabs) load((sl + 1) * BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][kk][ty * 4]), a1 = *reinterpret_cast<const float4 *>(&As[buf][kk][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[buf][kk][tx * 4]), b1 = *reinterpret_cast<const float4 *>(&Bs[buf][kk][64 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (sl + 1 < n_slabs) store(buf ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long r = row0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+        if (r >= g.rows) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
+            if (n >= g.n_dim) continue;
+            float v = acc[i][j];
+            float *c = g.C + r * g.ldc + n;
+            if (g.acc) v += *c;
+            if (g.bias) v += __ldg(g.bias + n);
+            if (g.act == ACT_RELU) v = v > 0.0f ? v : 0.0f;
+            else if (g.act == ACT_SIGMOID) v = sigmoidf_(v);
+            else if (g.act == ACT_NERF_HEAD) v = (n == 3) ? (v > 0.0f ? v : 0.0f) : sigmoidf_(v);
+            if (g.mask && !(__ldg(g.mask + r * g.ldmask + n) > 0.0f)) v = 0.0f;
+            *c = v;
+        }
+    }
+}
+
+// dW partials of a wide layer: partial[z][k][j] = sum over the chunk's rows of H[i][k] dZ[i][j] for a 128 x 128 (k, j)
+// tile, and (k-tile 0 only) the bias row partial[z][in_dim][j] = sum_i dZ[i][j].  Same register blocking.
+__global__ void __launch_bounds__(256)
+dw128_kernel(const float *__restrict__ H, int ldh, const float *__restrict__ dZ, int ldz, float *__restrict__ partial, int in_dim,
+             int out_dim, long long rows, long long rows_per_chunk)
+{
+    constexpr int SL = 16;
+    __shared__ __align__(16) float Hs[2][SL][128 + 4];
+    __shared__ __align__(16) float Zs[2][SL][128 + 4];
+    const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+    const int k0 = blockIdx.y * 128, j0 = blockIdx.z * 128;
+    const long long r_begin = (long long)blockIdx.x * rows_per_chunk;
+    long long r_end = r_begin + rows_per_chunk;
+    if (r_end > rows) r_end = rows;
+    const int li = t >> 5, lc = (t & 31) * 4;           // loader: slab rows li, li + 8; columns lc .. lc + 3
+    float4 ph[2], pz[2];
+    auto load = [&](long long r0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const long long r = r0 + li + 8 * h;
+            const bool live = r < r_end;
+            ph[h] = (live && k0 + lc < in_dim) ? __ldg(reinterpret_cast<const float4 *>(H + r * ldh + k0 + lc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            pz[h] = (live && j0 + lc < out_dim) ? __ldg(reinterpret_cast<const float4 *>(dZ + r * ldz + j0 + lc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto store = [&](int buf) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            *reinterpret_cast<float4 *>(&Hs[buf][li + 8 * h][lc]) = ph[h];
+            *reinterpret_cast<float4 *>(&Zs[buf][li + 8 * h][lc]) = pz[h];
+        }
+    };
+    float acc[8][8], bsum[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        bsum[i] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+    }
+    const bool do_bias = blockIdx.y == 0 && ty == 0;
+    if (r_begin < r_end) {
+        load(r_begin);
+        store(0);
+    }
+    __syncthreads();
+    int buf = 0;
+    for (long long r0 = r_begin; r0 < r_end; r0 += SL, buf ^= 1) {
+        const bool more = r0 + SL < r_end;
+        if (more) load(r0 + SL);
+#pragma unroll
+        for (int i = 0; i < SL; ++i) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&Hs[buf][i][ty * 4]), a1 = *reinterpret_cast<const float4 *>(&Hs[buf][i][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4 *>(&Zs[buf][i][tx * 4]), b1 = *reinterpret_cast<const float4 *>(&Zs[buf][i][64 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+            if (do_bias)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) bsum[b] += bv[b];
+        }
+        if (more) store(buf ^ 1);
+        __syncthreads();
+    }
+    float *out = partial + (size_t)blockIdx.x * (size_t)(in_dim + 1) * out_dim;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int k = k0 + (a < 4 ? ty * 4 + a : 64 + ty * 4 + a - 4);
+        if (k >= in_dim) continue;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int j = j0 + (b < 4 ? tx * 4 + b : 64 + tx * 4 + b - 4);
+            if (j < out_dim) out[(size_t)k * out_dim + j] = acc[a][b];
+        }
+    }
+    if (do_bias)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int j = j0 + (b < 4 ? tx * 4 + b : 64 + tx * 4 + b - 4);
+            if (j < out_dim) out[(size_t)in_dim * out_dim + j] = bsum[b];
+        }
 }
 
 // Fast path for narrow layers (in_dim + 1 <= KP <= 64, out_dim <= 32): one warp per row, lane j
@@ -488,6 +666,12 @@ __global__ void axpy2d_kernel(float *__restrict__ dst, long long ldd, const floa
 int lnb_launch_row_gemm(lnb_ctx *ctx, const lnb_gemm_args &g)
 {
     if (g.rows <= 0 || g.n_dim <= 0) return LNB_OK;
+    if (g.n_dim >= 64 && g.k_dim >= 64 && g.k_dim % 16 == 0 && g.lda % 4 == 0 && ((uintptr_t)g.A & 15) == 0 && g.rows >= 128) {
+        dim3 grid((unsigned)((g.rows + 127) / 128), (unsigned)((g.n_dim + 127) / 128));
+        sgemm128_kernel<<<grid, 256, 0, ctx->stream>>>(g);
+        LNB_CHECK_LAUNCH();
+        return LNB_OK;
+    }
     if (g.n_dim <= 32) {
         dim3 grid((unsigned)((g.rows + 127) / 128), (unsigned)((g.n_dim + 31) / 32));
         row_gemm_kernel<128, 32><<<grid, 256, 0, ctx->stream>>>(g);
@@ -513,6 +697,14 @@ int lnb_launch_dw_partials(lnb_ctx *ctx, const float *H, int ldh, const float *d
         else if (kp == 48) LNB_DWR(48);
         else LNB_DWR(64);
 #undef LNB_DWR
+        LNB_CHECK_LAUNCH();
+        return LNB_OK;
+    }
+    if (in_dim >= 64 && out_dim >= 64 && in_dim % 4 == 0 && out_dim % 4 == 0 && ldh % 4 == 0 && ldz % 4 == 0 && ((uintptr_t)H & 15) == 0 &&
+        ((uintptr_t)dZ & 15) == 0) {
+        rpc = (rpc + 15) / 16 * 16;
+        dim3 grid((unsigned)n_chunks, (unsigned)((in_dim + 127) / 128), (unsigned)((out_dim + 127) / 128));
+        dw128_kernel<<<grid, 256, 0, ctx->stream>>>(H, ldh, dZ, ldz, partial, in_dim, out_dim, rows, rpc);
         LNB_CHECK_LAUNCH();
         return LNB_OK;
     }

@@ -240,3 +240,21 @@ def test_wide_path_mlp_fit_against_f64_restatement(ctx, torch_cuda, N, width, la
                 d_bs=rel_err(out["d_bs"].cpu().numpy(), f["d_bs"]))
     _log("wide fit N=%d w=%d L=%d %s" % (N, width, layers, errs))
     assert max(errs.values()) <= WIDE_TOL, errs
+
+
+@pytest.mark.parametrize("R,S,width,layers", [(96, 64, 256, 5), (77, 33, 200, 4), (50, 20, 130, 3), (3, 100, 128, 6)])
+def test_exact_path_on_wide_layers_against_f64_restatement(ctx, torch_cuda, R, S, width, layers):
+    """The fp32 CUDA-core path on wide layers takes the register-blocked 128 x 128 kernels (sgemm128_kernel,
+    dw128_kernel in kernels_f32.cu) where shapes allow and the generic ones elsewhere; both within 1e-5."""
+    torch = torch_cuda
+    case = O.make_nerf_case(4100 + width, R, S, E=10, width=width, n_layers=layers)
+    cv = lambda a: torch.as_tensor(np.ascontiguousarray(a, np.float32)).cuda()  # noqa: E731
+    dims = [int(v) for v in case["dims"]]
+    out = ctx.nerf_step(dims, cv(case["X"]), cv(case["ws"]), cv(case["bs"]), cv(case["dists"]), cv(case["target"]), R=R, S=S, grad=True, seed="loss",
+                        outputs=("color", "loss", "d_X", "d_dists"), path="f32")
+    ctx.synchronize()
+    f = O.nerf_f64(case["X"], case["ws"], case["bs"], case["dims"], case["target"], case["dists"], R, S, g="loss")
+    errs = {k: rel_err(out[k].cpu().numpy().reshape(np.asarray(f[k]).shape), f[k]) for k in ("color", "d_ws", "d_bs", "d_X", "d_dists")}
+    errs["loss"] = rel_err(out["loss"].cpu().numpy()[0], f["loss"])
+    _log("exact wide R=%d S=%d w=%d L=%d %s" % (R, S, width, layers, errs))
+    assert max(errs.values()) <= 1e-5, errs
