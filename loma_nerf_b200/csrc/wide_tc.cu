@@ -8,12 +8,17 @@
 //   backward  dZ_{l-1} = (dZ_l W_l^T) * [H_l > 0]         (reverse_diff.py rules)
 //   gradient  dW_l = H_l^T dZ_l, db_l = colsum(dZ_l)      (contraction over all samples)
 //
-// One warp-specialised persistent kernel serves the first two (gemm_tc_kernel): a TMA producer warp
-// streams 128 x 64 A tiles and N x 64 B tiles (128-byte swizzle) through a 4-stage shared-memory
-// ring, one thread issues tcgen05.mma (M = 128, N <= 256, K = 16) into one of two TMEM accumulators,
-// four epilogue warps drain the other (tcgen05.ld -> bias / activation / mask -> bf16 -> global).
-// The weight-gradient kernel (dw_tc_kernel) reads the same row-major bf16 activations as MN-major
-// operands (features contiguous) and accumulates a 256 x N tile over a slab of samples in TMEM.
+// Kernels (all warp-specialised and persistent, one CTA per SM, TMA + mbarrier pipelines):
+//   chain_tc_kernel  the forward pass and the adjoint pass, each ONE launch: a CTA takes blocks of its 128-sample
+//                    tiles through all layers, the layer's weights in shared memory, the activations handed from
+//                    layer to layer through L2; tcgen05.mma (M = 128 or, on CTA pairs, 256; N <= 256; K = 16) into
+//                    two TMEM accumulators, 16 epilogue warps (tcgen05.ld -> bias / ReLU + bit pattern / mask ->
+//                    bf16 -> swizzled staging -> TMA store).  The default.
+//   gemm_tc_kernel   the same GEMM + epilogues as one launch per layer (tests, ray slabs, LNB_WIDE_NO_CHAIN).
+//   dw_tc_kernel     the weight gradient: the row-major bf16 activations read as MN-major operands (features
+//                    contiguous), a 256 x N product accumulated in TMEM over the CTA's share of the samples, the
+//                    column sums of dZ (the bias gradient) added up by the otherwise idle epilogue warps.
+//   wide_reduce_all_kernel  one fixed-order reduction of every layer's per-CTA partials per step.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdio.h>
@@ -25,7 +30,6 @@ namespace {
 
 constexpr int BM = 128;     // rows (samples) per tile
 constexpr int BK = 64;      // K elements per pipeline stage = one 128-byte swizzle atom of bf16
-constexpr int STAGES = 3;     // 3 x 48 KB operand ring + 32 KB epilogue staging (bf16 outputs leave by TMA store)
 constexpr int GEMM_THREADS = 320; // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant: one warp per
                                   // scheduler cannot hide its own ALU latency, and the epilogue is the long pole)
 constexpr int DW_THREADS = 192;   // weight-gradient kernel: warp 0 TMA, warp 1 MMA, warps 2..5 column sums + epilogue
