@@ -258,3 +258,36 @@ def test_exact_path_on_wide_layers_against_f64_restatement(ctx, torch_cuda, R, S
     errs["loss"] = rel_err(out["loss"].cpu().numpy()[0], f["loss"])
     _log("exact wide R=%d S=%d w=%d L=%d %s" % (R, S, width, layers, errs))
     assert max(errs.values()) <= 1e-5, errs
+
+
+def test_wide_path_random_shapes(ctx, torch_cuda):
+    """Sixteen random (bands, width, depth, rays, samples, input mode, forward-only or train) draws, fixed seed: odd
+    widths (padding to 64), ragged last tiles, a single sample per ray, up to 11 layers -- each within the wide bound."""
+    torch = torch_cuda
+    rng = np.random.default_rng(20261018)
+    cv = lambda a: torch.as_tensor(np.ascontiguousarray(a, np.float32)).cuda()  # noqa: E731
+    worst = 0.0
+    for it in range(16):
+        E = int(rng.integers(1, 11)); width = int(rng.integers(63, 257)); layers = int(rng.integers(2, 12))
+        R = int(rng.integers(1, 400)); S = int(rng.integers(1, 200)); rays = bool(rng.integers(0, 2)); grad = bool(rng.integers(0, 4))
+        case = O.make_nerf_case(6000 + it, R, S, E=E, width=width, n_layers=layers)
+        dims = [int(v) for v in case["dims"]]
+        if rays:
+            r = [torch.as_tensor(np.ascontiguousarray(case[k], np.float64)).cuda() for k in ("rays_o", "rays_d", "t")]
+            out = ctx.nerf_step_rays(dims, r[0], r[1], r[2], E, cv(case["ws"]), cv(case["bs"]), cv(case["target"]), grad=grad, seed=1.0,
+                                     outputs=("color", "loss"), path="tc")
+        else:
+            out = ctx.nerf_step(dims, cv(case["X"]), cv(case["ws"]), cv(case["bs"]), cv(case["dists"]), cv(case["target"]), R=R, S=S, grad=grad,
+                                seed=1.0, outputs=("color", "loss"), path="tc")
+        ctx.synchronize()
+        f = O.nerf_f64(case["X"], case["ws"], case["bs"], case["dims"], case["target"], case["dists"], R, S, g=1.0)
+        errs = dict(loss=rel_err(out["loss"].cpu().numpy()[0], f["loss"]), color=rel_err(out["color"].cpu().numpy(), f["color"]))
+        if grad:
+            errs.update(d_ws=rel_err(out["d_ws"].cpu().numpy(), f["d_ws"]), d_bs=rel_err(out["d_bs"].cpu().numpy(), f["d_bs"]))
+        shape = dict(E=E, width=width, layers=layers, R=R, S=S, rays=rays, grad=grad)
+        _log("wide random %s %s" % (shape, errs))
+        # a draw with one or two rays carries the single-ray amplification of the golden-vector test above
+        bound = WIDE_TOL if R >= 8 else 0.2
+        assert all(np.isfinite(v) for v in errs.values()) and max(errs.values()) <= bound, (shape, errs)
+        worst = max(worst, max(errs.values()))
+    _log("wide random worst %.3g" % worst)
