@@ -615,13 +615,14 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                                 reinterpret_cast<float4 *>(Ly.head_out)[row] = o;
                             }
                         }
-                    } else if (c0 < N) {
+                    } else if (c0 < N && !(p.l2_hints & 16)) {
                         uint32_t words[2] = {0u, 0u};
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             uint32_t v[32];
                             tmem_ld32(tbase + c0 + h * 32, v);
                             tmem_ld_wait();
+                            if (p.l2_hints & 8) { if (v[0] == 0x7fc12345u) words[0] = v[1]; continue; }   // timing experiment: drain only
                             tma_store_wait_read0();          // this warp's previous store has left the box
                             __syncwarp();
                             const uint32_t wsel = h == 0 ? mw.x : mw.y;
