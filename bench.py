@@ -499,7 +499,7 @@ def run_ours(args):
                                 "hbm_gbs": (b_fwd + b_adj) / 2 / sec / 1e9,
                                 "step_tflops": N * fl / (ms / args.steps * 1e-3) / 1e12,
                                 "step_tensor_frac": N * fl / (ms / args.steps * 1e-3) / 1e12 / tpeak,
-                                "note": "the rest of the step is the HBM-bound weight-gradient kernels (dw_tc_kernel, 8 launches); "
+                                "note": "the rest of the step is the HBM-bound weight-gradient kernels (dw_tc_kernel, one launch per layer); "
                                         "step_tensor_frac is SURVEY 8d's F_train x samples / step time against the sustained bf16 peak",
                                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside the step)" if peaks else "fallback 1389 TFLOP/s"}
         elif prof and prof["kernel"] == "gemm_tc_kernel":
