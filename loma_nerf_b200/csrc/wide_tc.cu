@@ -976,16 +976,20 @@ __global__ void f32_to_bf16_rows_kernel(const float *__restrict__ src, int lds, 
     *reinterpret_cast<uint4 *>(dst + i * ldd + c8) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
 }
 
-// weight images: Wf[l] = [out_pad][in_pad] (forward B operand, K = in), Wb[l] = [in_pad][out_pad] (backward, K = out)
-__global__ void wide_prep_kernel(const float *__restrict__ w, int ldw, int in_dim, int out_dim, int in_pad, int out_pad,
-                                 __nv_bfloat16 *__restrict__ Wf, __nv_bfloat16 *__restrict__ Wb)
+// weight images: Wf[l] = [out_pad][in_pad] (forward B operand, K = in), Wb[l] = [in_pad][out_pad] (backward, K = out);
+// every layer's weight images and padded bias in ONE launch: blockIdx.y = layer
+struct PrepJob { const float *w, *b; __nv_bfloat16 *Wf, *Wb; float *biasP; int in_dim, out_dim, in_pad, out_pad; };
+struct PrepJobs { PrepJob job[LNB_MAX_LAYERS]; int ldw; };
+__global__ void wide_prep_all_kernel(const __grid_constant__ PrepJobs jobs)
 {
+    const PrepJob &J = jobs.job[blockIdx.y];
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= in_pad * out_pad) return;
-    const int k = e / out_pad, j = e % out_pad;
-    const float v = (k < in_dim && j < out_dim) ? w[(size_t)k * ldw + j] : 0.0f;
-    Wb[(size_t)k * out_pad + j] = __float2bfloat16_rn(v);
-    Wf[(size_t)j * in_pad + k] = __float2bfloat16_rn(v);
+    if (e < J.out_pad) J.biasP[e] = e < J.out_dim ? J.b[e] : 0.0f;
+    if (e >= J.in_pad * J.out_pad) return;
+    const int k = e / J.out_pad, j = e % J.out_pad;
+    const float v = (k < J.in_dim && j < J.out_dim) ? J.w[(size_t)k * jobs.ldw + j] : 0.0f;
+    J.Wb[(size_t)k * J.out_pad + j] = __float2bfloat16_rn(v);
+    J.Wf[(size_t)j * J.in_pad + k] = __float2bfloat16_rn(v);
 }
 
 size_t dw_smem(int in_pad, int out_pad)
@@ -1285,13 +1289,17 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
     }
 
     // ---- weight images, padded biases
-    for (int l = 0; l < L; ++l) {
-        const int n = in_pad[l] * out_pad[l];
-        wide_prep_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(a->ws + (size_t)l * mlp->max_in * mlp->max_out, mlp->max_out, mlp->dims[l],
-                                                                   mlp->dims[l + 1], in_pad[l], out_pad[l], Wf[l], Wb[l]);
+    {
+        PrepJobs pj{};
+        int n_max = 0;
+        for (int l = 0; l < L; ++l) {
+            pj.job[l] = PrepJob{a->ws + (size_t)l * mlp->max_in * mlp->max_out, a->bs + (size_t)l * mlp->max_out, Wf[l], Wb[l], biasP[l], mlp->dims[l],
+                                mlp->dims[l + 1], in_pad[l], out_pad[l]};
+            n_max = in_pad[l] * out_pad[l] > n_max ? in_pad[l] * out_pad[l] : n_max;
+        }
+        pj.ldw = mlp->max_out;
+        wide_prep_all_kernel<<<dim3((n_max + 255) / 256, L), 256, 0, ctx->stream>>>(pj);
         LNB_CHECK_LAUNCH();
-        LNB_CUDA(cudaMemsetAsync(biasP[l], 0, (size_t)out_pad[l] * 4, ctx->stream));
-        LNB_CUDA(cudaMemcpyAsync(biasP[l], a->bs + (size_t)l * mlp->max_out, (size_t)mlp->dims[l + 1] * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     }
 
     // ---- forward and adjoint chain, slab by slab (unit seed; the seed scales d_ws / d_bs at the end).
