@@ -23,7 +23,8 @@ def get_rays(height, width, normalized_K, c2w_pose):
 def compute_psnr(img1, img2, max_val=1.0):
     """train_nerf.py:163-183."""
     mse = np.mean((np.asarray(img1, np.float64) - np.asarray(img2, np.float64)) ** 2)
-    return 20 * np.log10(max_val / np.sqrt(mse))
+    with np.errstate(divide="ignore"):      # identical images: +inf, as the reference's expression gives
+        return 20 * np.log10(max_val / np.sqrt(mse))
 
 
 def render_rays(ctx, dims, ws, bs, rays_o, rays_d, t, pe_bands, path="tc", rays_per_call=1 << 18):
@@ -63,3 +64,41 @@ def load_weights(prefix):
     if ws.ndim != 3 or bs.ndim != 2 or ws.shape[0] != bs.shape[0] or ws.shape[2] != bs.shape[1]:
         raise ValueError("not a padded (L,max_in,max_out) / (L,max_out) weight pair")
     return ws.astype(np.float32), bs.astype(np.float32)
+
+
+def pose_spherical(theta_deg, phi_deg, radius):
+    """Camera-to-world matrix of a camera on a sphere around the origin looking at it (the orbit the Blender scenes'
+    test poses follow, transforms_test.json; -z is the viewing direction as in get_rays above)."""
+    th, ph = np.deg2rad(theta_deg), np.deg2rad(phi_deg)
+    trans = np.eye(4); trans[2, 3] = radius
+    rot_phi = np.array([[1, 0, 0, 0], [0, np.cos(ph), -np.sin(ph), 0], [0, np.sin(ph), np.cos(ph), 0], [0, 0, 0, 1.0]])
+    rot_th = np.array([[np.cos(th), 0, -np.sin(th), 0], [0, 1, 0, 0], [np.sin(th), 0, np.cos(th), 0], [0, 0, 0, 1.0]])
+    flip = np.array([[-1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1.0]])
+    return flip @ rot_th @ rot_phi @ trans
+
+
+def render_video(ctx, dims, ws, bs, height, width, normalized_K, poses, n_samples, pe_bands, out_dir=None, near=2.0, far=6.0,
+                 path="tc", ground_truth=None, fps=30, frame_fn=None):
+    """What make_nerf_video.py is named for but does not do (it stitches ground-truth PNGs): render one frame per
+    camera pose with the trained weights, optionally score each against its ground-truth image
+    (train_nerf.py:163-183) and write frame_%04d.png plus an animated orbit.gif into out_dir (PIL; mp4 needs
+    imageio/ffmpeg, which the hosts' environment may not have).  Returns (frames uint8 [F][H][W][3], psnr list | None).
+    frame_fn(i, pose) -> float image may replace the device render (tests of the host side)."""
+    frames, psnr = [], ([] if ground_truth is not None else None)
+    for i, pose in enumerate(poses):
+        img = frame_fn(i, pose) if frame_fn else render_frame(ctx, dims, ws, bs, height, width, normalized_K, np.asarray(pose, np.float64),
+                                                            n_samples, pe_bands, near=near, far=far, path=path)
+        img = np.clip(np.asarray(img, np.float32), 0.0, 1.0)
+        if ground_truth is not None:
+            psnr.append(float(compute_psnr(img, ground_truth[i])))
+        frames.append((img * 255.0 + 0.5).astype(np.uint8))
+    frames = np.stack(frames) if frames else np.zeros((0, height, width, 3), np.uint8)
+    if out_dir is not None and len(frames):
+        import os
+        from PIL import Image
+        os.makedirs(out_dir, exist_ok=True)
+        pil = [Image.fromarray(f) for f in frames]
+        for i, im in enumerate(pil):
+            im.save(os.path.join(out_dir, "frame_%04d.png" % i))
+        pil[0].save(os.path.join(out_dir, "orbit.gif"), save_all=True, append_images=pil[1:], duration=max(1, int(1000 / fps)), loop=0)
+    return frames, psnr

@@ -58,3 +58,30 @@ def test_blender_scene_reader_follows_the_reference_conventions(tmp_path):
     assert np.isclose(s["focal_length"], 0.5 / np.tan(0.5 * 0.6911))      # dataloader.py:54
     assert np.array_equal(s["pose"][:3, 3], [1, 0, 4.0])
     assert np.isclose(sc.normalized_K[0, 0], s["focal_length"]) and sc.normalized_K[0, 2] == 0.5
+
+
+def test_pose_spherical_is_a_rigid_camera_looking_at_the_origin():
+    from loma_nerf_b200 import render
+    for th, ph, r in [(0.0, -30.0, 4.0), (123.0, -10.0, 2.5), (-77.0, -60.0, 6.0)]:
+        c2w = render.pose_spherical(th, ph, r)
+        R, T = c2w[:3, :3], c2w[:3, 3]
+        assert np.allclose(R.T @ R, np.eye(3), atol=1e-12) and np.isclose(np.linalg.det(R), 1.0)
+        assert np.isclose(np.linalg.norm(T), r)
+        view = R @ np.array([0.0, 0.0, -1.0])                 # get_rays looks down -z
+        assert np.allclose(view, -T / r, atol=1e-12)          # ... straight at the origin
+
+
+def test_render_video_writes_frames_gif_and_psnr(tmp_path):
+    from PIL import Image
+    from loma_nerf_b200 import render
+    H = 12
+    gt = [np.full((H, H, 3), 0.25 * (i + 1), np.float32) for i in range(3)]
+    poses = [render.pose_spherical(40.0 * i, -30.0, 4.0) for i in range(3)]
+    frames, psnr = render.render_video(None, None, None, None, H, H, None, poses, 8, 5, out_dir=str(tmp_path), ground_truth=gt,
+                                       frame_fn=lambda i, pose: gt[i] + (0.1 if i == 1 else 0.0))
+    assert frames.shape == (3, H, H, 3) and frames.dtype == np.uint8
+    assert np.isinf(psnr[0]) and np.isclose(psnr[1], 20.0, atol=1e-4) and np.isinf(psnr[2])
+    for i in range(3):
+        assert np.array(Image.open(tmp_path / ("frame_%04d.png" % i))).shape == (H, H, 3)
+    gif = Image.open(tmp_path / "orbit.gif")
+    assert getattr(gif, "n_frames", 1) == 3
