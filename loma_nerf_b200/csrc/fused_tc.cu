@@ -184,15 +184,20 @@ struct TcLayout {
     // TMEM columns: [0,HP) the layer output / dH region (drained by its epilogue before the next
     // MMA is issued), [HP, HP + ndw) the concatenated dW accumulator (see issue of the dW stage)
     __host__ __device__ static int ndw(int L) { return (L - 1) * HP + 16; }
-    __host__ __device__ static uint32_t tmem_cols(int L)
+    // forward only (render): no adjoint buffers, no dW accumulator -> more CTAs per SM
+    __host__ __device__ static uint32_t tmem_cols(int L, bool grad = true)
     {
-        const int need = HP + ndw(L);
+        const int need = grad ? HP + ndw(L) : HP;
         return need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512)));
     }
     static constexpr int MAX_STAGES = 2 * MAXL + 1; // records of the per-CTA MMA program
     __host__ __device__ static int a_off(int l, int K0P) { return l == 0 ? 0 : (K0P / 8 + (l - 1) * HSL) * SLAB; }
     __host__ __device__ static int dz_off(int l, int L, int K0P) { return (K0P / 8 + (L - 1) * HSL + l * HSL) * SLAB; }
-    __host__ __device__ static int act_bytes(int L, int K0P) { return (K0P / 8 + 2 * (L - 1) * HSL + 2) * SLAB; }
+    // forward only: the A buffers plus two slabs where dZ_0 would start (the per-ray colour / target scratch lives there)
+    __host__ __device__ static int act_bytes(int L, int K0P, bool grad = true)
+    {
+        return grad ? (K0P / 8 + 2 * (L - 1) * HSL + 2) * SLAB : (K0P / 8 + (L - 1) * HSL + 2) * SLAB;
+    }
     __host__ __device__ static int np(int l, int L) { return l < L - 1 ? HP : 16; }
     __host__ __device__ static int kp(int l, int K0P) { return l == 0 ? K0P : HP; }
     __host__ __device__ static int w_off(int l, int L, int K0P)
@@ -206,16 +211,12 @@ struct TcLayout {
     __host__ __device__ static int wimg_bytes(int L, int K0P) { return w_off(L, L, K0P) + MAXL * HP * 4; }
     __host__ __device__ static int stage_bytes(int c_in, int K0P) { return (TILE * c_in * 4 + 32 + K0P * 4 + 15) / 16 * 16; }
     static constexpr int SCRATCH_FLOATS = 48; // colour + target per ray, scan carries, loss
-    __host__ __device__ static size_t total(int L, int K0P, int c_in, bool rays = false)
+    __host__ __device__ static size_t total(int L, int K0P, int c_in, bool rays = false, bool grad = true)
     {
-        if (rays) {
-            const size_t t = (size_t)act_bytes(L, K0P) + wimg_bytes(L, K0P) + SCRATCH_FLOATS * 4 + 64 + MAX_STAGES * 48;
-            return t < 16 * SLAB ? 16 * SLAB : t;
-        }
         // the concatenated dW MMA reads 16 slabs (M = 128 features) from the start of shared
         // memory whatever the real feature count: keep that inside the allocation
-        const size_t t = (size_t)act_bytes(L, K0P) + wimg_bytes(L, K0P) + stage_bytes(c_in, K0P) + SCRATCH_FLOATS * 4 + 64 + MAX_STAGES * 48;
-        return t < 16 * SLAB ? 16 * SLAB : t;
+        const size_t t = (size_t)act_bytes(L, K0P, grad) + wimg_bytes(L, K0P) + (rays ? 0 : stage_bytes(c_in, K0P)) + SCRATCH_FLOATS * 4 + 64 + MAX_STAGES * 48;
+        return (grad && t < 16 * SLAB) ? 16 * SLAB : t;
     }
 };
 
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
 #endif
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = p.L, K0P = p.K0P, c_in = p.dims[0], S = p.S;
-    const int act_bytes = LY::act_bytes(L, K0P);
+    const int act_bytes = LY::act_bytes(L, K0P, p.want_grad != 0);
     uint8_t *const Wbase = smem + act_bytes;
     const float *const bias_s = reinterpret_cast<const float *>(Wbase + LY::w_off(L, L, K0P));
     float *const stage = reinterpret_cast<float *>(Wbase + LY::wimg_bytes(L, K0P));
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
                                    instr_desc(128, LY::ndw(L), 1, 1), (uint32_t)HP, (uint32_t)(TILE / 16), 2u, 0u, 0u};
         }
     }
-    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), LY::tmem_cols(L));
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), LY::tmem_cols(L, p.want_grad != 0));
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -730,7 +731,7 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, LY::tmem_cols(L));
+    if (warp == 0) tmem_dealloc(tmem, LY::tmem_cols(L, p.want_grad != 0));
 #ifdef LNB_TC_CLK
     clk_acc[13] += clock64() - clk_t; // (issue dW slot reused: epilogue after the last tile)
     unsigned long long gt_end;
@@ -1029,8 +1030,9 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     p.part_stride = off;
 
     const int c_in = mlp->dims[0];
-    size_t smem = (HP == 16 ? TcLayout<16>::total(L, K0P, c_in, rays) : (HP == 32 ? TcLayout<32>::total(L, K0P, c_in, rays) : TcLayout<64>::total(L, K0P, c_in, rays)));
-    const int tmem_cols = (int)(HP == 16 ? TcLayout<16>::tmem_cols(L) : (HP == 32 ? TcLayout<32>::tmem_cols(L) : TcLayout<64>::tmem_cols(L)));
+    const bool grad = a->want_grad != 0;
+    size_t smem = (HP == 16 ? TcLayout<16>::total(L, K0P, c_in, rays, grad) : (HP == 32 ? TcLayout<32>::total(L, K0P, c_in, rays, grad) : TcLayout<64>::total(L, K0P, c_in, rays, grad)));
+    const int tmem_cols = (int)(HP == 16 ? TcLayout<16>::tmem_cols(L, grad) : (HP == 32 ? TcLayout<32>::tmem_cols(L, grad) : TcLayout<64>::tmem_cols(L, grad)));
     if (K0P / 8 + (L - 1) * (HP / 8) > 16) return unsupported("input + hidden widths exceed 128 features in total");
     if ((L - 1) * HP + 16 > 256) return unsupported("hidden widths exceed 256 gradient columns");
     if (!rays && (reinterpret_cast<uintptr_t>(a->X) & 3) != 0) return unsupported("X must be 4-byte aligned");
