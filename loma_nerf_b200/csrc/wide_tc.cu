@@ -374,9 +374,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 __device__ unsigned long long g_wide_clk[8];
 #define WCLK_T0() const long long _t0 = clock64()
 #define WCLK_ADD(i) atomicAdd(&g_wide_clk[i], (unsigned long long)(clock64() - _t0))
+// timing experiments of the debug build only (results are invalid): LNB_WIDE_L2_HINTS bit 3 = no staging / stores,
+// bit 4 = no epilogue body
+#define WIDE_DEBUG_SKIP(bit) ((p.l2_hints & (bit)) != 0)
 #else
 #define WCLK_T0()
 #define WCLK_ADD(i)
+#define WIDE_DEBUG_SKIP(bit) false
 #endif
 constexpr int CHAIN_MAX_G = 8;
 constexpr int CHAIN_THREADS = 576;   // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue: the epilogue is the long pole of the chain
@@ -615,14 +619,14 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                                 reinterpret_cast<float4 *>(Ly.head_out)[row] = o;
                             }
                         }
-                    } else if (c0 < N && !(p.l2_hints & 16)) {
+                    } else if (c0 < N && !WIDE_DEBUG_SKIP(16)) {
                         uint32_t words[2] = {0u, 0u};
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             uint32_t v[32];
                             tmem_ld32(tbase + c0 + h * 32, v);
                             tmem_ld_wait();
-                            if (p.l2_hints & 8) { if (v[0] == 0x7fc12345u) words[0] = v[1]; continue; }   // timing experiment: drain only
+                            if (WIDE_DEBUG_SKIP(8)) { if (v[0] == 0x7fc12345u) words[0] = v[1]; continue; }   // timing experiment: drain only
                             tma_store_wait_read0();          // this warp's previous store has left the box
                             __syncwarp();
                             const uint32_t wsel = h == 0 ? mw.x : mw.y;
