@@ -17,7 +17,8 @@
  *
  * No torch types, no C++ types: plain pointers, ints, floats and POD structs.
  * There is NO CPU fallback: every entry point fails (status != 0 / NaN loss) without a CUDA
- * device.  All arithmetic is IEEE fp32 unless a *_tc entry point says otherwise.
+ * device.  All arithmetic is IEEE fp32 unless lnb_step_args.path selects the tensor cores
+ * (LNB_PATH_TC: bf16 operands, fp32 accumulation).
  */
 #ifndef LOMA_NERF_B200_H
 #define LOMA_NERF_B200_H

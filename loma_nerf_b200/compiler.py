@@ -6,18 +6,31 @@ The reference hosts do (train_nerf.py:209-213, fit_img.py:355-361)
     nerf_evaluate_and_march = lib.nerf_evaluate_and_march
     grad_nerf_evaluate_and_march = lib.grad_nerf_evaluate_and_march
 
-and every run regenerates and overwrites the `.so`.  Putting this package's directory first on
-`sys.path` (or `import loma_nerf_b200.compiler as compiler`) makes that call return
+and every run regenerates and overwrites the `.so`.  The hosts find the module as a TOP-LEVEL
+`compiler` (they append loma_public/ to sys.path and `import compiler`, train_nerf.py:4-12,
+fit_img.py:4-9), so this file works both ways: as `loma_nerf_b200.compiler` and as a plain
+`compiler` module found through PYTHONPATH=<repo>/loma_nerf_b200/dropin (a directory holding only
+a re-export of this file) or PYTHONPATH=<repo>/loma_nerf_b200.  Either way `compile()` returns
 `({}, libloma_nerf_b200.so)` with the same argtypes / restype that
 /root/reference/loma_public/compiler.py:262-276 would have set, so the hosts run unmodified on the
 GPU.  Nothing is compiled from the loma source: only the program's function names are looked at, to
 refuse programs this library does not implement.
 """
 import ctypes
+import os
 import re
+import sys
 from ctypes import POINTER, c_float, c_int
 
-from . import _lib
+if __package__:
+    from . import _lib
+else:
+    # imported as a top-level module (`import compiler` with this directory on sys.path): make the
+    # package importable by its real name and use its loader, so there is one library handle
+    _repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if _repo not in sys.path:
+        sys.path.append(_repo)
+    from loma_nerf_b200 import _lib
 
 c_float_p = POINTER(c_float)
 c_float_pp = POINTER(c_float_p)
