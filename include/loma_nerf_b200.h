@@ -266,7 +266,12 @@ LNB_API float *lnb_trainer_params(lnb_trainer *t, long long *n_w, long long *n_b
  * buffer, the host exchanges the handles (any transport), every rank attaches all `world` handles
  * (rank-major, 64 bytes each).  From then on lnb_trainer_step[_host] sums the gradients (and the
  * loss) of all ranks over NVLink inside its second kernel -- no separate collective -- and all ranks
- * must step in lockstep.  lnb_trainer_comm_status: 0 fine, 1 a peer never showed up. */
+ * must step in lockstep; with LNB_SEED_LOSS the gradient is (sum of losses) x (sum of unit-seed
+ * gradients), the reference's gradient of the whole batch.  Steps that cannot exchange in-kernel
+ * (fp32 path, wide MLPs, S > 128) return LNB_ERR_UNSUPPORTED instead of updating from local
+ * gradients.  A peer that stays silent for LNB_PEER_TIMEOUT_MS (default 5000) poisons that step:
+ * gradients, parameters and the returned loss become NaN, lnb_trainer_step_host / lnb_trainer_read
+ * return LNB_ERR_CUDA and lnb_trainer_comm_status returns 1 (0 = fine). */
 LNB_API int lnb_trainer_comm_export(lnb_trainer *t, void *handle64);
 LNB_API int lnb_trainer_comm_attach(lnb_trainer *t, int rank, int world, const void *handles);
 LNB_API int lnb_trainer_comm_status(lnb_trainer *t);

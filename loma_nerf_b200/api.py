@@ -57,7 +57,14 @@ def _ptr(x):
 
 
 class Context:
-    """One lnb_ctx: a device, a stream and a grow-only workspace."""
+    """One lnb_ctx: a device, a stream and a grow-only workspace.
+
+    Stream rule: the library launches on ONE stream per context.  With torch importable that stream
+    defaults to torch's current stream of the device at construction time, so torch-side work on the
+    tensors passed in (zero fills, NCCL collectives, allocator reuse) is ordered with the library's
+    kernels without further ado.  `set_stream` moves it; buffers this class allocates are then
+    filled on that stream, and caller tensors are recorded on it (`Tensor.record_stream`) so the
+    caching allocator does not hand their memory out while a kernel still reads it."""
 
     def __init__(self, device=None, stream=None):
         self.lib = L.load()
@@ -71,8 +78,11 @@ class Context:
         if rc != L.LNB_OK:
             raise LnbError("lnb_create failed (%d)" % rc)
         self.h = h
+        self._stream_raw = None          # None: the context's own non-blocking stream
         if stream is not None:
             self.set_stream(stream)
+        elif torch is not None and torch.cuda.is_available():
+            self.use_current_torch_stream()
 
     def close(self):
         if getattr(self, "h", None):
@@ -90,6 +100,50 @@ class Context:
         None (the context's own non-blocking stream)."""
         raw = ctypes.c_void_p(-1) if stream is None else ctypes.c_void_p(getattr(stream, "cuda_stream", stream))
         self._check(self.lib.lnb_set_stream(self.h, raw))
+        self._stream_raw = None if stream is None else int(getattr(stream, "cuda_stream", stream))
+
+    def torch_stream(self):
+        """The context's stream as a torch stream object (for events / wait_stream), or None when the
+        context runs on its own private stream (which torch cannot see: synchronize() orders it)."""
+        if torch is None or self._stream_raw is None:
+            return None
+        cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream == self._stream_raw:
+            return cur
+        return torch.cuda.ExternalStream(self._stream_raw, device=torch.device("cuda", self.device))
+
+    def _on_torch_current(self):
+        return torch is not None and self._stream_raw is not None and \
+            torch.cuda.current_stream(self.device).cuda_stream == self._stream_raw
+
+    def order_after_torch(self):
+        """Make the context's stream wait for everything queued on torch's current stream so far."""
+        if torch is None or self._on_torch_current():
+            return
+        ts = self.torch_stream()
+        if ts is None:                      # private stream: the only ordering tool is the host
+            torch.cuda.current_stream(self.device).synchronize()
+        else:
+            ts.wait_stream(torch.cuda.current_stream(self.device))
+
+    def order_torch_after(self):
+        """Make torch's current stream wait for everything the context has launched so far."""
+        if torch is None or self._on_torch_current():
+            return
+        ts = self.torch_stream()
+        if ts is None:
+            self.synchronize()
+        else:
+            torch.cuda.current_stream(self.device).wait_stream(ts)
+
+    def _hold(self, *tensors):
+        """Caller tensors read by kernels on a stream that is not torch's current one."""
+        if torch is None or self._on_torch_current():
+            return
+        ts = self.torch_stream()
+        for x in tensors:
+            if ts is not None and _is_cuda(x):
+                x.record_stream(ts)
 
     def use_current_torch_stream(self):
         self.set_stream(torch.cuda.current_stream(self.device))
@@ -175,6 +229,10 @@ class Context:
             setattr(a, k, _ptr(buf))
         fn = {(True, True): self.lib.lnb_nerf_step, (True, False): self.lib.lnb_nerf_step_host,
               (False, True): self.lib.lnb_fit_step, (False, False): self.lib.lnb_fit_step_host}[(nerf, dev)]
+        if dev:
+            # the zero fills above and whatever produced the inputs ran on torch's current stream
+            self.order_after_torch()
+            self._hold(X, ws, bs, target, dists, *(rays or ()), *res.values())
         self._check(fn(self.h, ctypes.byref(mlp), ctypes.byref(a)))
         return res
 
@@ -297,9 +355,14 @@ class Trainer:
             a.seed_mode, a.seed = L.SEED_VALUE, float(seed)
         return a, int(nerf)
 
+    def _order(self, batch):
+        self.ctx.order_after_torch()
+        self.ctx._hold(*[v for v in batch.values() if _is_cuda(v)], *[x for x in (batch.get("rays") or ()) if _is_cuda(x)])
+
     def step(self, **batch):
         """forward + backward + optimiser update on one batch."""
         a, nerf = self._batch(**batch)
+        self._order(batch)
         self.ctx._check(self.lib.lnb_trainer_step(self.h, ctypes.byref(a), nerf))
 
     def step_host(self, **batch):
@@ -313,6 +376,7 @@ class Trainer:
     def grad(self, **batch):
         """forward + backward only: gradients (and loss) land in grad_buffer()."""
         a, nerf = self._batch(**batch)
+        self._order(batch)
         self.ctx._check(self.lib.lnb_trainer_grad(self.h, ctypes.byref(a), nerf))
 
     def apply(self):
@@ -335,10 +399,17 @@ class Trainer:
         return True
 
     def comm_status(self):
+        """0 = fine, 1 = a peer timed out and that step was poisoned with NaN.  Synchronises."""
         return int(self.lib.lnb_trainer_comm_status(self.h))
 
+    def check_comm(self):
+        if self.comm_status() != 0:
+            raise LnbError("peer all-reduce: a rank did not deliver its gradients in time; the step was poisoned (NaN)")
+
     def grad_buffer(self):
-        """torch view of the flat [d_ws | d_bs | loss] device buffer (for dist.all_reduce)."""
+        """torch view of the flat [d_ws | d_bs | loss] device buffer (for dist.all_reduce).  The
+        library writes it on the context's stream: use ctx.order_torch_after() before torch reads it
+        and ctx.order_after_torch() before apply() (sharding.data_parallel_step does both)."""
         n = ctypes.c_longlong()
         ptr = self.lib.lnb_trainer_grad_buffer(self.h, ctypes.byref(n))
         return _torch_view(ptr, n.value, self.ctx.device)

@@ -853,31 +853,48 @@ __global__ void __launch_bounds__(1024) tc_reduce_kernel(const float *__restrict
         // step tag matches -- no fences, no separate flags, one NVLink traversal.  Slots are double-
         // buffered by step parity; ranks cannot drift more than one step apart (each needs every
         // peer's words of step s to finish step s).
+        // The words carry UNIT-seed gradients; with seed = loss (train_nerf.py:477) the reference's
+        // gradient of the whole batch is (sum of the ranks' losses) x (sum of the ranks' unit-seed
+        // gradients), so every block also collects the ranks' losses and scales afterwards.
+        // A peer that does not show up within LNB_PEER_TIMEOUT_NS of %globaltimer POISONS the step:
+        // the element (and through it the parameter) becomes NaN and the sticky status word is set,
+        // which lnb_trainer_step_host / lnb_trainer_read / lnb_trainer_comm_status report as an error.
+        __shared__ float s_loss_all;
         const unsigned step = (unsigned)ad.t_dev[0], par = step & 1u;
         const bool mine = grp == 0 && e_glob < n_el;
-        const bool loss_thread = blockIdx.x == 0 && threadIdx.x == 32;
+        const bool loss_thread = threadIdx.x == 32;        // every block reads the losses; block 0 publishes
         if (mine || loss_thread) {
             const int slot = mine ? e_glob : n_el;
-            const float val = mine ? g_local : sloss;
+            const float val = mine ? (seed_is_loss ? seed_value * s : g_local) : sloss;
             const unsigned long long word = ((unsigned long long)step << 32) | (unsigned long long)__float_as_uint(val);
             const size_t off = ((size_t)par * cm.world + cm.rank) * cm.n_slot + slot;
-            for (int r = 0; r < cm.world; ++r)
-                if (r != cm.rank) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(cm.peer_recv[r] + off), "l"(word) : "memory");
+            if (mine || blockIdx.x == 0)
+                for (int r = 0; r < cm.world; ++r)
+                    if (r != cm.rank) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(cm.peer_recv[r] + off), "l"(word) : "memory");
             float tot = 0.0f;
+            unsigned long long t0 = 0;
             for (int r = 0; r < cm.world; ++r) {
                 if (r == cm.rank) { tot += val; continue; }
                 const unsigned long long *src = cm.my_recv + ((size_t)par * cm.world + r) * cm.n_slot + slot;
                 unsigned long long w;
-                unsigned spins = 0;
-                for (;;) {
+                for (unsigned spins = 0;; ++spins) {
                     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
                     if ((unsigned)(w >> 32) == step) break;
-                    if (++spins > (1u << 24)) { *cm.status = 1; break; } // a lost peer must not hang the GPU
+                    if ((spins & 1023u) == 1023u) {       // a lost peer must not hang the GPU
+                        unsigned long long now;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        if (t0 == 0) t0 = now;
+                        else if (now - t0 > cm.timeout_ns) { *cm.status = 1; w = 0x7FC00000ull; break; }
+                    }
                 }
                 tot += __uint_as_float((unsigned)w);
             }
             if (mine) g_local = tot;
-            else { loss_total = tot; if (loss) loss[0] = tot; }
+            else { loss_total = tot; s_loss_all = tot; if (blockIdx.x == 0 && loss) loss[0] = tot; }
+        }
+        if (seed_is_loss) {
+            __syncthreads();
+            g_local *= s_loss_all;
         }
     }
     (void)loss_total;
@@ -1009,7 +1026,7 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     if (!nerf && N != R) return unsupported("needs n_rows == R");
     if (a->rows > N) return unsupported("rows > n_rows");
     if (!nerf && (a->target_w > 4)) return unsupported("target wider than 4");
-    if (a->want_grad && !a->target) return unsupported("gradient without target");
+    if (a->want_grad && !a->target && N > 0) return unsupported("gradient without target");
     if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
 
     TcParams p{};
@@ -1095,6 +1112,7 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
         LNB_CHECK_LAUNCH();
     } else {
         grid = 0;
+        if (p.t_dev) LNB_TRY(lnb_launch_incr(ctx, p.t_dev)); // an empty shard still takes the step (and publishes zeros)
     }
 #ifdef LNB_TC_CLK
     {
@@ -1138,7 +1156,7 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
         cudaLaunchConfig_t rc{};
         rc.gridDim = dim3((unsigned)blocks); rc.blockDim = dim3(1024); rc.dynamicSmemBytes = 0; rc.stream = ctx->stream;
         rc.attrs = pdl_attr; rc.numAttrs = use_pdl ? 1 : 0;
-        const lnb_tc_comm comm_arg = (ex && ex->comm && fuse && !seed_is_loss) ? *ex->comm : lnb_tc_comm{};
+        const lnb_tc_comm comm_arg = (ex && ex->comm && fuse) ? *ex->comm : lnb_tc_comm{};
         LNB_CUDA(cudaLaunchKernelEx(&rc, tc_reduce_kernel, (const float *)p.part, grid, p.part_stride, p,
                                     a->want_grad ? a->d_ws : (float *)nullptr, a->want_grad ? a->d_bs : (float *)nullptr, loss,
                                     seed_val, seed_is_loss, ex ? ex->overwrite_grads : 0, fuse, ad, im, comm_arg));

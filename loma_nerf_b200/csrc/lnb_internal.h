@@ -152,7 +152,8 @@ struct lnb_tc_comm {
     int n_slot = 0;                          // gradient elements + 1 (the loss)
     unsigned long long *my_recv = nullptr;   // [2 parities][world senders][n_slot] {step<<32 | float bits}
     unsigned long long *peer_recv[8] = {};   // the same array on every rank (peer-mapped; [rank] = own)
-    int *status = nullptr;                   // local: 1 after a spin timeout
+    int *status = nullptr;                   // local, sticky: 1 after a peer timed out (that step is poisoned with NaN)
+    unsigned long long timeout_ns = 5000000000ull; // LNB_PEER_TIMEOUT_MS
 };
 
 struct lnb_tc_extra {

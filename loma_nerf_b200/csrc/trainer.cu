@@ -7,6 +7,7 @@
 //     fused forward+backward kernel  ->  reduce partials + optimiser update + weight-image refresh
 // For multi-GPU data parallelism the step splits at the gradient buffer:
 //     lnb_trainer_grad -> (caller: NCCL all-reduce of lnb_trainer_grad_buffer) -> lnb_trainer_apply
+#include <stdlib.h>
 #include <string.h>
 
 #include "lnb_internal.h"
@@ -87,6 +88,15 @@ extern "C" void lnb_trainer_destroy(lnb_trainer *t)
     delete t;
 }
 
+// a peer never delivered its gradients: the step that noticed has poisoned the parameters with NaN
+static int comm_failed(lnb_trainer *t, float *loss_out)
+{
+    t->ctx->err = "trainer: a peer rank did not deliver its gradients in time; the step was poisoned (NaN) instead of "
+                  "applying a partial sum -- the replicas of this run are no longer usable";
+    if (loss_out) *loss_out = __builtin_nanf("");
+    return LNB_ERR_CUDA;
+}
+
 static int trainer_run(lnb_trainer *t, const lnb_step_args *batch, int nerf, bool fuse_update)
 {
     lnb_ctx *ctx = t->ctx;
@@ -106,12 +116,20 @@ static int trainer_run(lnb_trainer *t, const lnb_step_args *batch, int nerf, boo
             ex.fuse_adam = 1; ex.param = t->params; ex.m = t->opt == LNB_OPT_ADAM ? t->m : nullptr; ex.v = t->v;
             ex.lr = t->lr; ex.b1 = t->b1; ex.b2 = t->b2; ex.eps = t->eps; ex.wimg_out = t->wimg;
         }
-        LNB_TRY(lnb_step_ex(ctx, &t->mlp, &a, nerf != 0, &ex));
-        t->t_bumped = !fuse_update;
-        return LNB_OK;
+        const int rc = lnb_step_ex(ctx, &t->mlp, &a, nerf != 0, &ex);
+        if (rc == LNB_OK) { t->t_bumped = !fuse_update; return LNB_OK; }
+        // the MLP fits the fused kernel but this batch does not (e.g. S > 128): the layerwise
+        // tensor-core kernels below take it, exactly as lnb_nerf_step would
+        if (rc != LNB_ERR_UNSUPPORTED) return rc;
     }
-    // exact fp32 path, or a wide MLP on the layerwise tensor-core path: zero the gradient buffer
-    // (those kernels accumulate), step, optional update
+    // exact fp32 path, or the layerwise tensor-core path: zero the gradient buffer (those kernels
+    // accumulate), step, optional update.  These steps have no fused exchange: with a peer group
+    // attached they would update from local gradients only and the replicas would drift apart.
+    if (fuse_update && t->comm.world > 1) {
+        ctx->err = "trainer: the peer all-reduce is attached but this step (fp32 path, wide MLP or S > 128) cannot "
+                   "exchange gradients in-kernel; use lnb_trainer_grad + an all-reduce of lnb_trainer_grad_buffer + lnb_trainer_apply";
+        return LNB_ERR_UNSUPPORTED;
+    }
     LNB_CUDA(cudaMemsetAsync(t->grads, 0, (size_t)(t->n_w + t->n_b + 1) * 4, ctx->stream));
     LNB_TRY(nerf ? lnb_nerf_step(ctx, &t->mlp, &a) : lnb_fit_step(ctx, &t->mlp, &a));
     t->t_bumped = false;
@@ -212,8 +230,10 @@ extern "C" int lnb_trainer_step_host(lnb_trainer *t, const lnb_step_args *batch,
     float *pl = (float *)lnb_pinned_take(ctx, 16);
     if (!pl) { LNB_TRY(lnb_pinned_reserve(ctx, 4096)); pl = (float *)lnb_pinned_take(ctx, 16); }
     LNB_CUDA(cudaMemcpyAsync(pl, t->grads + t->n_w + t->n_b, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (t->comm.world > 1) LNB_CUDA(cudaMemcpyAsync(pl + 1, t->comm.status, 4, cudaMemcpyDeviceToHost, ctx->stream));
     LNB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (loss_out) *loss_out = *pl;
+    if (t->comm.world > 1 && *reinterpret_cast<const int *>(pl + 1) != 0) return comm_failed(t, loss_out);
     return LNB_OK;
 }
 
@@ -246,6 +266,7 @@ extern "C" int lnb_trainer_comm_attach(lnb_trainer *t, int rank, int world, cons
     const int n_slot = comm_slots(t);
     lnb_tc_comm c{};
     c.world = world; c.rank = rank; c.n_slot = n_slot;
+    if (const char *e = getenv("LNB_PEER_TIMEOUT_MS")) { const long long ms = atoll(e); if (ms > 0) c.timeout_ns = (unsigned long long)ms * 1000000ull; }
     c.status = reinterpret_cast<int *>(t->comm_buf);
     c.my_recv = reinterpret_cast<unsigned long long *>(t->comm_buf + 256);
     for (int r = 0; r < world; ++r) {
@@ -264,7 +285,7 @@ extern "C" int lnb_trainer_comm_attach(lnb_trainer *t, int rank, int world, cons
     return LNB_OK;
 }
 
-// 0 = fine; 1 = a peer's flag never arrived (the step went on with what it had). Synchronises.
+// 0 = fine; 1 = a peer's words never arrived and that step was poisoned with NaN. Synchronises.
 extern "C" int lnb_trainer_comm_status(lnb_trainer *t)
 {
     if (!t || !t->comm_buf) return 0;
@@ -298,6 +319,9 @@ extern "C" int lnb_trainer_read(lnb_trainer *t, float *ws_host, float *bs_host, 
     if (ws_host) LNB_CUDA(cudaMemcpyAsync(ws_host, t->params, (size_t)t->n_w * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (bs_host) LNB_CUDA(cudaMemcpyAsync(bs_host, t->params + t->n_w, (size_t)t->n_b * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (loss_host) LNB_CUDA(cudaMemcpyAsync(loss_host, t->grads + t->n_w + t->n_b, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    int st = 0;
+    if (t->comm.world > 1) LNB_CUDA(cudaMemcpyAsync(&st, t->comm.status, 4, cudaMemcpyDeviceToHost, ctx->stream));
     LNB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (st != 0) return comm_failed(t, loss_host);
     return LNB_OK;
 }

@@ -68,5 +68,7 @@ def allreduce_gradients(flat, group=None):
 def data_parallel_step(trainer, batch, group=None):
     """One data-parallel train step on this rank's shard: gradients, all-reduce, optimiser."""
     trainer.grad(**batch)
+    trainer.ctx.order_torch_after()       # the collective runs behind torch's current stream
     allreduce_gradients(trainer.grad_buffer(), group)
+    trainer.ctx.order_after_torch()       # ... and the optimiser behind the collective
     trainer.apply()

@@ -39,6 +39,37 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
+def l2_err(a, b):
+    """||a-b||_2 / ||b||_2 -- insensitive to where the largest entry sits."""
+    a = np.asarray(a, np.float64).ravel()
+    b = np.asarray(b, np.float64).ravel()
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def per_layer_err(a, b):
+    """max over the leading (layer) axis of max|a_l - b_l| / max|b_l|: a small layer's gradient cannot
+    hide behind a large one's (layers whose reference gradient is identically zero are skipped)."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    worst = 0.0
+    for l in range(b.shape[0]):
+        m = np.abs(b[l]).max()
+        if m > 0:
+            worst = max(worst, float(np.abs(a[l] - b[l]).max() / m))
+    return worst
+
+
+def grad_errs(o, ref, suffix=""):
+    """Every metric the tensor-core bounds are stated in, for d_ws / d_bs."""
+    out = {}
+    for k in ("d_ws", "d_bs"):
+        r = ref[k + suffix]
+        out[k] = rel_err(o[k], r)
+        out[k + "_layer"] = per_layer_err(o[k], r)
+        out[k + "_l2"] = l2_err(o[k], r)
+    return out
+
+
 @pytest.fixture(scope="session")
 def c_oracle():
     from oracle import oracle as O

@@ -6,11 +6,23 @@ import os
 import numpy as np
 import pytest
 
-from conftest import golden_files, load_golden, rel_err
+from conftest import golden_files, grad_errs, load_golden, rel_err
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
 TC_TOL = 3e-2     # bf16 operands: 2^-9 relative per element; measured errors are logged below
+# The gradient bounds are stated three ways (DESIGN.md 2.2 "Numerics"): norm-wise over the whole padded array
+# (TC_TOL), PER LAYER (max|a_l-b_l| / max|b_l|: a small layer cannot hide behind a large one) and in L2.
+TC_LAYER_TOL = 4e-2
+TC_L2_TOL = 2e-2
+
+
+def check_grads(errs):
+    assert max(errs["d_ws"], errs["d_bs"]) <= TC_TOL, errs
+    assert max(errs["d_ws_layer"], errs["d_bs_layer"]) <= TC_LAYER_TOL, errs
+    assert max(errs["d_ws_l2"], errs["d_bs_l2"]) <= TC_L2_TOL, errs
+
+
 NERF_GOLDEN = [p for p in golden_files("nerf_") if "c5" not in p and "s192" not in p]
 FIT_GOLDEN = golden_files("fit_")
 
@@ -57,10 +69,10 @@ def run_tc(ctx, torch, case, seed, grad=True, outputs=("color", "loss")):
 def test_tc_nerf_against_reference_golden(ctx, torch_cuda, gpath):
     gd = load_golden(gpath)
     o = run_tc(ctx, torch_cuda, gd, "loss")
-    errs = dict(loss=rel_err(o["loss"][0], gd["loss"]), color=rel_err(o["color"], gd["color"]),
-                d_ws=rel_err(o["d_ws"], gd["d_ws"]), d_bs=rel_err(o["d_bs"], gd["d_bs"]))
+    errs = dict(loss=rel_err(o["loss"][0], gd["loss"]), color=rel_err(o["color"], gd["color"]), **grad_errs(o, gd))
     log("%s %s" % (os.path.basename(gpath), errs))
-    assert max(errs.values()) <= TC_TOL, errs
+    assert max(errs["loss"], errs["color"]) <= TC_TOL, errs
+    check_grads(errs)
 
 
 @pytest.mark.parametrize("gpath", FIT_GOLDEN, ids=os.path.basename)
@@ -71,9 +83,10 @@ def test_tc_fit_against_reference_golden(ctx, torch_cuda, gpath):
                        dev(torch, gd["target"]), grad=True, seed="loss", outputs=("loss",), path="tc")
     ctx.synchronize()
     o = {k: host(v) for k, v in out.items()}
-    errs = dict(loss=rel_err(o["loss"][0], gd["loss"]), d_ws=rel_err(o["d_ws"], gd["d_ws"]), d_bs=rel_err(o["d_bs"], gd["d_bs"]))
+    errs = dict(loss=rel_err(o["loss"][0], gd["loss"]), **grad_errs(o, gd))
     log("%s %s" % (os.path.basename(gpath), errs))
-    assert max(errs.values()) <= TC_TOL, errs
+    assert errs["loss"] <= TC_TOL, errs
+    check_grads(errs)
 
 
 @pytest.mark.parametrize("R,S", [(4096, 64), (1000, 30), (257, 128), (64, 32), (700, 7)])
@@ -81,10 +94,10 @@ def test_tc_full_batches_against_f64_restatement(ctx, torch_cuda, R, S):
     case = O.make_nerf_case(500 + S, R, S)
     o = run_tc(ctx, torch_cuda, case, 1.0)
     f = O.nerf_f64(case["X"], case["ws"], case["bs"], case["dims"], case["target"], case["dists"], R, S, g=1.0)
-    errs = dict(loss=rel_err(o["loss"][0], f["loss"]), color=rel_err(o["color"], f["color"]),
-                d_ws=rel_err(o["d_ws"], f["d_ws"]), d_bs=rel_err(o["d_bs"], f["d_bs"]))
+    errs = dict(loss=rel_err(o["loss"][0], f["loss"]), color=rel_err(o["color"], f["color"]), **grad_errs(o, f))
     log("R=%d S=%d %s" % (R, S, errs))
-    assert max(errs.values()) <= TC_TOL, errs
+    assert max(errs["loss"], errs["color"]) <= TC_TOL, errs
+    check_grads(errs)
 
 
 def test_tc_render_only_and_unsupported_requests(ctx, torch_cuda):
@@ -120,10 +133,10 @@ def test_tc_rays_mode_fused_positional_encoding(ctx, torch_cuda, R, S, E, dtype)
     ctx.synchronize()
     o = {k: host(v) for k, v in out.items()}
     f = O.nerf_f64(case["X"], case["ws"], case["bs"], case["dims"], case["target"], case["dists"], R, S, g=1.0)
-    errs = dict(loss=rel_err(o["loss"][0], f["loss"]), color=rel_err(o["color"], f["color"]),
-                d_ws=rel_err(o["d_ws"], f["d_ws"]), d_bs=rel_err(o["d_bs"], f["d_bs"]))
+    errs = dict(loss=rel_err(o["loss"][0], f["loss"]), color=rel_err(o["color"], f["color"]), **grad_errs(o, f))
     log("rays %s R=%d S=%d E=%d %s" % (dtype, R, S, E, errs))
-    assert max(errs.values()) <= TC_TOL, errs
+    assert max(errs["loss"], errs["color"]) <= TC_TOL, errs
+    check_grads(errs)
 
 
 @pytest.mark.parametrize("path,tol", [("f32", 2e-5), ("tc", 5e-2)])
@@ -211,3 +224,46 @@ def test_training_on_a_synthetic_scene_improves_psnr(ctx, torch_cuda):
         after = render.compute_psnr(render.render_rays(ctx, dims, w, b, o, d, t, E, path="f32"), target)
         log("train-demo %s: loss %.2f -> %.2f, PSNR %.2f -> %.2f dB" % (path, losses[0], losses[-1], before, after))
         assert losses[-1] < 0.7 * losses[0] and after > before + 1.0, (path, losses, before, after)
+
+
+def test_context_runs_on_torchs_current_stream_by_default(torch_cuda):
+    """The library's kernels and torch's own work on the same tensors (zero fills, collectives, allocator
+    reuse) must be ordered without the caller doing anything: a new Context adopts torch's current stream."""
+    torch = torch_cuda
+    from loma_nerf_b200 import api
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        c = api.Context(0)
+        assert c._stream_raw == side.cuda_stream and c._on_torch_current()
+    assert not c._on_torch_current()          # torch moved back to its default stream, the context did not
+    # a step issued now is ordered behind torch's current stream (order_after_torch) and its inputs are
+    # recorded on the context's stream; results must not depend on the race either way
+    case = O.make_nerf_case(333, 64, 64)
+    o = run_tc(c, torch, case, 1.0)
+    c2 = api.Context(0)
+    assert c2._on_torch_current()
+    o2 = run_tc(c2, torch, case, 1.0)
+    assert np.array_equal(o["d_ws"], o2["d_ws"]) and np.array_equal(o["color"], o2["color"])
+    c.close(); c2.close()
+
+
+def test_trainer_takes_an_empty_batch_and_a_batch_the_fused_kernel_cannot(ctx, torch_cuda):
+    """(1) R = 0 (a rank whose shard is empty when R < world): the step counter still advances and nothing
+    becomes NaN.  (2) S = 192 on the 30-wide net: the MLP fits the fused kernel, the batch does not --
+    lnb_trainer_step falls through to the layerwise tensor-core kernels exactly as lnb_nerf_step does."""
+    torch = torch_cuda
+    from loma_nerf_b200 import api
+    case = O.make_nerf_case(77, 16, 192)
+    dims = [int(v) for v in case["dims"]]
+    tr = api.Trainer(ctx, dims, case["ws"], case["bs"])
+    z = lambda *shape: torch.zeros(shape, device="cuda")  # noqa: E731
+    tr.step(X=z(0, dims[0]), dists=z(0, 64), target=z(0, 3), R=0, S=64, path="tc")
+    w, b, loss = tr.read()
+    assert np.isfinite(w).all() and np.isfinite(b).all() and loss == 0.0
+    assert np.array_equal(w, case["ws"]) and np.allclose(b, case["bs"], atol=1e-6)   # zero gradient: Adam moves nothing
+    tr.step(X=dev(torch, case["X"]), dists=dev(torch, case["dists"]), target=dev(torch, case["target"]), path="tc")
+    w, b, loss = tr.read()
+    f = O.nerf_f64(case["X"], case["ws"], case["bs"], case["dims"], case["target"], case["dists"], 16, 192, g=1.0)
+    assert rel_err(loss, f["loss"]) <= TC_TOL
+    assert np.isfinite(w).all() and np.abs(w - case["ws"]).max() > 0            # the update happened (t = 2)
+    tr.close()

@@ -149,3 +149,14 @@ def test_reference_chunking_is_additive():
     assert rel_err(tot["loss"], f64["loss"]) <= 1e-5
     assert rel_err(tot["d_ws"], f64["d_ws"]) <= 1e-5
     assert rel_err(tot["d_bs"], f64["d_bs"]) <= 1e-5
+
+
+def test_f64_restatement_matches_the_eight_ray_paper_size_golden():
+    """BASELINE config 5 (63 -> 8 x 256 -> 4, S = 192) on eight rays: loss and weight gradients summed over eight
+    single-ray calls of the paper-size reference build (tests/golden/make_golden_c5_r8.py), unit seed."""
+    gd = load_golden(os.path.join(os.path.dirname(NERF_GOLDEN[0]), "wide_c5_r8_s192.npz"))
+    R, S = int(gd["R"]), int(gd["S"])
+    f = O.nerf_f64(gd["X"], gd["ws"], gd["bs"], gd["dims"], gd["target"], gd["dists"], R, S, g=1.0)
+    assert rel_err(f["loss"], gd["loss"]) <= 2e-6
+    assert rel_err(f["color"], gd["color"]) <= 2e-6
+    assert rel_err(f["d_ws"], gd["d_ws_g1"]) <= 5e-6 and rel_err(f["d_bs"], gd["d_bs_g1"]) <= 5e-6
