@@ -29,7 +29,7 @@ def sources():
 
 def _digest():
     h = hashlib.sha256()
-    files = sources() + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".h")]
+    files = sources() + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".h", ".cuh", ".inc"))]
     files += [os.path.join(INCLUDE, f) for f in sorted(os.listdir(INCLUDE))]
     for p in files:
         h.update(p.encode())

@@ -72,6 +72,7 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t done = 0;
+    unsigned long long t0 = 0;
     for (uint32_t it = 0; !done; ++it) {
         // the suspend-time hint lets the warp sleep in hardware instead of burning issue slots
         asm volatile(
@@ -79,7 +80,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(bar), "r"(parity), "r"(100000u) : "memory");
-        if (it > (1u << 22)) __trap(); // never hang the GPU: a lost arrival is a bug, fail loudly
+        if (!done && (it & 0x3FFu) == 0x3FFu) {
+            // never hang the GPU: a lost arrival is a bug, fail loudly (10 s by the global timer)
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 10000000000ull) __trap();
+        }
     }
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -137,6 +144,32 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
     return *reinterpret_cast<uint32_t *>(&h);
 }
 __device__ __forceinline__ float sigmoid_f(float z) { return __fdividef(1.0f, 1.0f + __expf(0.0f - z)); }
+// two floats -> packed bf16 pair (lo = first), with ReLU: ONE instruction (F2FP.RELU.BF16)
+__device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi)
+{
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// 0xFFFF per half where the bf16 half is > 0 (post-ReLU activations are >= 0)
+__device__ __forceinline__ uint32_t gt0_mask_bf16x2(uint32_t h)
+{
+    uint32_t r;
+    asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(h), "r"(0u));
+    return r;
+}
+
+
+// sin / cos of a sample coordinate for the positional encoding: one Cody-Waite step to [-pi, pi], then the
+// MUFU approximations (abs. error ~2^-21 there); doubled E-1 times this stays far below the bf16 operand step
+__device__ __forceinline__ void pe_sincos(float x, float *s, float *c)
+{
+    const float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(k, -6.28318548202514648f, x);
+    r = fmaf(k, 1.7484555e-7f, r);
+    __sincosf(r, s, c);
+}
+
 
 __device__ __forceinline__ float warp_incl_prod(float p, int lane)
 {
@@ -220,7 +253,13 @@ struct TcLayout {
     }
 };
 
-// fp32 padded weights -> the bf16 slab image + fp32 biases every CTA of the fused kernel copies
+// fp32 padded weights -> the bf16 slab image every CTA of the fused kernel copies.  The A operands carry an
+// all-ones feature at column in_l (it exists for the bias gradient), so row in_l of a HIDDEN layer's W holds
+// the bias b_l (the MMA adds it) and, at column out_l, a 1.0 that re-creates the ones feature in the layer's
+// output: the hidden-layer epilogue is then just ReLU + pack.  The head keeps its bias in fp32 (the image's
+// fp32 tail [MAXL][HP]; zero for hidden layers).  In the adjoint pass these extra entries only feed column
+// in_l of dH_l, which becomes the ones column of dZ_{l-1}: it meets zero weight columns and lands in
+// weight-gradient entries nobody reads.
 template <int HP>
 __global__ void tc_prep_kernel(const TcParams p, uint8_t *__restrict__ img)
 {
@@ -229,17 +268,20 @@ __global__ void tc_prep_kernel(const TcParams p, uint8_t *__restrict__ img)
     for (int l = 0; l < L; ++l) {
         const int in_l = p.dims[l], out_l = p.dims[l + 1], Np = LY::np(l, L), Kp = LY::kp(l, K0P);
         const float *wl = p.ws + (size_t)l * p.max_in * p.max_out;
+        const float *bl = p.bs + (size_t)l * p.max_out;
         __nv_bfloat16 *w = reinterpret_cast<__nv_bfloat16 *>(img + LY::w_off(l, L, K0P));
         for (int e = threadIdx.x; e < Np * Kp; e += blockDim.x) {
             const int k = e / Np, j = e % Np; // consecutive threads -> consecutive j (coalesced reads)
-            const float v = (k < in_l && j < out_l) ? __ldg(wl + (size_t)k * p.max_out + j) : 0.0f;
+            float v = 0.0f;
+            if (k < in_l && j < out_l) v = __ldg(wl + (size_t)k * p.max_out + j);
+            else if (k == in_l && l < L - 1) v = j < out_l ? __ldg(bl + j) : (j == out_l ? 1.0f : 0.0f);
             w[(k >> 3) * (Np * 8) + j * 8 + (k & 7)] = __float2bfloat16_rn(v);
         }
     }
     float *b = reinterpret_cast<float *>(img + LY::w_off(L, L, K0P));
     for (int e = threadIdx.x; e < MAXL * HP; e += blockDim.x) {
         const int l = e / HP, j = e % HP;
-        b[e] = (l < L && j < p.dims[l + 1]) ? __ldg(p.bs + (size_t)l * p.max_out + j) : 0.0f;
+        b[e] = (l == L - 1 && j < p.dims[l + 1]) ? __ldg(p.bs + (size_t)l * p.max_out + j) : 0.0f;
     }
 }
 
@@ -247,7 +289,7 @@ __global__ void tc_prep_kernel(const TcParams p, uint8_t *__restrict__ img)
 // coordinate, higher bands by angle doubling (sin 2a = 2 s c, cos 2a = 1 - 2 s^2).  The doubling
 // amplifies the base error by 2^(E-1): ~1e-6 at E = 5, far below the bf16 operand rounding.
 template <bool RAYS, int HP>
-__global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
+__global__ void __launch_bounds__(TILE) fused_v1_kernel(const TcParams p)
 {
     using LY = TcLayout<HP>;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -434,26 +476,41 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
                     for (int c = 0; c < 3; ++c) x[c] = fmaf(__ldg(d + c), tt, __ldg(o + c));
                 }
             }
-            if (dw_pending) { mbar_wait(bar_dw, dwphase); dwphase ^= 1; dw_pending = false; tc_fence_after(); }
-            CLK(12);
-            __nv_bfloat16 *a0 = reinterpret_cast<__nv_bfloat16 *>(a_buf(0));
-            auto put = [&](int f, float v) { a0[(f >> 3) * (TILE * 8) + tid * 8 + (f & 7)] = __float2bfloat16_rn(v); };
             float sn[3], cs[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                put(c, x[c]);
-                sincosf(x[c], &sn[c], &cs[c]);
-            }
-            for (int i = 0; i < p.pe_bands; ++i) {
+            for (int c = 0; c < 3; ++c) pe_sincos(x[c], &sn[c], &cs[c]);
+            if (dw_pending) { mbar_wait(bar_dw, dwphase); dwphase ^= 1; dw_pending = false; tc_fence_after(); }
+            CLK(12);
+            // feature f = 3 * slot + coord: x0 x1 | x2 s0 | s1 s2 | c0 c1 | c2 s0' | ... as bf16 pairs (pair j = features 2j, 2j+1);
+            // band i fills pairs 1+3i .. 3+3i and leaves its last cosine pending; the ones column (feature 3 + 6E, odd) closes the
+            // pending pair.  Four pairs make this row's 16 bytes of a slab, stored as soon as they are complete.
+            {
+                uint8_t *const a0 = a_buf(0);
+                const int live_slabs = (c_in + 8) >> 3;
+                uint32_t q4[4] = {pack_bf16(x[0], x[1]), 0u, 0u, 0u};
+                float pend = x[2];
+                bool closed = false;
+                auto put = [&](int j, uint32_t v) {            // j is a compile-time constant at every call site
+                    q4[j & 3] = v;
+                    if ((j & 3) == 3) { if ((j >> 2) < live_slabs) *row_ptr(a0, j >> 2) = make_uint4(q4[0], q4[1], q4[2], q4[3]); q4[0] = q4[1] = q4[2] = q4[3] = 0u; }
+                };
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    put((2 * i + 1) * 3 + c, sn[c]);
-                    put((2 * i + 2) * 3 + c, cs[c]);
-                    const float s2 = 2.0f * sn[c] * cs[c], c2 = fmaf(-2.0f * sn[c], sn[c], 1.0f);
-                    sn[c] = s2; cs[c] = c2;
+                for (int i = 0; i < 10; ++i) {
+                    const bool on = i < p.pe_bands;
+                    const bool close = !closed && !on;
+                    put(1 + 3 * i, on ? pack_bf16(pend, sn[0]) : (close ? pack_bf16(pend, 1.0f) : 0u));
+                    put(2 + 3 * i, on ? pack_bf16(sn[1], sn[2]) : 0u);
+                    put(3 + 3 * i, on ? pack_bf16(cs[0], cs[1]) : 0u);
+                    closed = closed || close;
+                    pend = cs[2];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float s2 = 2.0f * sn[c] * cs[c], c2 = fmaf(-2.0f * sn[c], sn[c], 1.0f);
+                        sn[c] = s2; cs[c] = c2;
+                    }
                 }
+                put(31, closed ? 0u : pack_bf16(pend, 1.0f));
             }
-            put(c_in, 1.0f); // the bias-gradient feature
         } else {
             // ---- features: wait for the TMA, convert this thread's row to bf16 slabs.  Columns beyond
             // c_in read the following floats of `stage` (finite: next row / zeroed slack) and meet zero
@@ -508,28 +565,21 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
             CLK(3);
             const float *bl = bias_s + l * HP;
             if (l < L - 1) {
-                const int ones_col = p.dims[l + 1];
                 uint8_t *an = a_buf(l + 1);
                 uint32_t v[HP / 16][16];
 #pragma unroll
                 for (int c16 = 0; c16 < HP / 16; ++c16) tmem_ld16(tmem + lane_base + c16 * 16, v[c16]);
                 tmem_ld_wait();
+                // the hidden layers' bias and the all-ones feature of the next layer's input came out of the MMA (see
+                // tc_prep_kernel): ReLU + round + pack is one instruction per pair
 #pragma unroll
                 for (int c16 = 0; c16 < HP / 16; ++c16) {
-                    float f[16];
+                    uint32_t o[8];
 #pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        const float4 b4 = *reinterpret_cast<const float4 *>(bl + c16 * 16 + j4 * 4);
-                        f[j4 * 4] = fmaxf(__uint_as_float(v[c16][j4 * 4]) + b4.x, 0.0f);
-                        f[j4 * 4 + 1] = fmaxf(__uint_as_float(v[c16][j4 * 4 + 1]) + b4.y, 0.0f);
-                        f[j4 * 4 + 2] = fmaxf(__uint_as_float(v[c16][j4 * 4 + 2]) + b4.z, 0.0f);
-                        f[j4 * 4 + 3] = fmaxf(__uint_as_float(v[c16][j4 * 4 + 3]) + b4.w, 0.0f);
-                    }
-                    *row_ptr(an, c16 * 2) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-                    *row_ptr(an, c16 * 2 + 1) = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
+                    for (int j = 0; j < 8; ++j) o[j] = pack_relu_bf16(__uint_as_float(v[c16][2 * j]), __uint_as_float(v[c16][2 * j + 1]));
+                    *row_ptr(an, c16 * 2) = make_uint4(o[0], o[1], o[2], o[3]);
+                    *row_ptr(an, c16 * 2 + 1) = make_uint4(o[4], o[5], o[6], o[7]);
                 }
-                __syncwarp();
-                reinterpret_cast<__nv_bfloat16 *>(an)[(ones_col >> 3) * (TILE * 8) + tid * 8 + (ones_col & 7)] = __float2bfloat16_rn(1.0f);
                 CLK(4);
                 publish_smem();
                 CLK(5);
@@ -675,7 +725,7 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int e = (c8 & 1) * 8 + 2 * j;
-                    o[j] = pack_bf16(__uint_as_float(v[c8 >> 1][e]), __uint_as_float(v[c8 >> 1][e + 1])) & __vcmpne2(hw[j], 0u);
+                    o[j] = pack_bf16(__uint_as_float(v[c8 >> 1][e]), __uint_as_float(v[c8 >> 1][e + 1])) & gt0_mask_bf16x2(hw[j]);
                 }
                 *row_ptr(dzn, c8) = make_uint4(o[0], o[1], o[2], o[3]);
             }
@@ -744,9 +794,12 @@ __global__ void __launch_bounds__(TILE) fused_tc_kernel(const TcParams p)
 #endif
 }
 
+#include "fused_pp.cuh"
+
 // image offset (bytes) of weight (l, k, j) / the fp32 bias region, mirroring tc_prep_kernel
 struct ImgMap {
     int L, HP, K0P;
+    int dims[MAXL + 1];
     __device__ int np(int l) const { return l < L - 1 ? HP : 16; }
     __device__ int kp(int l) const { return l == 0 ? K0P : HP; }
     __device__ int w_off(int l) const { int o = 0; for (int i = 0; i < l; ++i) o += np(i) * kp(i) * 2; return o; }
@@ -754,7 +807,11 @@ struct ImgMap {
     {
         reinterpret_cast<__nv_bfloat16 *>(img + w_off(l))[(k >> 3) * (np(l) * 8) + j * 8 + (k & 7)] = __float2bfloat16_rn(v);
     }
-    __device__ void put_b(uint8_t *img, int l, int j, float v) const { reinterpret_cast<float *>(img + w_off(L))[l * HP + j] = v; }
+    __device__ void put_b(uint8_t *img, int l, int j, float v) const
+    {
+        if (l < L - 1) put_w(img, l, dims[l], j, v);                          // hidden layers: bias row of the MMA operand
+        else reinterpret_cast<float *>(img + w_off(L))[l * HP + j] = v;     // head: fp32
+    }
 };
 
 struct AdamArgs {
@@ -991,7 +1048,8 @@ int lnb_tc_adam_img(lnb_ctx *ctx, const lnb_mlp *mlp, float *param, const float 
     TcParams p{};
     fill_layout(p, mlp, K0P);
     AdamArgs ad{param, m, v, t_dev, lr, b1, b2, eps, (uint8_t *)wimg, (long long)mlp->n_layers * mlp->max_in * mlp->max_out, m == nullptr};
-    ImgMap im{mlp->n_layers, HP, K0P};
+    ImgMap im{mlp->n_layers, HP, K0P, {}};
+    for (int l = 0; l <= mlp->n_layers; ++l) im.dims[l] = mlp->dims[l];
     const int n_el = p.part_stride - 1;
     tc_adam_img_kernel<<<(n_el + 255) / 256, 256, 0, ctx->stream>>>(p, grad, ad, im, n_el);
     LNB_CHECK_LAUNCH();
@@ -1048,18 +1106,36 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
 
     const int c_in = mlp->dims[0];
     const bool grad = a->want_grad != 0;
-    size_t smem = (HP == 16 ? TcLayout<16>::total(L, K0P, c_in, rays, grad) : (HP == 32 ? TcLayout<32>::total(L, K0P, c_in, rays, grad) : TcLayout<64>::total(L, K0P, c_in, rays, grad)));
-    const int tmem_cols = (int)(HP == 16 ? TcLayout<16>::tmem_cols(L, grad) : (HP == 32 ? TcLayout<32>::tmem_cols(L, grad) : TcLayout<64>::tmem_cols(L, grad)));
     if (K0P / 8 + (L - 1) * (HP / 8) > 16) return unsupported("input + hidden widths exceed 128 features in total");
     if ((L - 1) * HP + 16 > 256) return unsupported("hidden widths exceed 256 gradient columns");
     if (!rays && (reinterpret_cast<uintptr_t>(a->X) & 3) != 0) return unsupported("X must be 4-byte aligned");
+    // LNB_TC_V2=1 selects the warp-specialised two-rows-per-thread kernel of fused_pp.cuh (same results; measured
+    // 45 us against 41 us on the 4096 x 64 batch): kept for experiments, not the default
+    const bool v1 = getenv("LNB_TC_V2") == nullptr;
+    int nslot = 2;
+    if (const char *e = getenv("LNB_TC_NSLOT")) { const int v = atoi(e); if (v == 1 || v == 2) nslot = v; }
+    size_t smem;
+    int tmem_cols;
+    if (v1) {
+        smem = (HP == 16 ? TcLayout<16>::total(L, K0P, c_in, rays, grad) : (HP == 32 ? TcLayout<32>::total(L, K0P, c_in, rays, grad) : TcLayout<64>::total(L, K0P, c_in, rays, grad)));
+        tmem_cols = (int)(HP == 16 ? TcLayout<16>::tmem_cols(L, grad) : (HP == 32 ? TcLayout<32>::tmem_cols(L, grad) : TcLayout<64>::tmem_cols(L, grad)));
+        nslot = 1;
+    } else {
+        for (;; --nslot) {   // two tiles in flight per CTA unless shared memory or TMEM say otherwise
+            smem = (HP == 16 ? PpLayout<16>::total(L, K0P, c_in, nslot, rays, grad) : (HP == 32 ? PpLayout<32>::total(L, K0P, c_in, nslot, rays, grad) : PpLayout<64>::total(L, K0P, c_in, nslot, rays, grad)));
+            tmem_cols = (int)(HP == 16 ? PpLayout<16>::tmem_cols(L, nslot, grad) : (HP == 32 ? PpLayout<32>::tmem_cols(L, nslot, grad) : PpLayout<64>::tmem_cols(L, nslot, grad)));
+            if (nslot == 1 || (smem + 1024 <= 227 * 1024 && nslot * (HP + (grad ? (L - 1) * HP + 16 : 0)) <= 512)) break;
+        }
+    }
     int per_sm = 512 / tmem_cols;
-    int by_smem = (int)((227 * 1024) / (smem + 1024));
+    int by_smem = (int)((228 * 1024) / (smem + 1024));
     if (by_smem < per_sm) per_sm = by_smem;
+    if (!v1 && per_sm > 8) per_sm = 8;   // 256 threads each
     if (per_sm < 1) return unsupported("shared memory");
     if (const char *e = getenv("LNB_TC_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
     int grid = ctx->sm_count * per_sm;
-    if (grid > p.n_tiles) grid = p.n_tiles;
+    const int want = (p.n_tiles + nslot - 1) / nslot;   // every CTA should have a tile for each of its slots
+    if (grid > want) grid = want;
     if (grid < 1) grid = 1;
     const int wimg_bytes = HP == 16 ? TcLayout<16>::wimg_bytes(L, K0P) : (HP == 32 ? TcLayout<32>::wimg_bytes(L, K0P) : TcLayout<64>::wimg_bytes(L, K0P));
     LNB_TRY(lnb_arena_reserve(ctx, (size_t)grid * p.part_stride * sizeof(float) + wimg_bytes + 8192));
@@ -1067,11 +1143,13 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     uint8_t *wimg = (uint8_t *)lnb_arena_take(ctx, wimg_bytes);
     p.wimg = (ex && ex->wimg) ? ex->wimg : wimg;
     p.t_dev = ex ? ex->t_dev : nullptr;
-    if (!ctx->tc_counter) {
-        LNB_CUDA(cudaMalloc((void **)&ctx->tc_counter, 256));
-        LNB_CUDA(cudaMemsetAsync(ctx->tc_counter, 0, 256, ctx->stream));
+    if (v1) {
+        if (!ctx->tc_counter) {
+            LNB_CUDA(cudaMalloc((void **)&ctx->tc_counter, 256));
+            LNB_CUDA(cudaMemsetAsync(ctx->tc_counter, 0, 256, ctx->stream));
+        }
+        p.tile_counter = ctx->tc_counter;
     }
-    p.tile_counter = ctx->tc_counter;
     float *loss = a->loss ? a->loss : (float *)lnb_arena_take(ctx, 16);
 #ifdef LNB_TC_CLK
     float *dbg_dev = nullptr;
@@ -1085,17 +1163,18 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     const bool use_pdl = getenv("LNB_NO_PDL") == nullptr;
     if (N > 0) {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TILE); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(v1 ? TILE : PP_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
     cfg.attrs = pdl_attr; cfg.numAttrs = use_pdl ? 1 : 0;
+#define LNB_LAUNCH(KERNEL)                                                                        \
+    do {                                                                                         \
+        LNB_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        LNB_CUDA(cudaLaunchKernelEx(&cfg, KERNEL, p));                                           \
+    } while (0)
 #define LNB_TC(HPV)                                                                              \
     do {                                                                                         \
-        if (rays) {                                                                              \
-            LNB_CUDA(cudaFuncSetAttribute(fused_tc_kernel<true, HPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            LNB_CUDA(cudaLaunchKernelEx(&cfg, fused_tc_kernel<true, HPV>, p));                   \
-        } else {                                                                                 \
-            LNB_CUDA(cudaFuncSetAttribute(fused_tc_kernel<false, HPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            LNB_CUDA(cudaLaunchKernelEx(&cfg, fused_tc_kernel<false, HPV>, p));                  \
-        }                                                                                        \
+        if (v1) { if (rays) LNB_LAUNCH((fused_v1_kernel<true, HPV>)); else LNB_LAUNCH((fused_v1_kernel<false, HPV>)); } \
+        else if (nslot == 2) { if (rays) LNB_LAUNCH((fused_tc_kernel<true, HPV, 2>)); else LNB_LAUNCH((fused_tc_kernel<false, HPV, 2>)); } \
+        else { if (rays) LNB_LAUNCH((fused_tc_kernel<true, HPV, 1>)); else LNB_LAUNCH((fused_tc_kernel<false, HPV, 1>)); } \
     } while (0)
         if (!(ex && ex->wimg)) {
             if (HP == 16) tc_prep_kernel<16><<<1, 256, 0, ctx->stream>>>(p, wimg);
@@ -1109,6 +1188,7 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
         else LNB_TC(64);
         lnb_prof_end(ctx);
 #undef LNB_TC
+#undef LNB_LAUNCH
         LNB_CHECK_LAUNCH();
     } else {
         grid = 0;
@@ -1124,6 +1204,9 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
         if (++calls % 150 == 20) {
             double acc[24] = {0};
             for (int b = 0; b < grid; ++b) for (int i = 0; i < 24; ++i) acc[i] += h[(size_t)b * 24 + i];
+            const char *nm2[24] = {"wait dW (A_0)", "wait out: fwd epilogues", "", "wait out: head", "wait out: bwd epilogues", "", "", "",
+                                   "build A_0 + loads", "fwd epilogues", "", "head + compositing", "bwd epilogues", "", "", "",
+                                   "", "", "", "", "", "wait TMA", "prologue", "final wait dW"};
             const char *nm[24] = {"wait X", "convert+publish", "issue fwd", "wait fwd mma", "fwd epilogue", "fwd publish", "issue fwd AGAIN (experiment)", "dz publish",
                                   "issue bwd", "wait bwd mma", "bwd epilogue", "bwd publish", "wait dW", "issue dW + final epilogue", "prologue", "loop top",
                                   "head ld+bias", "comp: act+prodscan", "comp: sync1", "comp: carry+colour", "comp: sync2", "comp: dcol+affine", "comp: sync3", "comp: finish"};
@@ -1139,7 +1222,7 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
                 fprintf(stderr, "   CTA start spread %.1f us, first end at %.1f us, last end at %.1f us (from first start)\n",
                         (s1 - s0) * 1e-3, (e0 - s0) * 1e-3, (e1 - s0) * 1e-3);
             }
-            for (int i = 0; i < 24; ++i) if (acc[i] > 0) fprintf(stderr, "   %-18s %8.0f\n", nm[i], acc[i] / p.n_tiles);
+            for (int i = 0; i < 24; ++i) if (acc[i] > 0) fprintf(stderr, "   %-22s %8.0f\n", (v1 ? nm : nm2)[i], acc[i] / p.n_tiles);
         }
     }
 #endif
@@ -1148,7 +1231,8 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     const float seed_val = seed_is_loss ? 1.0f : a->seed;
     int blocks = a->want_grad ? (n_el + 31) / 32 : 1;
     AdamArgs ad{};
-    ImgMap im{L, HP, K0P};
+    ImgMap im{L, HP, K0P, {}};
+    for (int l = 0; l <= L; ++l) im.dims[l] = mlp->dims[l];
     const int fuse = ex && ex->fuse_adam && a->want_grad;
     if (fuse) ad = AdamArgs{ex->param, ex->m, ex->v, ex->t_dev, ex->lr, ex->b1, ex->b2, ex->eps, (uint8_t *)ex->wimg_out,
                             (long long)L * mlp->max_in * mlp->max_out, ex->m == nullptr};
