@@ -226,10 +226,13 @@ struct TcLayout {
     static constexpr int MAX_STAGES = 2 * MAXL + 1; // records of the per-CTA MMA program
     __host__ __device__ static int a_off(int l, int K0P) { return l == 0 ? 0 : (K0P / 8 + (l - 1) * HSL) * SLAB; }
     __host__ __device__ static int dz_off(int l, int L, int K0P) { return (K0P / 8 + (L - 1) * HSL + l * HSL) * SLAB; }
-    // forward only: the A buffers plus two slabs where dZ_0 would start (the per-ray colour / target scratch lives there)
+    // forward only (render): nothing is kept for a weight gradient, so every layer's input lives in the SAME buffer -- A_{l+1}
+    // overwrites A_l once layer l's MMA has completed -- followed by two slabs of per-ray colour / target scratch.  That is
+    // 16 KB + the weight image per CTA in rays mode: 9 tiles in flight per SM instead of 5.
+    __host__ __device__ static int fwd_slabs(int K0P) { return K0P / 8 > HSL ? K0P / 8 : HSL; }
     __host__ __device__ static int act_bytes(int L, int K0P, bool grad = true)
     {
-        return grad ? (K0P / 8 + 2 * (L - 1) * HSL + 2) * SLAB : (K0P / 8 + (L - 1) * HSL + 2) * SLAB;
+        return grad ? (K0P / 8 + 2 * (L - 1) * HSL + 2) * SLAB : (fwd_slabs(K0P) + 2) * SLAB;
     }
     __host__ __device__ static int np(int l, int L) { return l < L - 1 ? HP : 16; }
     __host__ __device__ static int kp(int l, int K0P) { return l == 0 ? K0P : HP; }
@@ -307,7 +310,8 @@ __global__ void __launch_bounds__(TILE) fused_v1_kernel(const TcParams p)
     const int stage_sz = RAYS ? 0 : LY::stage_bytes(c_in, K0P);
     // per-ray colour / target scratch aliases dZ_0: it is dead from the top of a tile (the previous
     // tile's dW MMAs have been awaited) until the last backward epilogue writes it
-    float *const color_s = reinterpret_cast<float *>(smem + LY::dz_off(0, L, K0P));
+    const bool fwd_only = p.want_grad == 0;
+    float *const color_s = reinterpret_cast<float *>(smem + (fwd_only ? LY::fwd_slabs(K0P) * SLAB : LY::dz_off(0, L, K0P)));
     float *const tgt_s = color_s + TILE * 3;
     float *const tailp = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(stage) + stage_sz); // [4] inclusive product at lane 31
     int *const tail_s = reinterpret_cast<int *>(tailp + 4);  // [4] sample index at lane 31
@@ -340,7 +344,7 @@ __global__ void __launch_bounds__(TILE) fused_v1_kernel(const TcParams p)
     // the upper 8 features of dZ_{L-1}, which must stay zero)
     for (uint8_t *z = smem + LY::dz_off(L - 1, L, K0P) + tid * 16; z < smem + act_bytes; z += TILE * 16) *reinterpret_cast<uint4 *>(z) = make_uint4(0, 0, 0, 0);
     // A_0: only the slabs holding live features are rewritten per tile; its padding must be zero
-    for (uint8_t *z = smem + tid * 16; z < smem + LY::a_off(1, K0P); z += TILE * 16) *reinterpret_cast<uint4 *>(z) = make_uint4(0, 0, 0, 0);
+    for (uint8_t *z = smem + tid * 16; z < smem + (fwd_only ? LY::fwd_slabs(K0P) * SLAB : LY::a_off(1, K0P)); z += TILE * 16) *reinterpret_cast<uint4 *>(z) = make_uint4(0, 0, 0, 0);
     for (uint8_t *z = reinterpret_cast<uint8_t *>(stage) + tid * 16; z < reinterpret_cast<uint8_t *>(tailp); z += TILE * 16)
         *reinterpret_cast<uint4 *>(z) = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
@@ -352,7 +356,7 @@ __global__ void __launch_bounds__(TILE) fused_v1_kernel(const TcParams p)
         // ---- build the MMA program.  Stages: fwd l (0..L-1), dH l (L+l, l = 1..L-1), dW (2L)
         for (int l = 0; l < L; ++l) {          // D[128 x Np] = A_l[128 x Kp] * W_l   (A, B K-major)
             const int Np = LY::np(l, L), Kp = LY::kp(l, K0P);
-            const uint32_t a0 = smem_u32(smem + LY::a_off(l, K0P)), b0 = smem_u32(Wbase + LY::w_off(l, L, K0P));
+            const uint32_t a0 = smem_u32(smem + (fwd_only ? 0 : LY::a_off(l, K0P))), b0 = smem_u32(Wbase + LY::w_off(l, L, K0P));
             prog[l] = StageRec{smem_desc(a0, SLAB, 128), smem_desc(b0, Np * 16, 128), (uint32_t)(2 * SLAB) >> 4, (uint32_t)(2 * Np * 16) >> 4,
                                instr_desc(128, Np, 0, 0), 0u, (uint32_t)(Kp / 16), 0u, 0u, 0u};
         }
@@ -397,7 +401,7 @@ __global__ void __launch_bounds__(TILE) fused_v1_kernel(const TcParams p)
     uint32_t dwphase = 0;
     mbar_wait(bar_w, 0); // weights + biases have landed
 
-    auto a_buf = [&](int l) { return smem + LY::a_off(l, K0P); };
+    auto a_buf = [&](int l) { return smem + (fwd_only ? 0 : LY::a_off(l, K0P)); };
     auto dz_buf = [&](int l) { return smem + LY::dz_off(l, L, K0P); };
     auto row_ptr = [&](uint8_t *buf, int slab) { return reinterpret_cast<uint4 *>(buf + slab * SLAB + tid * 16); };
     // issue one stage of the MMA program (thread 0 only)
