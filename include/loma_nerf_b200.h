@@ -35,7 +35,7 @@ extern "C" {
 #define LNB_API
 #endif
 
-#define LNB_ABI_VERSION 2
+#define LNB_ABI_VERSION 3
 #define LNB_MAX_LAYERS 16
 
 /* ------------------------------------------------------------------------------------------
@@ -133,6 +133,31 @@ typedef struct {
     int head; /* LNB_HEAD_* */
 } lnb_mlp;
 
+/* CAMERA MODE input (nerf only): rays AND sample depths are generated on the device from a pose, so nothing per ray or per
+ * sample crosses the bus or sits in HBM -- the device-side form of get_rays (train_nerf.py:23-62) and of the sample
+ * construction (train_nerf.py:289-311).  Ray r looks through pixel q = pixels ? pixels[r] : first_pixel + r of a
+ * height x width grid, row = q / width, col = q % width, with normalised coordinates i = col / (width-1),
+ * j = row / (width-1) (get_rays builds BOTH axes from linspace(0, 1, width), train_nerf.py:37-39);
+ *   dir = ((i - cx) / fx, -(j - cy) / fy, -1) @ R^T  (not normalised),  origin = T,  [R | T] = c2w (3 x 4, row-major).
+ * Sample depths: stratified == 0: t = linspace(near, far, S) (train_nerf.py:289, endpoint included);
+ * stratified == 1: t_s = near + (s + u)(far - near) / S with u = lnb_uniform(seed, q, s) in [0, 1), the counter-based
+ * generator documented at lnb_uniform below (SURVEY.md 8d's synthetic sampling; the reference has the jitter commented
+ * out).  dists = t[s+1] - t[s], last 1e8.  The exact path forms every value in float64 like numpy does and rounds
+ * once to float32; the tensor-core path computes in float32. */
+typedef struct {
+    double c2w[12];
+    double fx, fy, cx, cy;        /* normalized_K[0][0], [1][1], [0][2], [1][2] */
+    int width, height;
+    long long first_pixel;
+    const int *pixels;            /* optional [R] pixel indices (device pointer; host pointer for the *_host calls) */
+    double near, far;
+    int stratified;
+    unsigned long long seed;
+} lnb_camera;
+/* u = (z >> 40) * 2^-24 with z = mix(seed + 0x9E3779B97F4A7C15 * (q * 4096 + s + 1)), mix = the SplitMix64 finaliser
+ * (z ^= z >> 30; z *= 0xBF58476D1CE4E5B9; z ^= z >> 27; z *= 0x94D049BB133111EB; z ^= z >> 31).  Host-callable. */
+LNB_API double lnb_uniform(unsigned long long seed, long long pixel, int s);
+
 /* One forward(+backward) problem in the reference's layout.  N = R*S samples.  Pointers are
  * DEVICE pointers for lnb_nerf_step / lnb_fit_step and HOST pointers for the *_host variants.
  * Any output pointer may be NULL (not produced).  Accumulating outputs (+=) are marked. */
@@ -174,11 +199,15 @@ typedef struct {
     const void *t;            /* [R][S] sample depths along each ray                            */
     int ray_dtype;            /* LNB_RAY_F64 (the reference's get_rays/linspace dtype) or F32   */
     int pe_bands;             /* E; dims[0] must equal 3 + 6E                                   */
+    /* CAMERA MODE (selected when X == NULL, rays_o == NULL and cam != NULL): see lnb_camera.      */
+    /* `cam` is always a HOST pointer (a few bytes, passed to the kernels by value).               */
+    const lnb_camera *cam;
 } lnb_step_args;
 
 LNB_API int lnb_abi_version(void);
 /* Fills out[0..n) with {sizeof(lnb_mlp), sizeof(lnb_step_args), offsetof(lnb_step_args, X),
- * inter, rgba, loss, want_grad, d_ws, path, rays_o, pe_bands}; returns how many values exist.  Lets a foreign-
+ * inter, rgba, loss, want_grad, d_ws, path, rays_o, pe_bands, cam, sizeof(lnb_camera), offsetof(lnb_camera, pixels)};
+ * returns how many values exist.  Lets a foreign-
  * language binding verify its struct mirror without a GPU. */
 LNB_API int lnb_struct_layout(int *out, int n);
 LNB_API int lnb_device_count(void);
@@ -220,6 +249,14 @@ LNB_API int lnb_pos_encoding(lnb_ctx *ctx, const double *x, long long n, int F, 
  * rays_o, rays_d [R][3] float64, t [R][S] float64. Device pointers. */
 LNB_API int lnb_sample_encode(lnb_ctx *ctx, const double *rays_o, const double *rays_d, const double *t,
                       int R, int S, int E, float *X, float *dists);
+
+/* The rays and sample depths camera mode generates, written out (any pointer may be NULL): rays_o, rays_d [R][3], t [R][S]
+ * float64.  Device pointers (cam itself is a host pointer). */
+LNB_API int lnb_camera_rays(lnb_ctx *ctx, const lnb_camera *cam, int R, int S, double *rays_o, double *rays_d, double *t);
+
+/* out[i] = (unsigned char) rint(255 * clamp(rgb[i], 0, 1)), i < n: what the hosts do before writing a PNG / video frame
+ * (train_nerf.py:686-700), so that a rendered frame leaves the device as 3 bytes per pixel.  Device pointers. */
+LNB_API int lnb_color_to_u8(lnb_ctx *ctx, const float *rgb, long long n, unsigned char *out);
 
 /* c[a_h][b_w] += a[a_h][a_w] * b[a_w][b_w]; device pointers (scripts/mlp_fit.py:150-172). */
 LNB_API int lnb_mult_a_b(lnb_ctx *ctx, const float *a, int a_h, int a_w, const float *b, int b_w, float *c);

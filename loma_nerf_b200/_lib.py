@@ -26,6 +26,13 @@ class LnbMlp(Structure):
                 ("max_out", c_int), ("head", c_int)]
 
 
+class LnbCamera(Structure):
+    """Mirror of lnb_camera (camera mode: rays and sample depths generated on the device from a pose)."""
+    _fields_ = [("c2w", c_double * 12), ("fx", c_double), ("fy", c_double), ("cx", c_double), ("cy", c_double),
+                ("width", c_int), ("height", c_int), ("first_pixel", c_longlong), ("pixels", c_void_p),
+                ("near", c_double), ("far", c_double), ("stratified", c_int), ("seed", ctypes.c_ulonglong)]
+
+
 class LnbStepArgs(Structure):
     """Mirror of lnb_step_args; field order and types must match the header exactly
     (tests/test_abi.py compares sizeof and offsets with the values the library reports)."""
@@ -44,6 +51,7 @@ class LnbStepArgs(Structure):
         ("path", c_int),
         ("rays_o", c_void_p), ("rays_d", c_void_p), ("t", c_void_p), ("ray_dtype", c_int),
         ("pe_bands", c_int),
+        ("cam", POINTER(LnbCamera)),
     ]
 
 
@@ -90,6 +98,10 @@ def load():
     lib.lnb_pos_encoding.argtypes = [c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p]
     lib.lnb_sample_encode.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                       c_void_p, c_void_p]
+    lib.lnb_camera_rays.argtypes = [c_void_p, P(LnbCamera), c_int, c_int, c_void_p, c_void_p, c_void_p]
+    lib.lnb_color_to_u8.argtypes = [c_void_p, c_void_p, c_longlong, c_void_p]
+    lib.lnb_uniform.argtypes = [ctypes.c_ulonglong, c_longlong, c_int]
+    lib.lnb_uniform.restype = c_double
     lib.lnb_mult_a_b.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]
     lib.lnb_adam_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
                                   c_int, c_double, c_double, c_double, c_double]

@@ -29,6 +29,26 @@ class LnbError(RuntimeError):
     pass
 
 
+def make_camera(c2w, normalized_K, width, height=None, near=2.0, far=6.0, first_pixel=0, pixels=None, stratified=False, seed=0):
+    """lnb_camera from what the reference hosts hold: the 4x4 (or 3x4) camera-to-world pose and the normalised intrinsics
+    K = [[f, 0, .5], [0, f, .5], [0, 0, 1]] (train_nerf.py:265-271), near / far (train_nerf.py:201-202).  `pixels` (int32
+    array, on the device for device calls) picks arbitrary pixels; otherwise ray r is pixel first_pixel + r."""
+    c = L.LnbCamera()
+    m = np.asarray(c2w, np.float64)[:3, :4]
+    for i in range(12):
+        c.c2w[i] = float(m.flat[i])
+    K = np.asarray(normalized_K, np.float64)
+    c.fx, c.fy, c.cx, c.cy = float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
+    c.width, c.height = int(width), int(width if height is None else height)
+    c.first_pixel, c.near, c.far = int(first_pixel), float(near), float(far)
+    c.stratified, c.seed = int(bool(stratified)), int(seed) & 0xFFFFFFFFFFFFFFFF
+    if pixels is not None:
+        assert str(pixels.dtype).endswith("int32")
+        c.pixels = pixels.data_ptr() if torch is not None and isinstance(pixels, torch.Tensor) else pixels.ctypes.data
+        c._keep = pixels
+    return c
+
+
 def make_mlp(dims, ws_shape, head):
     m = L.LnbMlp()
     dims = [int(d) for d in dims]
@@ -176,7 +196,7 @@ class Context:
 
     # -------------------------------------------------------------------------------------------
     def _step(self, nerf, dims, X, ws, bs, target, dists, R, S, grad, seed, outputs, out, rows,
-              path, inter_accumulate, color_accumulate, head, rays=None, pe_bands=0):
+              path, inter_accumulate, color_accumulate, head, rays=None, pe_bands=0, camera=None):
         dev = _is_cuda(ws)
         mlp = make_mlp(dims, ws.shape, head)
         Ln, mi, mo = mlp.n_layers, mlp.max_in, mlp.max_out
@@ -194,6 +214,8 @@ class Context:
             assert tuple(ro.shape) == (R, 3) and tuple(rd.shape) == (R, 3) and tuple(tv.shape) == (R, S)
             a.rays_o, a.rays_d, a.t = _ptr(ro), _ptr(rd), _ptr(tv)
             a.ray_dtype, a.pe_bands = (L.RAY_F64 if f64 else L.RAY_F32), int(pe_bands)
+        if camera is not None:
+            a.cam, a.pe_bands = ctypes.pointer(camera), int(pe_bands)
         a.inter_rows, a.inter_ld = M, mo
         a.inter_accumulate, a.color_accumulate = int(inter_accumulate), int(color_accumulate)
         a.want_grad = int(bool(grad))
@@ -256,6 +278,33 @@ class Context:
         R, S = int(t.shape[0]), int(t.shape[1])
         return self._step(True, dims, None, ws, bs, target, None, R, S, grad, seed, outputs, out, None, path,
                           False, False, L.HEAD_NERF, rays=(rays_o, rays_d, t), pe_bands=pe_bands)
+
+    def nerf_step_camera(self, dims, camera, R, S, pe_bands, ws, bs, target=None, grad=False, seed=1.0,
+                         outputs=("color", "loss"), out=None, path="f32"):
+        """The same step with rays AND sample depths generated on the device from a pose (`make_camera`): the
+        device-side get_rays (train_nerf.py:23-62) and linspace / stratified depths (train_nerf.py:289-311).
+        Nothing per ray or per sample is read: R rays of S samples through pixels first_pixel .. (or `pixels`)."""
+        return self._step(True, dims, None, ws, bs, target, None, int(R), int(S), grad, seed, outputs, out, None, path,
+                          False, False, L.HEAD_NERF, pe_bands=pe_bands, camera=camera)
+
+    def camera_rays(self, camera, R, S):
+        """(rays_o, rays_d, t) float64 cuda tensors camera mode generates (for checks / hosts that want them)."""
+        dev = torch.device("cuda", self.device)
+        o = torch.empty((R, 3), dtype=torch.float64, device=dev)
+        d = torch.empty((R, 3), dtype=torch.float64, device=dev)
+        t = torch.empty((R, S), dtype=torch.float64, device=dev)
+        self.order_after_torch()
+        self._check(self.lib.lnb_camera_rays(self.h, ctypes.byref(camera), int(R), int(S), o.data_ptr(), d.data_ptr(), t.data_ptr()))
+        return o, d, t
+
+    def color_to_u8(self, rgb, out=None):
+        """uint8 image bytes of float colours, clamp(rgb, 0, 1) * 255 rounded (train_nerf.py:686-700), on the device."""
+        assert _is_cuda(rgb) and rgb.dtype == torch.float32 and rgb.is_contiguous()
+        if out is None:
+            out = torch.empty(rgb.shape, dtype=torch.uint8, device=rgb.device)
+        self.order_after_torch()
+        self._check(self.lib.lnb_color_to_u8(self.h, rgb.data_ptr(), rgb.numel(), out.data_ptr()))
+        return out
 
     def fit_step(self, dims, X, ws, bs, target, grad=False, seed=1.0, outputs=("loss",), out=None,
                  rows=None, path="f32", inter_accumulate=False):
@@ -328,10 +377,14 @@ class Trainer:
             self.lib.lnb_trainer_destroy(self.h)
             self.h = None
 
-    def _batch(self, X=None, dists=None, target=None, rays=None, pe_bands=0, R=None, S=None, path="tc", seed=1.0):
+    def _batch(self, X=None, dists=None, target=None, rays=None, pe_bands=0, R=None, S=None, path="tc", seed=1.0, camera=None):
         a = L.LnbStepArgs()
         nerf = self.head == L.HEAD_NERF
-        if rays is not None:
+        if camera is not None:
+            R, S = int(target.shape[0]) if R is None else int(R), int(S)
+            a.cam, a.pe_bands = ctypes.pointer(camera), int(pe_bands)
+            self._cam_keep = camera
+        elif rays is not None:
             ro, rd, tv = rays
             R, S = int(tv.shape[0]), int(tv.shape[1])
             a.rays_o, a.rays_d, a.t = _ptr(ro), _ptr(rd), _ptr(tv)

@@ -83,7 +83,8 @@ extern "C" int lnb_struct_layout(int *out, int n)
                      (int)offsetof(lnb_step_args, rgba), (int)offsetof(lnb_step_args, loss),
                      (int)offsetof(lnb_step_args, want_grad), (int)offsetof(lnb_step_args, d_ws),
                      (int)offsetof(lnb_step_args, path), (int)offsetof(lnb_step_args, rays_o),
-                     (int)offsetof(lnb_step_args, pe_bands)};
+                     (int)offsetof(lnb_step_args, pe_bands), (int)offsetof(lnb_step_args, cam),
+                     (int)sizeof(lnb_camera), (int)offsetof(lnb_camera, pixels)};
     const int k = (int)(sizeof(v) / sizeof(v[0]));
     for (int i = 0; i < k && i < n; ++i) out[i] = v[i];
     return k;
@@ -257,11 +258,19 @@ int validate(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, bool nerf
     d->M = a->rows > d->N ? a->rows : d->N;
     d->Wt = a->target_w > 0 ? a->target_w : 3;
     d->out_last = mlp->dims[mlp->n_layers];
-    const bool rays = !a->X && a->rays_o;
-    LNB_ARG((a->X || d->N == 0 || rays) && a->ws && a->bs, "X (or rays), ws, bs are required");
+    const bool cam = !a->X && !a->rays_o && a->cam;
+    const bool rays = !a->X && (a->rays_o || cam);
+    LNB_ARG((a->X || d->N == 0 || rays) && a->ws && a->bs, "X (or rays, or a camera), ws, bs are required");
+    if (cam) {
+        LNB_ARG(a->cam->width >= 2 && a->cam->height >= 1, "camera: width >= 2, height >= 1");
+        LNB_ARG(a->cam->fx != 0.0 && a->cam->fy != 0.0, "camera: zero focal length");
+        LNB_ARG(a->cam->pixels || (a->cam->first_pixel >= 0 && a->cam->first_pixel + d->R <= (long long)a->cam->width * a->cam->height),
+                "camera: pixel range outside the grid");
+        LNB_ARG(d->S <= 4096, "camera: at most 4096 samples per ray");
+    }
     if (rays) {
         LNB_ARG(nerf, "rays mode is a nerf-path feature");
-        LNB_ARG(a->rays_d && a->t, "rays mode needs rays_o, rays_d and t");
+        LNB_ARG(cam || (a->rays_d && a->t), "rays mode needs rays_o, rays_d and t");
         LNB_ARG(a->pe_bands >= 0 && d->c_in == 3 + 6 * a->pe_bands, "rays mode: dims[0] != 3 + 6*pe_bands");
         LNB_ARG(a->ray_dtype == LNB_RAY_F64 || a->ray_dtype == LNB_RAY_F32, "ray_dtype");
         LNB_ARG(!a->d_X, "d_X is not available in rays mode");
@@ -299,7 +308,8 @@ int step_layerwise(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, boo
     if (n_chunks < 1) n_chunks = 1;
 
     // ---- arena plan
-    const bool rays = !a->X && a->rays_o;
+    const bool cam = !a->X && !a->rays_o && a->cam;
+    const bool rays = !a->X && (a->rays_o || cam);
     size_t need = 4096;
     auto add = [&](size_t floats) { need += align_up(floats * sizeof(float), 256) + 256; };
     if (rays) { add((size_t)N * d.c_in); add((size_t)R * S); }
@@ -322,7 +332,8 @@ int step_layerwise(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, boo
     const float *X = a->X, *dists = a->dists;
     if (rays) {
         float *Xe = takef((size_t)N * d.c_in), *de = takef((size_t)R * S);
-        LNB_TRY(lnb_launch_sample_encode(ctx, a->rays_o, a->rays_d, a->t, a->ray_dtype == LNB_RAY_F64, R, S, a->pe_bands, Xe, de));
+        if (cam) LNB_TRY(lnb_launch_camera_encode(ctx, a->cam, R, S, a->pe_bands, Xe, de, nullptr, 0));
+        else LNB_TRY(lnb_launch_sample_encode(ctx, a->rays_o, a->rays_d, a->t, a->ray_dtype == LNB_RAY_F64, R, S, a->pe_bands, Xe, de));
         X = Xe; dists = de;
     }
     // ---- forward
@@ -515,10 +526,17 @@ int step_host(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, bool ner
         reg(a->rays_d, nullptr, R * 3 * w, BUF_IN, (void **)&dev.rays_d);
         reg(a->t, nullptr, R * S * w, BUF_IN, (void **)&dev.t);
     }
+    lnb_camera cam_dev;   // camera mode: the struct stays on the host; its pixel list (if any) is staged like an input
+    const bool cam_mode = !a->X && !a->rays_o && a->cam;
+    if (cam_mode) {
+        cam_dev = *a->cam;
+        dev.cam = &cam_dev;
+        if (a->cam->pixels) reg(a->cam->pixels, nullptr, R, BUF_IN, (void **)&cam_dev.pixels);
+    }
     IN_(ws, nW);
     IN_(bs, nB);
     IN_(target, R * d.Wt);
-    if (nerf && !(!a->X && a->rays_o)) IN_(dists, R * S);
+    if (nerf && !(!a->X && (a->rays_o || cam_mode))) IN_(dists, R * S);
     if (a->inter) reg(a->inter, a->inter, nInter, a->inter_accumulate ? BUF_INOUT : BUF_OUT, (void **)&dev.inter);
     if (nerf) {
         OUT_(rgba, R * S * 4);

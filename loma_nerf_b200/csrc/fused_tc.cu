@@ -32,6 +32,7 @@
 
 #include <vector>
 
+#include "camera.cuh"
 #include "lnb_internal.h"
 
 namespace {
@@ -39,6 +40,16 @@ namespace {
 constexpr int TILE = 128;          // samples per tile = UMMA M
 constexpr int SLAB = TILE * 16;    // bytes per 8-feature slab
 constexpr int MAXL = 4;            // layers supported by the fused kernel
+
+// camera mode in float32 (the tensor-core path): see camera.cuh / lnb_camera
+struct CamF32 {
+    float c2w[12];
+    float inv_fx, inv_fy, cx, cy, step, near, far, dt_lin, dt_str;   // dt_lin = (far-near)/(S-1), dt_str = (far-near)/S
+    long long first_pixel;
+    const int *pixels;
+    unsigned long long seed;
+    int width, stratified;
+};
 
 struct TcParams {
     const float *X, *dists, *target, *ws, *bs;
@@ -49,6 +60,8 @@ struct TcParams {
     // rays mode (X == NULL): features are computed in the kernel from rays and sample depths
     const void *rays_o, *rays_d, *tvals; // [R][3], [R][3], [R][S]; float64 when ray_f64 else float32
     int ray_f64, pe_bands;
+    int cam_mode;      // rays and depths generated from `cam` instead of read from rays_o / rays_d / tvals
+    CamF32 cam;
     int *t_dev;        // optimiser step counter, incremented once per launch (or NULL)
     int *tile_counter; // dynamic tile scheduler: tiles beyond the first are claimed with atomicAdd
     long long N;       // samples (rows of X)
@@ -460,7 +473,30 @@ __global__ void __launch_bounds__(TILE) fused_v1_kernel(const TcParams p)
             // ---- features from rays: pts = o + d t (train_nerf.py:289-299), PE (pos_encoding.py:38-70),
             // dist = t[s+1] - t[s], last 1e8 (train_nerf.py:306-311); written straight into A_0
             float x[3] = {0.f, 0.f, 0.f};
-            if (live) {
+            if (live && p.cam_mode) {
+                // ray of pixel q and depth of sample smp straight from the pose (get_rays, train_nerf.py:23-62; linspace /
+                // stratified depths, train_nerf.py:289-311): no per-ray or per-sample input at all
+                const CamF32 &c = p.cam;
+                const long long ray = row0 / S + ray_l;
+                const long long q = c.pixels ? (long long)__ldg(c.pixels + ray) : c.first_pixel + ray;
+                const unsigned uq = (unsigned)q, col = uq % (unsigned)c.width, row = uq / (unsigned)c.width;
+                const float fi = col == (unsigned)c.width - 1 ? 1.0f : (float)col * c.step, fj = row == (unsigned)c.width - 1 ? 1.0f : (float)row * c.step;
+                const float dx = (fi - c.cx) * c.inv_fx, dy = (c.cy - fj) * c.inv_fy;
+                float tt, tn;
+                if (c.stratified) {
+                    tt = fmaf((float)smp + (float)lnb_uniform_bits(c.seed, q, smp) * (1.0f / 16777216.0f), c.dt_str, c.near);
+                    tn = fmaf((float)(smp + 1) + (float)lnb_uniform_bits(c.seed, q, smp + 1) * (1.0f / 16777216.0f), c.dt_str, c.near);
+                } else {
+                    tt = smp == S - 1 && S > 1 ? c.far : fmaf((float)smp, c.dt_lin, c.near);
+                    tn = smp + 1 == S - 1 ? c.far : fmaf((float)(smp + 1), c.dt_lin, c.near);
+                }
+                my_dist = smp + 1 < S ? tn - tt : 1e8f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float dk = fmaf(dx, c.c2w[4 * k], fmaf(dy, c.c2w[4 * k + 1], 0.0f - c.c2w[4 * k + 2]));
+                    x[k] = fmaf(dk, tt, c.c2w[4 * k + 3]);
+                }
+            } else if (live) {
                 const long long ray = row0 / S + ray_l, smpl = row0 + tid;
                 if (p.ray_f64) {
                     const double *o = reinterpret_cast<const double *>(p.rays_o) + ray * 3;
@@ -1082,9 +1118,12 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     const int R = a->R, S = nerf ? a->S : 1;
     const long long N = a->n_rows > 0 ? a->n_rows : (long long)R * S;
     if (nerf && (S > TILE || N != (long long)R * S)) return unsupported("needs S <= 128 and n_rows == R*S");
-    const bool rays = a->X == nullptr && a->rays_o != nullptr;
-    if (rays && (!nerf || !a->rays_d || !a->t || mlp->dims[0] != 3 + 6 * a->pe_bands))
-        return unsupported("rays mode needs rays_o, rays_d, t and dims[0] == 3 + 6 * pe_bands");
+    const bool cam = a->X == nullptr && a->rays_o == nullptr && a->cam != nullptr;
+    const bool rays = a->X == nullptr && (a->rays_o != nullptr || cam);
+    if (rays && (!nerf || (!cam && (!a->rays_d || !a->t)) || mlp->dims[0] != 3 + 6 * a->pe_bands))
+        return unsupported("rays mode needs rays_o, rays_d, t (or a camera) and dims[0] == 3 + 6 * pe_bands");
+    if (cam && (long long)a->cam->width * a->cam->height >= (1ll << 31)) return unsupported("camera: more than 2^31 pixels");
+    if (cam && getenv("LNB_TC_V2")) return unsupported("the experimental LNB_TC_V2 kernel has no camera mode");
     if (!nerf && N != R) return unsupported("needs n_rows == R");
     if (a->rows > N) return unsupported("rows > n_rows");
     if (!nerf && (a->target_w > 4)) return unsupported("target wider than 4");
@@ -1094,6 +1133,15 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     TcParams p{};
     p.X = a->X; p.dists = a->dists; p.target = a->target; p.ws = a->ws; p.bs = a->bs;
     p.rays_o = a->rays_o; p.rays_d = a->rays_d; p.tvals = a->t; p.ray_f64 = a->ray_dtype == LNB_RAY_F64; p.pe_bands = a->pe_bands;
+    if (cam) {
+        const lnb_camera &c = *a->cam;
+        p.cam_mode = 1;
+        for (int i = 0; i < 12; ++i) p.cam.c2w[i] = (float)c.c2w[i];
+        p.cam.inv_fx = (float)(1.0 / c.fx); p.cam.inv_fy = (float)(1.0 / c.fy); p.cam.cx = (float)c.cx; p.cam.cy = (float)c.cy;
+        p.cam.step = (float)(1.0 / (double)(c.width - 1)); p.cam.near = (float)c.near; p.cam.far = (float)c.far;
+        p.cam.dt_lin = (float)((c.far - c.near) / (double)(a->S > 1 ? a->S - 1 : 1)); p.cam.dt_str = (float)((c.far - c.near) / (double)a->S);
+        p.cam.first_pixel = c.first_pixel; p.cam.pixels = c.pixels; p.cam.seed = c.seed; p.cam.width = c.width; p.cam.stratified = c.stratified;
+    }
     p.color = nerf ? a->color : nullptr;
     p.N = N; p.R = R; p.S = S;
     p.G = nerf ? TILE / S : TILE;

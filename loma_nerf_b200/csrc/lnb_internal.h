@@ -187,6 +187,8 @@ int lnb_launch_sample_encode(lnb_ctx *ctx, const void *o, const void *d, const v
                              int R, int S, int E, float *X, float *dists);
 int lnb_launch_sample_encode_bf16(lnb_ctx *ctx, const void *o, const void *d, const void *t, int f64,
                                   int R, int S, int E, float *X, float *dists, void *Xb, int ldb);
+// camera mode (lnb_camera): features / dists (or the wide path's bf16 rows) straight from the pose
+int lnb_launch_camera_encode(lnb_ctx *ctx, const lnb_camera *cam, int R, int S, int E, float *X, float *dists, void *Xb, int ldb);
 int lnb_launch_adam(lnb_ctx *ctx, float *p, const float *g, float *m, float *v, long long n, int t,
                     double lr, double b1, double b2, double eps);
 int lnb_launch_adam_dev(lnb_ctx *ctx, float *p, const float *g, float *m, float *v, long long n,

@@ -182,11 +182,17 @@ extern "C" int lnb_trainer_step_host(lnb_trainer *t, const lnb_step_args *batch,
     const size_t R = (size_t)a.R, S = nerf ? (size_t)a.S : 1, N = a.n_rows > 0 ? (size_t)a.n_rows : R * S;
     const size_t c_in = (size_t)t->mlp.dims[0], Wt = a.target_w > 0 ? (size_t)a.target_w : 3;
     const bool rays = !a.X && a.rays_o;
+    const bool cam = !a.X && !a.rays_o && a.cam;
     const size_t rw = a.ray_dtype == LNB_RAY_F64 ? 8 : 4;
     struct In { const void **slot; size_t bytes; };
     In ins[6];
     int n_in = 0;
-    if (rays) {
+    lnb_camera cam_dev;   // camera mode: nothing per ray but the optional pixel list and the targets crosses the bus
+    if (cam) {
+        cam_dev = *a.cam;
+        a.cam = &cam_dev;
+        if (cam_dev.pixels) ins[n_in++] = In{(const void **)&cam_dev.pixels, R * sizeof(int)};
+    } else if (rays) {
         ins[n_in++] = In{&a.rays_o, R * 3 * rw};
         ins[n_in++] = In{&a.rays_d, R * 3 * rw};
         ins[n_in++] = In{&a.t, R * S * rw};

@@ -1218,7 +1218,8 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
     if (N > 0x7fffffffLL - 256) return unsupported("too many samples for one call");
     if (a->want_grad && !a->target) return unsupported("gradient without target");
     if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
-    const bool rays = !a->X && a->rays_o;
+    const bool cam = !a->X && !a->rays_o && a->cam;
+    const bool rays = !a->X && (a->rays_o || cam);
     const bool grad = a->want_grad != 0;
     const int c_in = mlp->dims[0];
     int in_pad[LNB_MAX_LAYERS], out_pad[LNB_MAX_LAYERS];
@@ -1267,7 +1268,9 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
     const float *X = a->X, *dists = a->dists;
     if (rays) {   // sample positions and positional encoding straight into the bf16 operand of layer 0
         float *de = (float *)take((size_t)R * S * 4);
-        if (N > 0)
+        if (N > 0 && cam)
+            LNB_TRY(lnb_launch_camera_encode(ctx, a->cam, R, S, a->pe_bands, nullptr, de, H[0], in_pad[0]));
+        else if (N > 0)
             LNB_TRY(lnb_launch_sample_encode_bf16(ctx, a->rays_o, a->rays_d, a->t, a->ray_dtype == LNB_RAY_F64, R, S, a->pe_bands, nullptr, de, H[0],
                                                   in_pad[0]));
         dists = de;

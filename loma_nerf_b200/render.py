@@ -52,6 +52,25 @@ def render_frame(ctx, dims, ws, bs, height, width, normalized_K, c2w_pose, n_sam
     return render_rays(ctx, dims, ws, bs, o, d, np.ascontiguousarray(t), pe_bands, path=path).reshape(height, width, 3)
 
 
+def render_frame_device(ctx, dims, ws_dev, bs_dev, height, width, normalized_K, c2w_pose, n_samples, pe_bands, near=2.0, far=6.0,
+                        path="tc", out_u8=None, color=None, rays_per_call=None):
+    """One frame with NOTHING per ray crossing the bus: the pose goes in (camera mode: rays and the linspace depths of
+    train_nerf.py:589-605 are generated inside the kernels), a uint8 H x W x 3 frame (torch cuda tensor) comes out.
+    ws_dev / bs_dev are cuda tensors in the padded layout."""
+    import torch
+    from . import api
+    n = height * width
+    dev = ws_dev.device
+    color = torch.empty((n, 3), dtype=torch.float32, device=dev) if color is None else color
+    step = n if rays_per_call is None else int(rays_per_call)
+    for r0 in range(0, n, step):
+        r1 = min(n, r0 + step)
+        cam = api.make_camera(c2w_pose, normalized_K, width, height, near=near, far=far, first_pixel=r0)
+        ctx.nerf_step_camera(dims, cam, r1 - r0, n_samples, pe_bands, ws_dev, bs_dev, target=None, grad=False,
+                             outputs=("color",), out={"color": color[r0:r1]}, path=path)
+    return ctx.color_to_u8(color, out_u8).reshape(height, width, 3)
+
+
 def save_weights(prefix, ws_padded, bs_padded):
     """The padded (L,max_in,max_out) / (L,max_out) float32 arrays as models/weights.npy /
     models/biases.npy hold them (the save the reference has commented out, train_nerf.py:559-564)."""

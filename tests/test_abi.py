@@ -55,10 +55,32 @@ def test_struct_mirror_matches_c_layout(lib):
     A = L.LnbStepArgs
     mine = [ctypes.sizeof(L.LnbMlp), ctypes.sizeof(A), A.X.offset, A.inter.offset, A.rgba.offset,
             A.loss.offset, A.want_grad.offset, A.d_ws.offset, A.path.offset, A.rays_o.offset,
-            A.pe_bands.offset]
+            A.pe_bands.offset, A.cam.offset, ctypes.sizeof(L.LnbCamera), L.LnbCamera.pixels.offset]
     assert n == len(mine)
     assert list(out[:n]) == mine
-    assert lib.lnb_abi_version() == 2
+    assert lib.lnb_abi_version() == 3
+
+
+def test_counter_based_jitter_generator_matches_its_restatement(lib):
+    """lnb_uniform (host-callable, the generator camera mode's stratified depths use): SplitMix64 finaliser over
+    (seed, pixel, sample), 24 bits -- restated here in numpy uint64 arithmetic."""
+    import numpy as np
+
+    def mix(seed, q, s):
+        with np.errstate(over="ignore"):
+            z = np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * (np.uint64(q) * np.uint64(4096) + np.uint64(s) + np.uint64(1))
+            z ^= z >> np.uint64(30); z *= np.uint64(0xBF58476D1CE4E5B9)
+            z ^= z >> np.uint64(27); z *= np.uint64(0x94D049BB133111EB)
+            z ^= z >> np.uint64(31)
+        return float(int(z) >> 40) / 16777216.0
+    rng = np.random.default_rng(3)
+    us = []
+    for _ in range(200):
+        seed, q, s = int(rng.integers(0, 2 ** 62)), int(rng.integers(0, 640000)), int(rng.integers(0, 192))
+        u = lib.lnb_uniform(seed, q, s)
+        assert u == mix(seed, q, s) and 0.0 <= u < 1.0
+        us.append(u)
+    assert 0.4 < np.mean(us) < 0.6
 
 
 def test_compile_shim_binds_reference_argtypes(lib):
