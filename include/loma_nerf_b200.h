@@ -35,7 +35,7 @@ extern "C" {
 #define LNB_API
 #endif
 
-#define LNB_ABI_VERSION 3
+#define LNB_ABI_VERSION 4
 #define LNB_MAX_LAYERS 16
 
 /* ------------------------------------------------------------------------------------------
@@ -294,6 +294,15 @@ LNB_API int lnb_trainer_step(lnb_trainer *t, const lnb_step_args *batch, int ner
 /* the same step with the batch in HOST memory (pinned buffers are copied from directly): stages
  * host->device, steps, returns the loss through *loss_out; synchronous */
 LNB_API int lnb_trainer_step_host(lnb_trainer *t, const lnb_step_args *batch, int nerf, float *loss_out);
+/* PIPELINED host-buffer steps (the hosts' chunk loop, train_nerf.py:275-499, with the copy of batch i+1 under the step
+ * of batch i): lnb_trainer_submit_host stages the batch on a copy stream into one of two device staging slots, enqueues the
+ * step behind it and returns without waiting for the GPU.  Pinned host buffers are read by the DMA engine directly and must
+ * stay unchanged until the submission after next has returned (or until lnb_trainer_wait); pageable buffers are copied to a
+ * pinned bounce slot before the call returns.  lnb_trainer_wait blocks until every submitted step has finished and copies
+ * the losses of the steps submitted since the previous wait, oldest first, into losses[0 .. *n_out) (at most max_losses of
+ * the newest 4096; losses may be NULL).  Errors of a poisoned peer exchange surface at lnb_trainer_wait. */
+LNB_API int lnb_trainer_submit_host(lnb_trainer *t, const lnb_step_args *batch, int nerf);
+LNB_API int lnb_trainer_wait(lnb_trainer *t, float *losses, int max_losses, int *n_out);
 LNB_API int lnb_trainer_grad(lnb_trainer *t, const lnb_step_args *batch, int nerf);
 LNB_API int lnb_trainer_apply(lnb_trainer *t);
 LNB_API float *lnb_trainer_grad_buffer(lnb_trainer *t, long long *n_floats);

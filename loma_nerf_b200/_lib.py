@@ -115,6 +115,8 @@ def load():
     for name in ("lnb_trainer_step", "lnb_trainer_grad"):
         getattr(lib, name).argtypes = [c_void_p, P(LnbStepArgs), c_int]
     lib.lnb_trainer_step_host.argtypes = [c_void_p, P(LnbStepArgs), c_int, P(c_float)]
+    lib.lnb_trainer_submit_host.argtypes = [c_void_p, P(LnbStepArgs), c_int]
+    lib.lnb_trainer_wait.argtypes = [c_void_p, P(c_float), c_int, P(c_int)]
     lib.lnb_trainer_comm_export.argtypes = [c_void_p, c_void_p]
     lib.lnb_trainer_comm_attach.argtypes = [c_void_p, c_int, c_int, c_void_p]
     lib.lnb_trainer_comm_status.argtypes = [c_void_p]

@@ -426,6 +426,20 @@ class Trainer:
         self.ctx._check(self.lib.lnb_trainer_step_host(self.h, ctypes.byref(a), nerf, ctypes.byref(loss)))
         return float(loss.value)
 
+    def submit_host(self, **batch):
+        """step_host() without the wait: the batch is staged on a copy stream while the previous step still runs
+        (lnb_trainer_submit_host).  Pinned host buffers must stay unchanged until the submission after next."""
+        a, nerf = self._batch(**batch)
+        self._keep = (self.__dict__.get("_keep", []) + [batch])[-3:]
+        self.ctx._check(self.lib.lnb_trainer_submit_host(self.h, ctypes.byref(a), nerf))
+
+    def wait(self, max_losses=4096):
+        """Block until every submitted step is done; losses of the steps submitted since the last wait (oldest first)."""
+        buf = (ctypes.c_float * max_losses)()
+        n = ctypes.c_int()
+        self.ctx._check(self.lib.lnb_trainer_wait(self.h, buf, max_losses, ctypes.byref(n)))
+        return [float(buf[i]) for i in range(n.value)]
+
     def grad(self, **batch):
         """forward + backward only: gradients (and loss) land in grad_buffer()."""
         a, nerf = self._batch(**batch)

@@ -30,6 +30,17 @@ struct lnb_trainer {
     size_t comm_bytes = 0;
     lnb_tc_comm comm{};
     void *peer_base[8] = {};
+    // pipelined host-buffer steps (lnb_trainer_submit_host / lnb_trainer_wait)
+    struct Pipe {
+        static constexpr int RING = 4096;
+        cudaStream_t copy_stream = nullptr;
+        cudaEvent_t staged[2] = {}, consumed[2] = {};
+        char *dslot[2] = {}, *pslot[2] = {};
+        size_t dcap = 0, pcap = 0;
+        float *loss_ring = nullptr;
+        int pending = 0;
+        long long seq = 0;
+    } pipe;
 };
 
 static int comm_slots(const lnb_trainer *t)
@@ -83,6 +94,16 @@ extern "C" void lnb_trainer_destroy(lnb_trainer *t)
     for (int r = 0; r < 8; ++r)
         if (t->peer_base[r]) cudaIpcCloseMemHandle(t->peer_base[r]);
     if (t->comm_buf) cudaFree(t->comm_buf);
+    if (t->pipe.copy_stream) {
+        cudaStreamSynchronize(t->pipe.copy_stream);
+        cudaStreamDestroy(t->pipe.copy_stream);
+        for (int s = 0; s < 2; ++s) {
+            cudaEventDestroy(t->pipe.staged[s]); cudaEventDestroy(t->pipe.consumed[s]);
+            if (t->pipe.dslot[s]) cudaFree(t->pipe.dslot[s]);
+            if (t->pipe.pslot[s]) cudaFreeHost(t->pipe.pslot[s]);
+        }
+        cudaFreeHost(t->pipe.loss_ring);
+    }
     cudaFree(t->params); cudaFree(t->grads); cudaFree(t->m); cudaFree(t->v); cudaFree(t->t_dev);
     if (t->wimg) cudaFree(t->wimg);
     delete t;
@@ -170,6 +191,46 @@ extern "C" int lnb_trainer_apply(lnb_trainer *t)
     return lnb_launch_adam_dev(ctx, t->params, t->grads, t->m, t->v, np, t->t_dev, t->lr, t->b1, t->b2, t->eps);
 }
 
+// ---- host-buffer steps ---------------------------------------------------------------------------
+// The batch's inputs as (pointer slot, bytes) pairs; `a` is the caller's batch copied, `cam_dev` the
+// copy of its camera (camera mode: only the optional pixel list and the targets cross the bus).
+struct HostIn { const void **slot; size_t bytes; };
+static int host_inputs(lnb_trainer *t, lnb_step_args &a, lnb_camera &cam_dev, int nerf, HostIn *ins, int *n_in_out)
+{
+    lnb_ctx *ctx = t->ctx;
+    const size_t R = (size_t)a.R, S = nerf ? (size_t)a.S : 1, N = a.n_rows > 0 ? (size_t)a.n_rows : R * S;
+    const size_t c_in = (size_t)t->mlp.dims[0], Wt = a.target_w > 0 ? (size_t)a.target_w : 3;
+    const bool rays = !a.X && a.rays_o;
+    const bool cam = !a.X && !a.rays_o && a.cam;
+    const size_t rw = a.ray_dtype == LNB_RAY_F64 ? 8 : 4;
+    int n_in = 0;
+    if (cam) {
+        cam_dev = *a.cam;
+        a.cam = &cam_dev;
+        if (cam_dev.pixels) ins[n_in++] = HostIn{(const void **)&cam_dev.pixels, R * sizeof(int)};
+    } else if (rays) {
+        ins[n_in++] = HostIn{&a.rays_o, R * 3 * rw};
+        ins[n_in++] = HostIn{&a.rays_d, R * 3 * rw};
+        ins[n_in++] = HostIn{&a.t, R * S * rw};
+    } else {
+        LNB_ARG(a.X, "trainer: X or rays required");
+        ins[n_in++] = HostIn{(const void **)&a.X, N * c_in * 4};
+        if (nerf) { LNB_ARG(a.dists, "trainer: dists required"); ins[n_in++] = HostIn{(const void **)&a.dists, R * S * 4}; }
+    }
+    LNB_ARG(a.target, "trainer: target required");
+    ins[n_in++] = HostIn{(const void **)&a.target, R * Wt * 4};
+    *n_in_out = n_in;
+    return LNB_OK;
+}
+
+static bool host_pinned(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost) return true;
+    cudaGetLastError();
+    return false;
+}
+
 // Host-buffer step: stages the batch (pinned buffers are copied directly, pageable ones bounce
 // through the context's pinned block), runs lnb_trainer_step, returns the loss.  Synchronous.
 extern "C" int lnb_trainer_step_host(lnb_trainer *t, const lnb_step_args *batch, int nerf, float *loss_out)
@@ -179,36 +240,15 @@ extern "C" int lnb_trainer_step_host(lnb_trainer *t, const lnb_step_args *batch,
     LNB_ARG(batch, "trainer: null batch");
     if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
     lnb_step_args a = *batch;
-    const size_t R = (size_t)a.R, S = nerf ? (size_t)a.S : 1, N = a.n_rows > 0 ? (size_t)a.n_rows : R * S;
-    const size_t c_in = (size_t)t->mlp.dims[0], Wt = a.target_w > 0 ? (size_t)a.target_w : 3;
-    const bool rays = !a.X && a.rays_o;
-    const bool cam = !a.X && !a.rays_o && a.cam;
-    const size_t rw = a.ray_dtype == LNB_RAY_F64 ? 8 : 4;
-    struct In { const void **slot; size_t bytes; };
-    In ins[6];
+    lnb_camera cam_dev;
+    HostIn ins[6];
     int n_in = 0;
-    lnb_camera cam_dev;   // camera mode: nothing per ray but the optional pixel list and the targets crosses the bus
-    if (cam) {
-        cam_dev = *a.cam;
-        a.cam = &cam_dev;
-        if (cam_dev.pixels) ins[n_in++] = In{(const void **)&cam_dev.pixels, R * sizeof(int)};
-    } else if (rays) {
-        ins[n_in++] = In{&a.rays_o, R * 3 * rw};
-        ins[n_in++] = In{&a.rays_d, R * 3 * rw};
-        ins[n_in++] = In{&a.t, R * S * rw};
-    } else {
-        LNB_ARG(a.X, "trainer: X or rays required");
-        ins[n_in++] = In{(const void **)&a.X, N * c_in * 4};
-        if (nerf) { LNB_ARG(a.dists, "trainer: dists required"); ins[n_in++] = In{(const void **)&a.dists, R * S * 4}; }
-    }
-    LNB_ARG(a.target, "trainer: target required");
-    ins[n_in++] = In{(const void **)&a.target, R * Wt * 4};
+    LNB_TRY(host_inputs(t, a, cam_dev, nerf, ins, &n_in));
     size_t dtotal = 0, ptotal = 0;
     bool direct[6];
     for (int i = 0; i < n_in; ++i) {
-        cudaPointerAttributes at;
-        direct[i] = cudaPointerGetAttributes(&at, *ins[i].slot) == cudaSuccess && at.type == cudaMemoryTypeHost;
-        if (!direct[i]) { cudaGetLastError(); ptotal += (ins[i].bytes + 255) / 256 * 256 + 256; }
+        direct[i] = host_pinned(*ins[i].slot);
+        if (!direct[i]) ptotal += (ins[i].bytes + 255) / 256 * 256 + 256;
         dtotal += (ins[i].bytes + 255) / 256 * 256;
     }
     if (dtotal + 256 > ctx->dstage_cap) {
@@ -240,6 +280,111 @@ extern "C" int lnb_trainer_step_host(lnb_trainer *t, const lnb_step_args *batch,
     LNB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (loss_out) *loss_out = *pl;
     if (t->comm.world > 1 && *reinterpret_cast<const int *>(pl + 1) != 0) return comm_failed(t, loss_out);
+    return LNB_OK;
+}
+
+// Pipelined host-buffer steps.  Two device staging slots and a copy stream: the host->device copy of
+// batch i+1 runs under the step of batch i, and nothing waits for the GPU until lnb_trainer_wait.
+//   copy stream : wait(consumed[slot]) -> H2D of the batch -> record(staged[slot])
+//   step stream : wait(staged[slot])   -> the step -> D2H of its loss into a pinned ring -> record(consumed[slot])
+// Pageable host buffers are copied into a pinned bounce slot at once (the call then waits for the H2D
+// that last read that slot, two submissions ago); pinned buffers are read by the DMA engine directly
+// and must stay unchanged until the submission after next has returned (or lnb_trainer_wait).
+extern "C" int lnb_trainer_submit_host(lnb_trainer *t, const lnb_step_args *batch, int nerf)
+{
+    if (!t) return LNB_ERR_ARG;
+    lnb_ctx *ctx = t->ctx;
+    LNB_ARG(batch, "trainer: null batch");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
+    lnb_trainer::Pipe &pp = t->pipe;
+    if (!pp.copy_stream) {
+        LNB_CUDA(cudaStreamCreateWithFlags(&pp.copy_stream, cudaStreamNonBlocking));
+        for (int s = 0; s < 2; ++s) {
+            LNB_CUDA(cudaEventCreateWithFlags(&pp.staged[s], cudaEventDisableTiming));
+            LNB_CUDA(cudaEventCreateWithFlags(&pp.consumed[s], cudaEventDisableTiming));
+        }
+        LNB_CUDA(cudaMallocHost((void **)&pp.loss_ring, lnb_trainer::Pipe::RING * sizeof(float)));
+    }
+    if (pp.pending == lnb_trainer::Pipe::RING) {   // the ring of undelivered losses is full: drain the GPU, keep the newest
+        LNB_CUDA(cudaStreamSynchronize(ctx->stream));
+        pp.pending = 0;
+    }
+    lnb_step_args a = *batch;
+    lnb_camera cam_dev;
+    HostIn ins[6];
+    int n_in = 0;
+    LNB_TRY(host_inputs(t, a, cam_dev, nerf, ins, &n_in));
+    const int slot = (int)(pp.seq & 1);
+    size_t dtotal = 0, ptotal = 0;
+    bool direct[6];
+    for (int i = 0; i < n_in; ++i) {
+        direct[i] = host_pinned(*ins[i].slot);
+        if (!direct[i]) ptotal += (ins[i].bytes + 255) / 256 * 256;
+        dtotal += (ins[i].bytes + 255) / 256 * 256;
+    }
+    if (dtotal > pp.dcap || ptotal > pp.pcap) {    // grow (rare): drain both streams first
+        LNB_CUDA(cudaStreamSynchronize(pp.copy_stream));
+        LNB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (dtotal > pp.dcap) {
+            const size_t cap = (dtotal + dtotal / 4 + (1 << 20)) / (1 << 20) * (1 << 20);
+            for (int s = 0; s < 2; ++s) {
+                if (pp.dslot[s]) LNB_CUDA(cudaFree(pp.dslot[s]));
+                pp.dslot[s] = nullptr;
+                LNB_CUDA(cudaMalloc((void **)&pp.dslot[s], cap));
+            }
+            pp.dcap = cap;
+        }
+        if (ptotal > pp.pcap) {
+            const size_t cap = (ptotal + ptotal / 4 + (1 << 20)) / (1 << 20) * (1 << 20);
+            for (int s = 0; s < 2; ++s) {
+                if (pp.pslot[s]) LNB_CUDA(cudaFreeHost(pp.pslot[s]));
+                pp.pslot[s] = nullptr;
+                LNB_CUDA(cudaMallocHost((void **)&pp.pslot[s], cap));
+            }
+            pp.pcap = cap;
+        }
+    }
+    if (ptotal && pp.seq >= 2) LNB_CUDA(cudaEventSynchronize(pp.staged[slot]));   // the DMA that last read this bounce slot
+    if (pp.seq >= 2) LNB_CUDA(cudaStreamWaitEvent(pp.copy_stream, pp.consumed[slot], 0));
+    size_t off = 0, poff = 0;
+    for (int i = 0; i < n_in; ++i) {
+        const void *src = *ins[i].slot;
+        if (!direct[i]) {
+            memcpy(pp.pslot[slot] + poff, src, ins[i].bytes);
+            src = pp.pslot[slot] + poff;
+            poff += (ins[i].bytes + 255) / 256 * 256;
+        }
+        LNB_CUDA(cudaMemcpyAsync(pp.dslot[slot] + off, src, ins[i].bytes, cudaMemcpyHostToDevice, pp.copy_stream));
+        *ins[i].slot = pp.dslot[slot] + off;
+        off += (ins[i].bytes + 255) / 256 * 256;
+    }
+    LNB_CUDA(cudaEventRecord(pp.staged[slot], pp.copy_stream));
+    LNB_CUDA(cudaStreamWaitEvent(ctx->stream, pp.staged[slot], 0));
+    LNB_TRY(trainer_run(t, &a, nerf, true));
+    LNB_CUDA(cudaMemcpyAsync(pp.loss_ring + pp.pending, t->grads + t->n_w + t->n_b, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    LNB_CUDA(cudaEventRecord(pp.consumed[slot], ctx->stream));
+    pp.pending++;
+    pp.seq++;
+    return LNB_OK;
+}
+
+// Waits for every submitted step; copies the losses of the steps submitted since the previous wait
+// (oldest first, at most max_losses of the newest RING) and returns their number through *n_out.
+extern "C" int lnb_trainer_wait(lnb_trainer *t, float *losses, int max_losses, int *n_out)
+{
+    if (!t) return LNB_ERR_ARG;
+    lnb_ctx *ctx = t->ctx;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return LNB_ERR_CUDA;
+    lnb_trainer::Pipe &pp = t->pipe;
+    int st = 0;
+    if (t->comm.world > 1) LNB_CUDA(cudaMemcpyAsync(&st, t->comm.status, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    LNB_CUDA(cudaStreamSynchronize(ctx->stream));
+    int n = pp.pending;
+    if (n > max_losses) n = max_losses < 0 ? 0 : max_losses;
+    if (losses) for (int i = 0; i < n; ++i) losses[i] = pp.loss_ring[pp.pending - n + i];
+    if (n_out) *n_out = n;
+    pp.pending = 0;
+    if (st != 0) return comm_failed(t, nullptr);
     return LNB_OK;
 }
 

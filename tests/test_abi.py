@@ -58,7 +58,7 @@ def test_struct_mirror_matches_c_layout(lib):
             A.pe_bands.offset, A.cam.offset, ctypes.sizeof(L.LnbCamera), L.LnbCamera.pixels.offset]
     assert n == len(mine)
     assert list(out[:n]) == mine
-    assert lib.lnb_abi_version() == 3
+    assert lib.lnb_abi_version() == 4
 
 
 def test_counter_based_jitter_generator_matches_its_restatement(lib):

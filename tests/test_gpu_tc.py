@@ -267,3 +267,43 @@ def test_trainer_takes_an_empty_batch_and_a_batch_the_fused_kernel_cannot(ctx, t
     assert rel_err(loss, f["loss"]) <= TC_TOL
     assert np.isfinite(w).all() and np.abs(w - case["ws"]).max() > 0            # the update happened (t = 2)
     tr.close()
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_pipelined_host_steps_equal_the_synchronous_ones(ctx, torch_cuda, pinned):
+    """lnb_trainer_submit_host / lnb_trainer_wait (H2D of batch i+1 under step i, two staging slots) must walk exactly the
+    trajectory of lnb_trainer_step_host: same losses, bit-identical weights, features and rays batches interleaved."""
+    torch = torch_cuda
+    from loma_nerf_b200 import api
+    R, S, E = 128, 64, 5
+    cases = [O.make_nerf_case(1200 + i, R, S) for i in range(7)]
+    dims = [int(v) for v in cases[0]["dims"]]
+    ws0, bs0 = cases[0]["ws"].copy(), cases[0]["bs"].copy()
+
+    def hostbuf(a, dt=np.float32):
+        a = np.ascontiguousarray(a, dt)
+        return torch.as_tensor(a).pin_memory() if pinned else a
+
+    batches = []
+    for i, c in enumerate(cases):
+        if i % 3 == 2:
+            batches.append(dict(rays=tuple(hostbuf(c[k], np.float64) for k in ("rays_o", "rays_d", "t")), pe_bands=E,
+                                target=hostbuf(c["target"]), path="tc"))
+        else:
+            batches.append(dict(X=hostbuf(c["X"]), dists=hostbuf(c["dists"]), target=hostbuf(c["target"]), path="tc"))
+    ta = api.Trainer(ctx, dims, ws0, bs0)
+    want = [ta.step_host(**b) for b in batches]
+    wa, ba, _ = ta.read()
+    ta.close()
+    tb = api.Trainer(ctx, dims, ws0, bs0)
+    for b in batches[:3]:
+        tb.submit_host(**b)
+    got = tb.wait()
+    for b in batches[3:]:
+        tb.submit_host(**b)
+    got += tb.wait()
+    assert tb.wait() == []
+    wb, bb, _ = tb.read()
+    tb.close()
+    assert got == want, (got, want)
+    assert np.array_equal(wa, wb) and np.array_equal(ba, bb)
