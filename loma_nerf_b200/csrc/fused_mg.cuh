@@ -1,0 +1,560 @@
+// fused_mg.cuh -- the fused tensor-core TRAIN step, multi-group form.  Included by fused_tc.cu inside its anonymous
+// namespace (PTX wrappers, TcParams, TcLayout, SLAB / TILE / MAXL come from there).
+//
+// Why: a 128-sample tile takes ~10 000 cycles from features to weight gradients even alone on an SM (six dependent
+// tcgen05 stages at ~555 + 145 g cycles each, three scans, five epilogues), a 4096 x 64 batch is only 13.8 tiles per
+// SM, and fused_v1_kernel keeps 46 KB of activations + adjoints per tile alive, so 3-4 tiles share an SM and the launch
+// is ceil(13.8 / 4) = 4-5 tile latencies long (measured: 39 us; the same kernel on a batch 8 x larger needs 25.8 us per
+// 262 144 samples).  What helps is MORE TILES IN FLIGHT, i.e. less shared memory and TMEM per tile:
+//   * ONE persistent CTA per SM holds up to seven independent 128-thread GROUPS; a group is what a CTA of the first
+//     kernel was (thread r owns sample row r = TMEM lane r of the group's accumulator columns), synchronised with its
+//     own named barrier and its own mbarriers.  The bf16 weight image is loaded once per SM instead of once per tile slot.
+//   * adjoints are written IN PLACE: dZ_{l-1} = relu'(A_l) . dH_l has the shape of A_l and overwrites it, so a slot is
+//     A_0 | dZ_{L-1} | A_1 .. A_{L-1} = 28 KB for the 33 -> 30 -> 30 -> 4 network instead of 46 KB.  The price: the
+//     weight gradient of layer l, dW_l = A_l^T dZ_l, must be issued while both still exist -- per layer, next to the
+//     dH_l MMAs, by the elected lanes of warps 1-3 (two or three K-steps each, so nobody issues for long) -- and the
+//     in-place store waits for it (by then the epilogue arithmetic has hidden most of its latency).
+//   * ALL groups accumulate their weight gradients into ONE set of TMEM columns (zeroed once with tcgen05.st; every
+//     MMA accumulates): 7 x 32 result columns + 80 gradient columns = 304 of the SM's 512, one partial per SM.
+//   * features mode: the fp32 tile is brought by one bulk-async copy into the slot's A_1.. region, which is dead between
+//     the previous tile's last weight-gradient MMA and this tile's first epilogue -- no staging buffer.
+// Forward-only launches (render) keep fused_v1_kernel: nothing is kept for a gradient there and nine 16 KB tiles
+// already fit an SM.
+
+constexpr int MG_MAX_GROUPS = 7;
+constexpr int MG_MISC = 2304;       // per group: colour / target scratch, scan carries, mbarriers, MMA program
+constexpr int MG_GLOBALS = 64;      // per CTA: weight-image mbarrier, TMEM base
+
+template <int HP>
+struct MgLayout {
+    using LY = TcLayout<HP>;
+    static constexpr int HSL = HP / 8;
+    __host__ __device__ static int a0s(int c_in) { return (c_in + 8) >> 3; }   // slabs holding features 0..c_in (ones column included)
+    // slot: A_0 [a0s] | dZ_{L-1} [1] | A_1 [HSL] .. A_{L-1} [HSL].  A K-padding read past A_0 lands in the dZ slab and one past
+    // the dZ slab in A_1: bf16 values a previous stage wrote (finite), never raw fp32 staging bytes.
+    __host__ __device__ static int dzl_off(int A0S) { return A0S * SLAB; }
+    __host__ __device__ static int a_off(int l, int A0S) { return l == 0 ? 0 : (A0S + 1 + (l - 1) * HSL) * SLAB; }
+    __host__ __device__ static int slot_bytes(int L, int c_in, int K0P, bool rays)
+    {
+        const int A0S = a0s(c_in);
+        int nat = (A0S + 1 + (L - 1) * HSL) * SLAB;
+        if (!rays) {   // the fp32 tile is staged from A_1 on
+            const int need = a_off(1, A0S) + LY::stage_bytes(c_in, K0P);
+            if (need > nat) nat = (need + 1023) / 1024 * 1024;
+        }
+        return nat;
+    }
+    __host__ __device__ static int ndw(int L) { return (L - 1) * HP + 16; }
+    __host__ __device__ static int tmem_need(int L, int ng) { return ng * HP + ndw(L); }
+    __host__ __device__ static size_t total(int L, int c_in, int K0P, bool rays, int ng)
+    {
+        const int A0S = a0s(c_in);
+        const size_t slot = (size_t)slot_bytes(L, c_in, K0P, rays);
+        const size_t t = ng * slot + LY::wimg_bytes(L, K0P) + MG_GLOBALS + (size_t)ng * MG_MISC;
+        // a weight-gradient MMA reads 8 slabs (M = 64 feature rows) from the start of A_l whatever its real width (the rows
+        // beyond are never read back): the last group's last such read must stay inside the allocation
+        const size_t need = (ng - 1) * slot + a_off(L - 1, A0S) + 8 * SLAB;
+        return t > need ? t : need;
+    }
+};
+
+__device__ __forceinline__ void bar_group(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(TILE) : "memory"); }
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int HP> constexpr int mg_max_groups() { return HP <= 32 ? MG_MAX_GROUPS : 4; }   // registers: 64 K / (groups x 128 threads)
+
+template <bool RAYS, int HP>
+__global__ void __launch_bounds__(mg_max_groups<HP>() * TILE, 1) fused_mg_kernel(const TcParams p)
+{
+    using LY = TcLayout<HP>;
+    using MG = MgLayout<HP>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int NG = (int)blockDim.x / TILE;
+    const int g = (int)threadIdx.x / TILE, tid = (int)threadIdx.x % TILE, warp = tid >> 5, lane = tid & 31;
+    const int L = p.L, K0P = p.K0P, c_in = p.dims[0], S = p.S;
+    const int A0S = MG::a0s(c_in);
+    const int slot_bytes = MG::slot_bytes(L, c_in, K0P, RAYS);
+    uint8_t *const slot = smem + (size_t)g * slot_bytes;
+    uint8_t *const Wbase = smem + (size_t)NG * slot_bytes;
+    const float *const bias_s = reinterpret_cast<const float *>(Wbase + LY::w_off(L, L, K0P));
+    uint8_t *const globals = Wbase + LY::wimg_bytes(L, K0P);
+    uint8_t *const misc = globals + MG_GLOBALS + (size_t)g * MG_MISC;
+    float *const stage = reinterpret_cast<float *>(slot + MG::a_off(1, A0S));   // features mode: fp32 tile, dead A_1.. region
+    float *const color_s = reinterpret_cast<float *>(misc);     // [64][3]
+    float *const tgt_s = color_s + 192;                         // [64][3]
+    float *const tailp = tgt_s + 192;                           // [4] inclusive product at lane 31
+    int *const tail_s = reinterpret_cast<int *>(tailp + 4);     // [4] sample index at lane 31
+    float *const headq = tailp + 8;                             // [5] q at lane 0 of each warp
+    float *const headA = tailp + 13;                            // [5]
+    float *const headB = tailp + 18;                            // [5]
+    float *const red_s = tailp + 24;                            // [4]
+    int *const next_tile_s = reinterpret_cast<int *>(tailp + 28);
+    uint64_t *const bar_p = reinterpret_cast<uint64_t *>(misc + 1664);
+    const uint32_t bar_mma = smem_u32(bar_p), bar_x = smem_u32(bar_p + 1), bar_dw = smem_u32(bar_p + 2);
+    const uint32_t bar_w = smem_u32(globals);
+    uint32_t *const tmem_slot = reinterpret_cast<uint32_t *>(globals + 8);
+    struct StageRec { uint64_t a, b; uint32_t inc_a, inc_b, idesc, dcol; uint32_t count, first_acc, pad0, pad1; };
+    StageRec *const prog = reinterpret_cast<StageRec *>(misc + 1728);   // fwd l | dH l (L + l) | dW l (2L + l)
+
+    auto a_buf = [&](int l) { return slot + MG::a_off(l, A0S); };
+    uint8_t *const dzl_buf = slot + MG::dzl_off(A0S);
+    // where the adjoint dZ_l lives: the last layer's in its own slab, the others in place of A_{l+1}
+    auto dz_buf = [&](int l) { return l == L - 1 ? dzl_buf : a_buf(l + 1); };
+
+    // TMA source of a tile's features (16 B aligned start, `lead` floats in front of the tile)
+    auto x_src = [&](int tile, int &lead, uint32_t &bytes) -> const void * {
+        const long long row0 = (long long)tile * p.rows_per_tile;
+        long long rem = p.N - row0;
+        const int valid = rem < p.rows_per_tile ? (int)rem : p.rows_per_tile;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p.X + row0 * c_in);
+        const uintptr_t a16 = a & ~(uintptr_t)15;
+        lead = (int)((a - a16) >> 2);
+        bytes = (uint32_t)(((a - a16) + (uintptr_t)valid * c_in * 4 + 15) & ~(uintptr_t)15);
+        return reinterpret_cast<const void *>(a16);
+    };
+
+    // ---- one-time setup: zero every slot (padding features and K-padding reads must see zeros / finite values)
+    for (uint8_t *z = smem + (size_t)threadIdx.x * 16; z < Wbase; z += (size_t)blockDim.x * 16) *reinterpret_cast<uint4 *>(z) = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        mbar_init(bar_mma, 1);
+        mbar_init(bar_x, 1);
+        mbar_init(bar_dw, 3);          // the three threads that issue a layer's weight-gradient MMAs
+        if (g == 0) mbar_init(bar_w, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t dcol = (uint32_t)(g * HP);
+        for (int l = 0; l < L; ++l) {          // D[128 x Np] = A_l[128 x Kp] * W_l   (A, B K-major)
+            const int Np = LY::np(l, L), Kp = LY::kp(l, K0P);
+            const uint32_t a0 = smem_u32(a_buf(l)), b0 = smem_u32(Wbase + LY::w_off(l, L, K0P));
+            prog[l] = StageRec{smem_desc(a0, SLAB, 128), smem_desc(b0, Np * 16, 128), (uint32_t)(2 * SLAB) >> 4, (uint32_t)(2 * Np * 16) >> 4,
+                               instr_desc(128, Np, 0, 0), dcol, (uint32_t)(Kp / 16), 0u, 0u, 0u};
+        }
+        for (int l = 1; l < L; ++l) {          // dH_l[128 x Kp] = dZ_l[128 x Np] * W_l^T (same W bytes, MN-major)
+            const int Np = LY::np(l, L), Kp = LY::kp(l, K0P);
+            const uint32_t a0 = smem_u32(dz_buf(l)), b0 = smem_u32(Wbase + LY::w_off(l, L, K0P));
+            prog[L + l] = StageRec{smem_desc(a0, SLAB, 128), smem_desc(b0, 128, Np * 16), (uint32_t)(2 * SLAB) >> 4, 256u >> 4,
+                                   instr_desc(128, Kp, 0, 1), dcol, (uint32_t)(Np / 16), 0u, 0u, 0u};
+        }
+        for (int l = 0; l < L; ++l) {          // dW_l[features x Np] += A_l^T dZ_l, K = the tile's 128 samples, both MN-major
+            const uint32_t a0 = smem_u32(a_buf(l)), b0 = smem_u32(dz_buf(l));
+            prog[2 * L + l] = StageRec{smem_desc(a0, 128, SLAB), smem_desc(b0, 128, SLAB), 256u >> 4, 256u >> 4,
+                                       instr_desc(64, LY::np(l, L), 1, 1), (uint32_t)(NG * HP + l * HP), (uint32_t)(TILE / 16), 1u, 0u, 0u};
+        }
+    }
+    const int tmem_need = MG::tmem_need(L, NG);
+    const uint32_t tmem_cols = tmem_need <= 32 ? 32u : (tmem_need <= 64 ? 64u : (tmem_need <= 128 ? 128u : (tmem_need <= 256 ? 256u : 512u)));
+    if (g == 0 && warp == 0) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    // the shared weight-gradient accumulator starts at zero; every MMA into it accumulates
+    if (g == 0) {
+        for (int c = 0; c < MG::ndw(L); c += 16) tmem_st16_zero(tmem + lane_base + (uint32_t)(NG * HP + c));
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    // Programmatic dependent launch: everything above overlaps the tail of the previous kernel in the stream; from here on
+    // we read what it produced (weight image, tile counter).  No-op without PDL.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (threadIdx.x == 0) {
+        const uint32_t wb = (uint32_t)LY::wimg_bytes(L, K0P);
+        mbar_expect_tx(bar_w, wb);
+        bulk_g2s(smem_u32(Wbase), p.wimg, wb, bar_w);
+    }
+    __syncthreads();
+    tc_fence_after();
+    uint32_t phase = 0, xphase = 0, dwphase = 0;
+    float loss_acc = 0.0f;
+    bool dw_pending = false;
+    mbar_wait(bar_w, 0); // weights + biases have landed
+
+    auto row_ptr = [&](uint8_t *buf, int slab) { return reinterpret_cast<uint4 *>(buf + slab * SLAB + tid * 16); };
+    // issue K-steps [k0, k1) of one stage of the MMA program (one thread)
+    auto issue_steps = [&](int stage_id, uint32_t k0, uint32_t k1) {
+        const uint4 r0 = *reinterpret_cast<const uint4 *>(prog + stage_id);
+        const uint4 r1 = *(reinterpret_cast<const uint4 *>(prog + stage_id) + 1);
+        const uint4 r2 = *(reinterpret_cast<const uint4 *>(prog + stage_id) + 2);
+        if (k1 > r2.x) k1 = r2.x;
+        uint32_t alo = r0.x + k0 * r1.x, blo = r0.z + k0 * r1.y;
+        const uint32_t ahi = r0.y, bhi = r0.w;
+        uint32_t acc = (k0 > 0) ? 1u : r2.y;
+        const uint32_t d = tmem + r1.w;
+        for (uint32_t k = k0; k < k1; ++k) {
+            umma_bf16(d, ((uint64_t)ahi << 32) | alo, ((uint64_t)bhi << 32) | blo, r1.z, acc);
+            alo += r1.x; blo += r1.y; acc = 1u;
+        }
+    };
+    auto commit_and_wait = [&]() {
+        if (tid == 0) umma_commit(bar_mma);
+        mbar_wait(bar_mma, phase);
+        phase ^= 1;
+        tc_fence_after();
+    };
+    auto publish_smem = [&]() { // generic-proxy smem writes -> visible to the tensor core, all threads of the group
+        fence_async_smem();
+        tc_fence_before();
+        bar_group(g);
+        tc_fence_after();
+    };
+    // the weight-gradient MMAs of layer l: 8 K-steps of 16 samples, dealt 3 / 3 / 2 to the elected lanes of warps 1-3
+    auto issue_dw = [&](int l) {
+        if (lane == 0 && warp > 0) {
+            const uint32_t k0 = warp == 1 ? 0u : (warp == 2 ? 3u : 6u), k1 = warp == 1 ? 3u : (warp == 2 ? 6u : 8u);
+            issue_steps(2 * L + l, k0, k1);
+            umma_commit(bar_dw);
+        }
+    };
+    auto wait_dw = [&]() { mbar_wait(bar_dw, dwphase); dwphase ^= 1; tc_fence_after(); };
+
+    for (int tile = g * (int)gridDim.x + (int)blockIdx.x; tile < p.n_tiles;) {
+        const long long row0 = (long long)tile * p.rows_per_tile;
+        long long rem = p.N - row0;
+        const int valid = rem < p.rows_per_tile ? (int)rem : p.rows_per_tile;
+        const int rays_here = valid / S;
+        const int smp = tid % S, ray_l = tid / S;        // this thread's sample within its ray
+        const bool live = tid < rays_here * S;
+        // the previous tile's last weight-gradient MMAs read A_0 and A_1's buffer (dZ_0): both are rewritten below
+        if (dw_pending) { wait_dw(); dw_pending = false; }
+        if (!RAYS && tid == 0) {
+            int lead; uint32_t bytes;
+            const void *src = x_src(tile, lead, bytes);
+            mbar_expect_tx(bar_x, bytes);
+            bulk_g2s(smem_u32(stage), src, bytes, bar_x);
+        }
+        // early, latency-tolerant loads for this tile (consumed after the MLP forward)
+        float my_dist = 0.0f, tg0 = 0.0f, tg1 = 0.0f, tg2 = 0.0f;
+        if (p.head == LNB_HEAD_NERF && live) {
+            if (!RAYS) my_dist = __ldg(p.dists + row0 + tid);
+            if (p.target && smp == 0) {
+                const float *tg = p.target + (row0 / S + ray_l) * 3;
+                tg0 = __ldg(tg); tg1 = __ldg(tg + 1); tg2 = __ldg(tg + 2);
+            }
+        }
+        if (tid == 0) *next_tile_s = atomicAdd(p.tile_counter, 1) + (int)gridDim.x * NG;   // read after several group barriers
+        if (RAYS) {
+            // ---- features from rays: pts = o + d t (train_nerf.py:289-299), PE (pos_encoding.py:38-70),
+            // dist = t[s+1] - t[s], last 1e8 (train_nerf.py:306-311); written straight into A_0
+            float x[3] = {0.f, 0.f, 0.f};
+            if (live && p.cam_mode) {
+                // ray of pixel q and depth of sample smp straight from the pose (get_rays, train_nerf.py:23-62; linspace /
+                // stratified depths, train_nerf.py:289-311): no per-ray or per-sample input at all
+                const CamF32 &c = p.cam;
+                const long long ray = row0 / S + ray_l;
+                const long long q = c.pixels ? (long long)__ldg(c.pixels + ray) : c.first_pixel + ray;
+                const unsigned uq = (unsigned)q, col = uq % (unsigned)c.width, row = uq / (unsigned)c.width;
+                const float fi = col == (unsigned)c.width - 1 ? 1.0f : (float)col * c.step, fj = row == (unsigned)c.width - 1 ? 1.0f : (float)row * c.step;
+                const float dx = (fi - c.cx) * c.inv_fx, dy = (c.cy - fj) * c.inv_fy;
+                float tt, tn;
+                if (c.stratified) {
+                    tt = fmaf((float)smp + (float)lnb_uniform_bits(c.seed, q, smp) * (1.0f / 16777216.0f), c.dt_str, c.near);
+                    tn = fmaf((float)(smp + 1) + (float)lnb_uniform_bits(c.seed, q, smp + 1) * (1.0f / 16777216.0f), c.dt_str, c.near);
+                } else {
+                    tt = smp == S - 1 && S > 1 ? c.far : fmaf((float)smp, c.dt_lin, c.near);
+                    tn = smp + 1 == S - 1 ? c.far : fmaf((float)(smp + 1), c.dt_lin, c.near);
+                }
+                my_dist = smp + 1 < S ? tn - tt : 1e8f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float dk = fmaf(dx, c.c2w[4 * k], fmaf(dy, c.c2w[4 * k + 1], 0.0f - c.c2w[4 * k + 2]));
+                    x[k] = fmaf(dk, tt, c.c2w[4 * k + 3]);
+                }
+            } else if (live) {
+                const long long ray = row0 / S + ray_l, smpl = row0 + tid;
+                if (p.ray_f64) {
+                    const double *o = reinterpret_cast<const double *>(p.rays_o) + ray * 3;
+                    const double *d = reinterpret_cast<const double *>(p.rays_d) + ray * 3;
+                    const double *tv = reinterpret_cast<const double *>(p.tvals) + smpl;
+                    const double tt = __ldg(tv);
+                    my_dist = smp + 1 < S ? (float)(__ldg(tv + 1) - tt) : 1e8f;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) x[c] = (float)(__ldg(o + c) + __ldg(d + c) * tt);
+                } else {
+                    const float *o = reinterpret_cast<const float *>(p.rays_o) + ray * 3;
+                    const float *d = reinterpret_cast<const float *>(p.rays_d) + ray * 3;
+                    const float *tv = reinterpret_cast<const float *>(p.tvals) + smpl;
+                    const float tt = __ldg(tv);
+                    my_dist = smp + 1 < S ? __ldg(tv + 1) - tt : 1e8f;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) x[c] = fmaf(__ldg(d + c), tt, __ldg(o + c));
+                }
+            }
+            float sn[3], cs[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) pe_sincos(x[c], &sn[c], &cs[c]);
+            // feature f = 3 * slot + coord as bf16 pairs (pair j = features 2j, 2j+1); band i fills pairs 1+3i .. 3+3i and leaves
+            // its last cosine pending; the ones column (feature 3 + 6E, odd) closes the pending pair.  Four pairs make this row's
+            // 16 bytes of a slab, stored as soon as they are complete.
+            {
+                uint8_t *const a0 = a_buf(0);
+                uint32_t q4[4] = {pack_bf16(x[0], x[1]), 0u, 0u, 0u};
+                float pend = x[2];
+                bool closed = false;
+                auto put = [&](int j, uint32_t v) {            // j is a compile-time constant at every call site
+                    q4[j & 3] = v;
+                    if ((j & 3) == 3) { if ((j >> 2) < A0S) *row_ptr(a0, j >> 2) = make_uint4(q4[0], q4[1], q4[2], q4[3]); q4[0] = q4[1] = q4[2] = q4[3] = 0u; }
+                };
+#pragma unroll
+                for (int i = 0; i < 10; ++i) {
+                    const bool on = i < p.pe_bands;
+                    const bool close = !closed && !on;
+                    put(1 + 3 * i, on ? pack_bf16(pend, sn[0]) : (close ? pack_bf16(pend, 1.0f) : 0u));
+                    put(2 + 3 * i, on ? pack_bf16(sn[1], sn[2]) : 0u);
+                    put(3 + 3 * i, on ? pack_bf16(cs[0], cs[1]) : 0u);
+                    closed = closed || close;
+                    pend = cs[2];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float s2 = 2.0f * sn[c] * cs[c], c2 = fmaf(-2.0f * sn[c], sn[c], 1.0f);
+                        sn[c] = s2; cs[c] = c2;
+                    }
+                }
+                put(31, closed ? 0u : pack_bf16(pend, 1.0f));
+            }
+        } else {
+            // ---- features: wait for the TMA, convert this thread's row to bf16 slabs.  Columns beyond c_in read the
+            // following floats of `stage` (finite: next row / zeroed or stale bf16 bytes seen as tiny floats... they meet
+            // zero weight rows only if finite) -- so only columns < 8 * A0S are converted, and column c_in is patched to 1.
+            int lead; uint32_t bytes;
+            (void)x_src(tile, lead, bytes);
+            mbar_wait(bar_x, xphase);
+            xphase ^= 1;
+            uint8_t *a0 = a_buf(0);
+            const float *xr = stage + lead + tid * c_in;
+            if (tid < valid) {
+                for (int c8 = 0; c8 < A0S - 1; ++c8) {     // (A0S - 1) * 8 <= c_in: every column of these slabs is a feature
+                    float f[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] = xr[c8 * 8 + j];
+                    *row_ptr(a0, c8) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                }
+                {
+                    const int c8 = A0S - 1;
+                    float f[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { const int c = c8 * 8 + j; f[j] = c < c_in ? xr[c] : (c == c_in ? 1.0f : 0.0f); }
+                    *row_ptr(a0, c8) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                }
+            } else {
+                for (int c8 = 0; c8 < A0S; ++c8) *row_ptr(a0, c8) = make_uint4(0, 0, 0, 0);
+            }
+        }
+        publish_smem(); // also: every thread is done reading `stage` (the first epilogue overwrites it)
+        const int next_tile = *next_tile_s;   // thread 0 rewrites it only after the next tile's first barrier
+        // ---- forward
+        float hz[4];
+        for (int l = 0; l < L; ++l) {
+            if (tid == 0) issue_steps(l, 0u, 64u);
+            commit_and_wait();
+            const float *bl = bias_s + l * HP;
+            if (l < L - 1) {
+                uint8_t *an = a_buf(l + 1);
+                uint32_t v[HP / 16][16];
+#pragma unroll
+                for (int c16 = 0; c16 < HP / 16; ++c16) tmem_ld16(tmem + lane_base + (uint32_t)(g * HP + c16 * 16), v[c16]);
+                tmem_ld_wait();
+                // the hidden layers' bias and the all-ones feature of the next layer's input came out of the MMA (see
+                // tc_prep_kernel): ReLU + round + pack is one instruction per pair
+#pragma unroll
+                for (int c16 = 0; c16 < HP / 16; ++c16) {
+                    uint32_t o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = pack_relu_bf16(__uint_as_float(v[c16][2 * j]), __uint_as_float(v[c16][2 * j + 1]));
+                    *row_ptr(an, c16 * 2) = make_uint4(o[0], o[1], o[2], o[3]);
+                    *row_ptr(an, c16 * 2 + 1) = make_uint4(o[4], o[5], o[6], o[7]);
+                }
+                publish_smem();
+            } else {
+                uint32_t v[16];
+                tmem_ld16(tmem + lane_base + (uint32_t)(g * HP), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hz[j] = __uint_as_float(v[j]) + bl[j];
+            }
+        }
+        // ---- head + loss + adjoint of the head's pre-activation (unit seed)
+        float dz[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.head == LNB_HEAD_SIGMOID) {
+            // mlp_fit: row r <-> target row (scripts/mlp_fit.py:121-145)
+            if (tid < valid && row0 + tid < p.R) {
+                const float *tg = p.target + (row0 + tid) * p.Wt;
+                for (int c = 0; c < p.Wt && c < 4; ++c) {
+                    float y = sigmoid_f(hz[c]);
+                    float d = y - __ldg(tg + c);
+                    loss_acc = fmaf(d, d, loss_acc);
+                    dz[c] = 2.0f * d * (y * (1.0f - y));
+                }
+            }
+        } else {
+            // Compositing with one thread per sample (thread r <-> sample r of the tile): segmented warp-shuffle scans
+            // inside each warp, carries across the 4 warps through shared memory.  scripts/nerf.py:176-288 and its reverse.
+            const float cr = sigmoid_f(hz[0]), cg = sigmoid_f(hz[1]), cb = sigmoid_f(hz[2]);
+            const float sg = fmaxf(hz[3], 0.0f);
+            const float e = __expf((0.0f - sg) * my_dist);
+            const float a = 1.0f - e;
+            const float qv = live ? (1.0f - a) + 1e-10f : 1.0f;
+            float pr = qv;                                   // segmented inclusive product
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                float o = __shfl_up_sync(0xffffffffu, pr, d);
+                if (lane >= d && smp >= d) pr *= o;
+            }
+            if (lane == 31) { tailp[warp] = pr; tail_s[warp] = smp; }
+            if (lane == 0) headq[warp] = qv;
+            if (live && smp == 0) {
+                color_s[ray_l * 3] = 0.f; color_s[ray_l * 3 + 1] = 0.f; color_s[ray_l * 3 + 2] = 0.f;
+                tgt_s[ray_l * 3] = tg0; tgt_s[ray_l * 3 + 1] = tg1; tgt_s[ray_l * 3 + 2] = tg2;
+            }
+            bar_group(g);
+            float carry = 1.0f;                              // product of this ray's samples in earlier warps
+            if (smp > lane) {
+                for (int w2 = warp - 1; w2 >= 0; --w2) {
+                    carry *= tailp[w2];
+                    if (tail_s[w2] < 32) break;              // that warp's last segment started inside it
+                }
+            }
+            const float Cpre = pr * carry;                   // true inclusive product prod_{k<=s} q_k
+            const float T = (smp == 0) ? 1.0f : Cpre;
+            const float wgt = a * T;
+            {   // colour: segmented inclusive sums, one shared-memory atomic per (warp, ray) segment
+                float s0 = live ? wgt * cr : 0.f, s1 = live ? wgt * cg : 0.f, s2 = live ? wgt * cb : 0.f;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    float o0 = __shfl_up_sync(0xffffffffu, s0, d), o1 = __shfl_up_sync(0xffffffffu, s1, d), o2 = __shfl_up_sync(0xffffffffu, s2, d);
+                    if (lane >= d && smp >= d) { s0 += o0; s1 += o1; s2 += o2; }
+                }
+                if (live && (lane == 31 || smp == S - 1)) {
+                    atomicAdd(color_s + ray_l * 3, s0); atomicAdd(color_s + ray_l * 3 + 1, s1); atomicAdd(color_s + ray_l * 3 + 2, s2);
+                }
+            }
+            bar_group(g);
+            float dc0 = 0.f, dc1 = 0.f, dc2 = 0.f;
+            if (live) {
+                const float c0 = color_s[ray_l * 3], c1 = color_s[ray_l * 3 + 1], c2 = color_s[ray_l * 3 + 2];
+                if (smp == 0 && p.color) {
+                    float *co = p.color + (row0 / S + ray_l) * 3;
+                    co[0] = c0; co[1] = c1; co[2] = c2;
+                }
+                const float d0 = c0 - tgt_s[ray_l * 3], d1 = c1 - tgt_s[ray_l * 3 + 1], d2 = c2 - tgt_s[ray_l * 3 + 2];
+                if (smp == 0) loss_acc += d0 * d0 + d1 * d1 + d2 * d2;
+                dc0 = 2.0f * d0; dc1 = 2.0f * d1; dc2 = 2.0f * d2;
+            }
+            {
+                // G_s = dT_s + q_{s+1} G_{s+1}: suffix scan of affine maps; B = 0 at a ray's last sample
+                const float d_w = cr * dc0 + cg * dc1 + cb * dc2;
+                const float dT = (smp == 0 || !live) ? 0.0f : d_w * a;
+                float qn = __shfl_down_sync(0xffffffffu, qv, 1);
+                if (lane == 31) qn = warp < 3 ? headq[warp + 1] : 0.0f;
+                float Aa = dT, Bb = (live && smp + 1 < S) ? qn : 0.0f;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    float A2 = __shfl_down_sync(0xffffffffu, Aa, d);
+                    float B2 = __shfl_down_sync(0xffffffffu, Bb, d);
+                    if (lane + d < 32) { Aa = fmaf(Bb, A2, Aa); Bb = Bb * B2; }
+                }
+                if (lane == 0) { headA[warp] = Aa; headB[warp] = Bb; }
+                bar_group(g);
+                float Gn = 0.0f;                             // G at lane 0 of the next warp
+                for (int w2 = 3; w2 > warp; --w2) Gn = fmaf(headB[w2], Gn, headA[w2]);
+                const float Gv = fmaf(Bb, Gn, Aa);
+                float Cm1 = __shfl_up_sync(0xffffffffu, Cpre, 1);
+                if (lane == 0) Cm1 = carry;
+                if (smp == 0) Cm1 = 1.0f;
+                const float d_alpha = d_w * T - Cm1 * Gv;
+                if (live) {
+                    dz[0] = (wgt * dc0) * (cr * (1.0f - cr));
+                    dz[1] = (wgt * dc1) * (cg * (1.0f - cg));
+                    dz[2] = (wgt * dc2) * (cb * (1.0f - cb));
+                    dz[3] = sg > 0.0f ? d_alpha * e * my_dist : 0.0f;
+                }
+            }
+        }
+        // ---- backward.  dZ_{L-1}: 4 live features of its one slab
+        *row_ptr(dzl_buf, 0) = make_uint4(pack_bf16(dz[0], dz[1]), pack_bf16(dz[2], dz[3]), 0u, 0u);
+        publish_smem();
+        for (int l = L - 1; l >= 1; --l) {
+            if (tid == 0) issue_steps(L + l, 0u, 64u);
+            issue_dw(l);                       // dW_l = A_l^T dZ_l while both are still there
+            commit_and_wait();
+            uint8_t *al = a_buf(l);
+            uint32_t v[HP / 16][16];
+#pragma unroll
+            for (int c16 = 0; c16 < HP / 16; ++c16) tmem_ld16(tmem + lane_base + (uint32_t)(g * HP + c16 * 16), v[c16]);
+            uint4 hm[HP / 8];
+#pragma unroll
+            for (int c8 = 0; c8 < HP / 8; ++c8) hm[c8] = *row_ptr(al, c8);
+            tmem_ld_wait();
+            uint4 oz[HP / 8];
+#pragma unroll
+            for (int c8 = 0; c8 < HP / 8; ++c8) {
+                // ReLU mask: bf16 post-ReLU values are >= 0, so positive <=> non-zero halfword
+                const uint32_t hw[4] = {hm[c8].x, hm[c8].y, hm[c8].z, hm[c8].w};
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int e = (c8 & 1) * 8 + 2 * j;
+                    o[j] = pack_bf16(__uint_as_float(v[c8 >> 1][e]), __uint_as_float(v[c8 >> 1][e + 1])) & gt0_mask_bf16x2(hw[j]);
+                }
+                oz[c8] = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            wait_dw();                         // ... and only now may A_l become dZ_{l-1}
+#pragma unroll
+            for (int c8 = 0; c8 < HP / 8; ++c8) *row_ptr(al, c8) = oz[c8];
+            publish_smem();
+        }
+        issue_dw(0);                           // dW_0 = A_0^T dZ_0 in the background; awaited at the top of the next tile
+        dw_pending = true;
+        tile = next_tile;
+    }
+
+    // ---- epilogue: this CTA's partials.  loss, then per layer the valid (in_l+1) x out_l block.
+    if (dw_pending) wait_dw();
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, d);
+    if (lane == 0) red_s[warp] = loss_acc;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    float *part = p.part + (size_t)blockIdx.x * p.part_stride;
+    if (threadIdx.x == 0) {
+        float s = 0.0f;
+        for (int gg = 0; gg < NG; ++gg) {
+            const float *r = reinterpret_cast<const float *>(globals + MG_GLOBALS + (size_t)gg * MG_MISC) + 384 + 24;
+            s += (r[0] + r[1]) + (r[2] + r[3]);
+        }
+        part[0] = s;
+        if (blockIdx.x == 0 && p.t_dev) p.t_dev[0] += 1; // read by the kernels that follow in the stream
+    }
+    // M = 64 accumulators occupy half of every lane quadrant: feature row f sits in TMEM lane 32 (f / 16) + f % 16; thread tid of
+    // a group reads lane tid.  The 16-column chunks of the gradient columns are dealt round-robin to the groups.
+    {
+        int chunk = 0;
+        for (int l = 0; l < L; ++l) {
+            const int in_l = p.dims[l], out_l = p.dims[l + 1], Np = LY::np(l, L);
+            float *o = part + p.part_off[l];
+            for (int c16 = 0; c16 * 16 < Np; ++c16, ++chunk) {
+                if (chunk % NG != g || c16 * 16 >= out_l) continue;
+                uint32_t v[16];
+                tmem_ld16(tmem + lane_base + (uint32_t)(NG * HP + l * HP + c16 * 16), v);
+                tmem_ld_wait();
+                const int f = warp * 16 + lane;
+                if (lane < 16 && f <= in_l) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int col = c16 * 16 + j;
+                        if (col < out_l) o[f * out_l + col] = __uint_as_float(v[j]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (g == 0 && warp == 0) tmem_dealloc(tmem, tmem_cols);
+}

@@ -834,7 +834,7 @@ __global__ void __launch_bounds__(TILE) fused_v1_kernel(const TcParams p)
 #endif
 }
 
-#include "fused_pp.cuh"
+#include "fused_mg.cuh"
 
 // image offset (bytes) of weight (l, k, j) / the fp32 bias region, mirroring tc_prep_kernel
 struct ImgMap {
@@ -1123,7 +1123,6 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     if (rays && (!nerf || (!cam && (!a->rays_d || !a->t)) || mlp->dims[0] != 3 + 6 * a->pe_bands))
         return unsupported("rays mode needs rays_o, rays_d, t (or a camera) and dims[0] == 3 + 6 * pe_bands");
     if (cam && (long long)a->cam->width * a->cam->height >= (1ll << 31)) return unsupported("camera: more than 2^31 pixels");
-    if (cam && getenv("LNB_TC_V2")) return unsupported("the experimental LNB_TC_V2 kernel has no camera mode");
     if (!nerf && N != R) return unsupported("needs n_rows == R");
     if (a->rows > N) return unsupported("rows > n_rows");
     if (!nerf && (a->target_w > 4)) return unsupported("target wider than 4");
@@ -1161,47 +1160,57 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     if (K0P / 8 + (L - 1) * (HP / 8) > 16) return unsupported("input + hidden widths exceed 128 features in total");
     if ((L - 1) * HP + 16 > 256) return unsupported("hidden widths exceed 256 gradient columns");
     if (!rays && (reinterpret_cast<uintptr_t>(a->X) & 3) != 0) return unsupported("X must be 4-byte aligned");
-    // LNB_TC_V2=1 selects the warp-specialised two-rows-per-thread kernel of fused_pp.cuh (same results; measured
-    // 45 us against 41 us on the 4096 x 64 batch): kept for experiments, not the default
-    const bool v1 = getenv("LNB_TC_V2") == nullptr;
-    int nslot = 2;
-    if (const char *e = getenv("LNB_TC_NSLOT")) { const int v = atoi(e); if (v == 1 || v == 2) nslot = v; }
-    size_t smem;
-    int tmem_cols;
-    if (v1) {
-        smem = (HP == 16 ? TcLayout<16>::total(L, K0P, c_in, rays, grad) : (HP == 32 ? TcLayout<32>::total(L, K0P, c_in, rays, grad) : TcLayout<64>::total(L, K0P, c_in, rays, grad)));
-        tmem_cols = (int)(HP == 16 ? TcLayout<16>::tmem_cols(L, grad) : (HP == 32 ? TcLayout<32>::tmem_cols(L, grad) : TcLayout<64>::tmem_cols(L, grad)));
-        nslot = 1;
+    // Train steps run on the multi-group kernel (fused_mg.cuh: one CTA per SM, up to seven 128-thread groups, adjoints in
+    // place); forward-only launches and LNB_TC_V1=1 on the one-tile-per-CTA kernel above.
+    const bool mg = grad && getenv("LNB_TC_V1") == nullptr && (!nerf || S >= 2);
+    size_t smem = 0;
+    int grid = 0, ng = 1;
+    const void *mg_fn = nullptr;
+    if (mg) {
+#define LNB_MG_PICK(HPV)                                                                                         \
+    do {                                                                                                         \
+        mg_fn = rays ? (const void *)fused_mg_kernel<true, HPV> : (const void *)fused_mg_kernel<false, HPV>;     \
+        ng = mg_max_groups<HPV>();                                                                               \
+        while (ng > 1 && (MgLayout<HPV>::total(L, c_in, K0P, rays, ng) > 232448 || MgLayout<HPV>::tmem_need(L, ng) > 512)) --ng; \
+    } while (0)
+        if (HP == 16) LNB_MG_PICK(16);
+        else if (HP == 32) LNB_MG_PICK(32);
+        else LNB_MG_PICK(64);
+#undef LNB_MG_PICK
+        cudaFuncAttributes fa;
+        LNB_CUDA(cudaFuncGetAttributes(&fa, mg_fn));
+        while (ng > 1 && (long long)ng * TILE * ((fa.numRegs + 7) / 8 * 8) > 65536) --ng;
+        if (const char *e = getenv("LNB_TC_GROUPS")) { const int v = atoi(e); if (v >= 1 && v < ng) ng = v; }
+        const int per_sm = (p.n_tiles + ctx->sm_count - 1) / ctx->sm_count;   // small batches: no idle groups
+        if (ng > per_sm) ng = per_sm < 1 ? 1 : per_sm;
+        grid = (p.n_tiles + ng - 1) / ng;
+        if (grid > ctx->sm_count) grid = ctx->sm_count;
+        if (grid < 1) grid = 1;
+        smem = HP == 16 ? MgLayout<16>::total(L, c_in, K0P, rays, ng) : (HP == 32 ? MgLayout<32>::total(L, c_in, K0P, rays, ng) : MgLayout<64>::total(L, c_in, K0P, rays, ng));
+        if (smem > 232448) return unsupported("shared memory");
     } else {
-        for (;; --nslot) {   // two tiles in flight per CTA unless shared memory or TMEM say otherwise
-            smem = (HP == 16 ? PpLayout<16>::total(L, K0P, c_in, nslot, rays, grad) : (HP == 32 ? PpLayout<32>::total(L, K0P, c_in, nslot, rays, grad) : PpLayout<64>::total(L, K0P, c_in, nslot, rays, grad)));
-            tmem_cols = (int)(HP == 16 ? PpLayout<16>::tmem_cols(L, nslot, grad) : (HP == 32 ? PpLayout<32>::tmem_cols(L, nslot, grad) : PpLayout<64>::tmem_cols(L, nslot, grad)));
-            if (nslot == 1 || (smem + 1024 <= 227 * 1024 && nslot * (HP + (grad ? (L - 1) * HP + 16 : 0)) <= 512)) break;
-        }
+        smem = (HP == 16 ? TcLayout<16>::total(L, K0P, c_in, rays, grad) : (HP == 32 ? TcLayout<32>::total(L, K0P, c_in, rays, grad) : TcLayout<64>::total(L, K0P, c_in, rays, grad)));
+        const int tmem_cols = (int)(HP == 16 ? TcLayout<16>::tmem_cols(L, grad) : (HP == 32 ? TcLayout<32>::tmem_cols(L, grad) : TcLayout<64>::tmem_cols(L, grad)));
+        int per_sm = 512 / tmem_cols;
+        int by_smem = (int)((228 * 1024) / (smem + 1024));
+        if (by_smem < per_sm) per_sm = by_smem;
+        if (per_sm < 1) return unsupported("shared memory");
+        if (const char *e = getenv("LNB_TC_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
+        grid = ctx->sm_count * per_sm;
+        if (grid > p.n_tiles) grid = p.n_tiles;
+        if (grid < 1) grid = 1;
     }
-    int per_sm = 512 / tmem_cols;
-    int by_smem = (int)((228 * 1024) / (smem + 1024));
-    if (by_smem < per_sm) per_sm = by_smem;
-    if (!v1 && per_sm > 8) per_sm = 8;   // 256 threads each
-    if (per_sm < 1) return unsupported("shared memory");
-    if (const char *e = getenv("LNB_TC_CTAS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
-    int grid = ctx->sm_count * per_sm;
-    const int want = (p.n_tiles + nslot - 1) / nslot;   // every CTA should have a tile for each of its slots
-    if (grid > want) grid = want;
-    if (grid < 1) grid = 1;
     const int wimg_bytes = HP == 16 ? TcLayout<16>::wimg_bytes(L, K0P) : (HP == 32 ? TcLayout<32>::wimg_bytes(L, K0P) : TcLayout<64>::wimg_bytes(L, K0P));
     LNB_TRY(lnb_arena_reserve(ctx, (size_t)grid * p.part_stride * sizeof(float) + wimg_bytes + 8192));
     p.part = (float *)lnb_arena_take(ctx, (size_t)grid * p.part_stride * sizeof(float));
     uint8_t *wimg = (uint8_t *)lnb_arena_take(ctx, wimg_bytes);
     p.wimg = (ex && ex->wimg) ? ex->wimg : wimg;
     p.t_dev = ex ? ex->t_dev : nullptr;
-    if (v1) {
-        if (!ctx->tc_counter) {
-            LNB_CUDA(cudaMalloc((void **)&ctx->tc_counter, 256));
-            LNB_CUDA(cudaMemsetAsync(ctx->tc_counter, 0, 256, ctx->stream));
-        }
-        p.tile_counter = ctx->tc_counter;
+    if (!ctx->tc_counter) {
+        LNB_CUDA(cudaMalloc((void **)&ctx->tc_counter, 256));
+        LNB_CUDA(cudaMemsetAsync(ctx->tc_counter, 0, 256, ctx->stream));
     }
+    p.tile_counter = ctx->tc_counter;
     float *loss = a->loss ? a->loss : (float *)lnb_arena_take(ctx, 16);
 #ifdef LNB_TC_CLK
     float *dbg_dev = nullptr;
@@ -1215,7 +1224,7 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     const bool use_pdl = getenv("LNB_NO_PDL") == nullptr;
     if (N > 0) {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(v1 ? TILE : PP_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(mg ? ng * TILE : TILE); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
     cfg.attrs = pdl_attr; cfg.numAttrs = use_pdl ? 1 : 0;
 #define LNB_LAUNCH(KERNEL)                                                                        \
     do {                                                                                         \
@@ -1224,9 +1233,8 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     } while (0)
 #define LNB_TC(HPV)                                                                              \
     do {                                                                                         \
-        if (v1) { if (rays) LNB_LAUNCH((fused_v1_kernel<true, HPV>)); else LNB_LAUNCH((fused_v1_kernel<false, HPV>)); } \
-        else if (nslot == 2) { if (rays) LNB_LAUNCH((fused_tc_kernel<true, HPV, 2>)); else LNB_LAUNCH((fused_tc_kernel<false, HPV, 2>)); } \
-        else { if (rays) LNB_LAUNCH((fused_tc_kernel<true, HPV, 1>)); else LNB_LAUNCH((fused_tc_kernel<false, HPV, 1>)); } \
+        if (mg) { if (rays) LNB_LAUNCH((fused_mg_kernel<true, HPV>)); else LNB_LAUNCH((fused_mg_kernel<false, HPV>)); } \
+        else { if (rays) LNB_LAUNCH((fused_v1_kernel<true, HPV>)); else LNB_LAUNCH((fused_v1_kernel<false, HPV>)); } \
     } while (0)
         if (!(ex && ex->wimg)) {
             if (HP == 16) tc_prep_kernel<16><<<1, 256, 0, ctx->stream>>>(p, wimg);
@@ -1256,9 +1264,6 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
         if (++calls % 150 == 20) {
             double acc[24] = {0};
             for (int b = 0; b < grid; ++b) for (int i = 0; i < 24; ++i) acc[i] += h[(size_t)b * 24 + i];
-            const char *nm2[24] = {"wait dW (A_0)", "wait out: fwd epilogues", "", "wait out: head", "wait out: bwd epilogues", "", "", "",
-                                   "build A_0 + loads", "fwd epilogues", "", "head + compositing", "bwd epilogues", "", "", "",
-                                   "", "", "", "", "", "wait TMA", "prologue", "final wait dW"};
             const char *nm[24] = {"wait X", "convert+publish", "issue fwd", "wait fwd mma", "fwd epilogue", "fwd publish", "issue fwd AGAIN (experiment)", "dz publish",
                                   "issue bwd", "wait bwd mma", "bwd epilogue", "bwd publish", "wait dW", "issue dW + final epilogue", "prologue", "loop top",
                                   "head ld+bias", "comp: act+prodscan", "comp: sync1", "comp: carry+colour", "comp: sync2", "comp: dcol+affine", "comp: sync3", "comp: finish"};
@@ -1274,7 +1279,7 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
                 fprintf(stderr, "   CTA start spread %.1f us, first end at %.1f us, last end at %.1f us (from first start)\n",
                         (s1 - s0) * 1e-3, (e0 - s0) * 1e-3, (e1 - s0) * 1e-3);
             }
-            for (int i = 0; i < 24; ++i) if (acc[i] > 0) fprintf(stderr, "   %-22s %8.0f\n", (v1 ? nm : nm2)[i], acc[i] / p.n_tiles);
+            for (int i = 0; i < 24; ++i) if (acc[i] > 0) fprintf(stderr, "   %-22s %8.0f\n", nm[i], acc[i] / p.n_tiles);
         }
     }
 #endif

@@ -150,5 +150,8 @@ def test_trainer_steps_from_a_camera_batch_on_host_and_device(env):
         loss_h = tr_h.step_host(camera=cam_h, S=S, pe_bands=E, target=target, path="tc")
     wd, bd, loss_d = tr_d.read()
     wh, bh, _ = tr_h.read()
-    assert np.array_equal(wd, wh) and np.array_equal(bd, bh) and loss_d == loss_h
+    # same arithmetic on both routes; the weight gradients of a launch are summed in TMEM in MMA completion order, so the
+    # two trajectories agree to fp32 rounding, not bit for bit
+    tol = lambda a, b: float(np.abs(a - b).max()) <= 2e-5 * float(np.abs(b).max())  # noqa: E731
+    assert tol(wd, wh) and tol(bd, bh) and abs(loss_d - loss_h) <= 1e-5 * abs(loss_h)
     tr_d.close(); tr_h.close()

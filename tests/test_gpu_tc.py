@@ -243,7 +243,10 @@ def test_context_runs_on_torchs_current_stream_by_default(torch_cuda):
     c2 = api.Context(0)
     assert c2._on_torch_current()
     o2 = run_tc(c2, torch, case, 1.0)
-    assert np.array_equal(o["d_ws"], o2["d_ws"]) and np.array_equal(o["color"], o2["color"])
+    # colours are a per-ray computation (bit-identical); the weight gradients of one launch are accumulated in TMEM by several
+    # issuing threads / groups in completion order, so their last bits may differ between launches (fp32 addition order)
+    assert np.array_equal(o["color"], o2["color"])
+    assert rel_err(o["d_ws"], o2["d_ws"]) <= 1e-5 and rel_err(o["d_bs"], o2["d_bs"]) <= 1e-5
     c.close(); c2.close()
 
 
@@ -271,8 +274,9 @@ def test_trainer_takes_an_empty_batch_and_a_batch_the_fused_kernel_cannot(ctx, t
 
 @pytest.mark.parametrize("pinned", [True, False])
 def test_pipelined_host_steps_equal_the_synchronous_ones(ctx, torch_cuda, pinned):
-    """lnb_trainer_submit_host / lnb_trainer_wait (H2D of batch i+1 under step i, two staging slots) must walk exactly the
-    trajectory of lnb_trainer_step_host: same losses, bit-identical weights, features and rays batches interleaved."""
+    """lnb_trainer_submit_host / lnb_trainer_wait (H2D of batch i+1 under step i, two staging slots) must walk the trajectory
+    of lnb_trainer_step_host: same losses and weights (to fp32 rounding: the gradient sum order inside a launch is not fixed),
+    features and rays batches interleaved."""
     torch = torch_cuda
     from loma_nerf_b200 import api
     R, S, E = 128, 64, 5
@@ -305,5 +309,5 @@ def test_pipelined_host_steps_equal_the_synchronous_ones(ctx, torch_cuda, pinned
     assert tb.wait() == []
     wb, bb, _ = tb.read()
     tb.close()
-    assert got == want, (got, want)
-    assert np.array_equal(wa, wb) and np.array_equal(ba, bb)
+    assert len(got) == len(want) and rel_err(got, want) <= 1e-5, (got, want)
+    assert rel_err(wb, wa) <= 2e-5 and rel_err(bb, ba) <= 2e-5
