@@ -443,7 +443,16 @@ static int step_dispatch(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *
 {
     if (!ctx) return LNB_ERR_ARG;
     LNB_ARG(a, "null args");
-    if (a->path == LNB_PATH_F32 || a->path == LNB_PATH_F32_LAYERWISE) return step_layerwise(ctx, mlp, a, nerf);
+    if (a->path == LNB_PATH_F32_LAYERWISE) return step_layerwise(ctx, mlp, a, nerf);
+    if (a->path == LNB_PATH_F32) {
+        // same arithmetic type and tolerance either way: the fused kernel when the problem and the outputs asked for fit
+        // it (loss, colour, d_ws, d_bs of a 2-3 layer network of the reference's widths), else the layerwise kernels
+        StepDims d;
+        LNB_TRY(validate(ctx, mlp, a, nerf, &d));
+        const int rc = getenv("LNB_F32_NO_FUSED") ? LNB_ERR_UNSUPPORTED : lnb_fused_f32_step(ctx, mlp, a, nerf, 0);
+        if (rc != LNB_ERR_UNSUPPORTED) return rc;
+        return step_layerwise(ctx, mlp, a, nerf);
+    }
     if (a->path == LNB_PATH_TC) {
         StepDims d;
         LNB_TRY(validate(ctx, mlp, a, nerf, &d));
@@ -458,6 +467,15 @@ static int step_dispatch(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *
     }
     LNB_ARG(false, "unknown path");
     return LNB_ERR_ARG;
+}
+
+// validated entry to the fused exact kernel for the trainer (overwrite: gradients written, not accumulated)
+int lnb_step_f32_fused(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, bool nerf, int overwrite)
+{
+    if (!ctx) return LNB_ERR_ARG;
+    StepDims d;
+    LNB_TRY(validate(ctx, mlp, a, nerf, &d));
+    return lnb_fused_f32_step(ctx, mlp, a, nerf, overwrite);
 }
 
 int lnb_step_ex(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, bool nerf, const lnb_tc_extra *ex)

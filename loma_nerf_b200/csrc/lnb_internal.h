@@ -181,6 +181,11 @@ int lnb_tc_prep(lnb_ctx *ctx, const lnb_mlp *mlp, const float *ws, const float *
 int lnb_tc_adam_img(lnb_ctx *ctx, const lnb_mlp *mlp, float *param, const float *grad, float *m, float *v,
                     const int *t_dev, double lr, double b1, double b2, double eps, void *wimg);
 
+// ---- fused_f32.cu: the fused exact (fp32 CUDA-core) step for the reference's own network shapes; LNB_ERR_UNSUPPORTED
+// when the problem (or the outputs asked for) does not fit it
+int lnb_fused_f32_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, bool nerf, int overwrite);
+int lnb_step_f32_fused(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, bool nerf, int overwrite);   // validated (api_flat.cu)
+
 // ---- encode.cu / optim.cu ---------------------------------------------------------------------
 int lnb_launch_pos_encoding(lnb_ctx *ctx, const double *x, long long n, int F, int E, float *out);
 int lnb_launch_sample_encode(lnb_ctx *ctx, const void *o, const void *d, const void *t, int f64,

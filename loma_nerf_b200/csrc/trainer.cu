@@ -151,8 +151,16 @@ static int trainer_run(lnb_trainer *t, const lnb_step_args *batch, int nerf, boo
                    "exchange gradients in-kernel; use lnb_trainer_grad + an all-reduce of lnb_trainer_grad_buffer + lnb_trainer_apply";
         return LNB_ERR_UNSUPPORTED;
     }
-    LNB_CUDA(cudaMemsetAsync(t->grads, 0, (size_t)(t->n_w + t->n_b + 1) * 4, ctx->stream));
-    LNB_TRY(nerf ? lnb_nerf_step(ctx, &t->mlp, &a) : lnb_fit_step(ctx, &t->mlp, &a));
+    int rc = LNB_ERR_UNSUPPORTED;
+    if (a.path == LNB_PATH_F32 && !getenv("LNB_F32_NO_FUSED")) {
+        // fused exact kernel writing the (zero-padded, never otherwise touched) gradient buffer: no memset
+        rc = lnb_step_f32_fused(ctx, &t->mlp, &a, nerf != 0, 1);
+        if (rc != LNB_OK && rc != LNB_ERR_UNSUPPORTED) return rc;
+    }
+    if (rc == LNB_ERR_UNSUPPORTED) {
+        LNB_CUDA(cudaMemsetAsync(t->grads, 0, (size_t)(t->n_w + t->n_b + 1) * 4, ctx->stream));
+        LNB_TRY(nerf ? lnb_nerf_step(ctx, &t->mlp, &a) : lnb_fit_step(ctx, &t->mlp, &a));
+    }
     t->t_bumped = false;
     if (fuse_update) return lnb_trainer_apply(t);
     return LNB_OK;
