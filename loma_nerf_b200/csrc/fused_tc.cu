@@ -1036,7 +1036,6 @@ int tc_pick(const lnb_mlp *mlp, int *HP, int *K0P)
     *HP = hw + 1 <= 16 ? 16 : (hw + 1 <= 32 ? 32 : (hw + 1 <= 64 ? 64 : 0));
     *K0P = (mlp->dims[0] + 1 + 15) / 16 * 16;
     if (!*HP || *K0P > 64 || mlp->dims[L] > 16) return 0;
-    if (*K0P / 8 + (L - 1) * (*HP / 8) > 16 || (L - 1) * *HP + 16 > 256) return 0;
     return 1;
 }
 
@@ -1157,12 +1156,14 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
 
     const int c_in = mlp->dims[0];
     const bool grad = a->want_grad != 0;
-    if (K0P / 8 + (L - 1) * (HP / 8) > 16) return unsupported("input + hidden widths exceed 128 features in total");
-    if ((L - 1) * HP + 16 > 256) return unsupported("hidden widths exceed 256 gradient columns");
     if (!rays && (reinterpret_cast<uintptr_t>(a->X) & 3) != 0) return unsupported("X must be 4-byte aligned");
     // Train steps run on the multi-group kernel (fused_mg.cuh: one CTA per SM, up to seven 128-thread groups, adjoints in
     // place); forward-only launches and LNB_TC_V1=1 on the one-tile-per-CTA kernel above.
     const bool mg = grad && getenv("LNB_TC_V1") == nullptr && (!nerf || S >= 2);
+    if (grad && !mg) {   // the one-tile-per-CTA kernel computes all weight gradients with ONE concatenated M = 128 MMA per K-step
+        if (K0P / 8 + (L - 1) * (HP / 8) > 16) return unsupported("input + hidden widths exceed 128 features in total");
+        if ((L - 1) * HP + 16 > 256) return unsupported("hidden widths exceed 256 gradient columns");
+    }
     size_t smem = 0;
     int grid = 0, ng = 1;
     const void *mg_fn = nullptr;
