@@ -422,7 +422,7 @@ class TrainRun:
         probe = max(3, min(steps, 12))
         self.prepare(probe)
         est = env.timed(lambda: self.run(probe)) / probe
-        reps = max(1, int(-(-min_ms // max(est * steps, 1e-6))))
+        reps = max(1, int(-(-(1.2 * min_ms) // max(est * steps, 1e-6))))   # 20 % margin: the probe runs cold
         T = reps * steps
         self.prepare(T)
         env.barrier()

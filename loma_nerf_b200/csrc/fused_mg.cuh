@@ -73,6 +73,13 @@ __global__ void __launch_bounds__(mg_max_groups<HP>() * TILE, 1) fused_mg_kernel
     using LY = TcLayout<HP>;
     using MG = MgLayout<HP>;
     extern __shared__ __align__(1024) uint8_t smem[];
+#ifdef LNB_TC_CLK
+    unsigned long long stamp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define MG_STAMP(i) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(stamp[i]))
+    MG_STAMP(0);
+#else
+#define MG_STAMP(i)
+#endif
     const int NG = (int)blockDim.x / TILE;
     const int g = (int)threadIdx.x / TILE, tid = (int)threadIdx.x % TILE, warp = tid >> 5, lane = tid & 31;
     const int L = p.L, K0P = p.K0P, c_in = p.dims[0], S = p.S;
@@ -92,7 +99,6 @@ __global__ void __launch_bounds__(mg_max_groups<HP>() * TILE, 1) fused_mg_kernel
     float *const headA = tailp + 13;                            // [5]
     float *const headB = tailp + 18;                            // [5]
     float *const red_s = tailp + 24;                            // [4]
-    int *const next_tile_s = reinterpret_cast<int *>(tailp + 28);
     uint64_t *const bar_p = reinterpret_cast<uint64_t *>(misc + 1664);
     const uint32_t bar_mma = smem_u32(bar_p), bar_x = smem_u32(bar_p + 1), bar_dw = smem_u32(bar_p + 2);
     const uint32_t bar_w = smem_u32(globals);
@@ -117,31 +123,32 @@ __global__ void __launch_bounds__(mg_max_groups<HP>() * TILE, 1) fused_mg_kernel
         return reinterpret_cast<const void *>(a16);
     };
 
-    // ---- one-time setup: zero every slot (padding features and K-padding reads must see zeros / finite values)
-    for (uint8_t *z = smem + (size_t)threadIdx.x * 16; z < Wbase; z += (size_t)blockDim.x * 16) *reinterpret_cast<uint4 *>(z) = make_uint4(0, 0, 0, 0);
+    // ---- one-time setup.  Every buffer is fully rewritten each tile before an MMA reads it as data; the one K-padding read
+    // that can come first is the layer-0 MMA's look into the dZ_{L-1} slab behind A_0 (zero weights, but the values must be
+    // finite): zero that slab.  (Zeroing the whole 200 KB cost 0.8 us of every launch.)
+    *reinterpret_cast<uint4 *>(slot + MG::dzl_off(A0S) + tid * 16) = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         mbar_init(bar_mma, 1);
         mbar_init(bar_x, 1);
         mbar_init(bar_dw, 3);          // the three threads that issue a layer's weight-gradient MMAs
         if (g == 0) mbar_init(bar_w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // the MMA program: one record per stage, one THREAD per record (a single thread building all of them cost 3 us)
+    if (tid >= 32 && tid < 32 + 3 * L) {
+        const int r = tid - 32, kind = r / L, l = r % L;
         const uint32_t dcol = (uint32_t)(g * HP);
-        for (int l = 0; l < L; ++l) {          // D[128 x Np] = A_l[128 x Kp] * W_l   (A, B K-major)
-            const int Np = LY::np(l, L), Kp = LY::kp(l, K0P);
-            const uint32_t a0 = smem_u32(a_buf(l)), b0 = smem_u32(Wbase + LY::w_off(l, L, K0P));
-            prog[l] = StageRec{smem_desc(a0, SLAB, 128), smem_desc(b0, Np * 16, 128), (uint32_t)(2 * SLAB) >> 4, (uint32_t)(2 * Np * 16) >> 4,
+        const int Np = LY::np(l, L), Kp = LY::kp(l, K0P);
+        const uint32_t wl = smem_u32(Wbase + LY::w_off(l, L, K0P));
+        if (kind == 0) {               // D[128 x Np] = A_l[128 x Kp] * W_l   (A, B K-major)
+            prog[l] = StageRec{smem_desc(smem_u32(a_buf(l)), SLAB, 128), smem_desc(wl, Np * 16, 128), (uint32_t)(2 * SLAB) >> 4, (uint32_t)(2 * Np * 16) >> 4,
                                instr_desc(128, Np, 0, 0), dcol, (uint32_t)(Kp / 16), 0u, 0u, 0u};
-        }
-        for (int l = 1; l < L; ++l) {          // dH_l[128 x Kp] = dZ_l[128 x Np] * W_l^T (same W bytes, MN-major)
-            const int Np = LY::np(l, L), Kp = LY::kp(l, K0P);
-            const uint32_t a0 = smem_u32(dz_buf(l)), b0 = smem_u32(Wbase + LY::w_off(l, L, K0P));
-            prog[L + l] = StageRec{smem_desc(a0, SLAB, 128), smem_desc(b0, 128, Np * 16), (uint32_t)(2 * SLAB) >> 4, 256u >> 4,
+        } else if (kind == 1) {        // dH_l[128 x Kp] = dZ_l[128 x Np] * W_l^T (same W bytes, MN-major); unused for l = 0
+            prog[L + l] = StageRec{smem_desc(smem_u32(dz_buf(l)), SLAB, 128), smem_desc(wl, 128, Np * 16), (uint32_t)(2 * SLAB) >> 4, 256u >> 4,
                                    instr_desc(128, Kp, 0, 1), dcol, (uint32_t)(Np / 16), 0u, 0u, 0u};
-        }
-        for (int l = 0; l < L; ++l) {          // dW_l[features x Np] += A_l^T dZ_l, K = the tile's 128 samples, both MN-major
-            const uint32_t a0 = smem_u32(a_buf(l)), b0 = smem_u32(dz_buf(l));
-            prog[2 * L + l] = StageRec{smem_desc(a0, 128, SLAB), smem_desc(b0, 128, SLAB), 256u >> 4, 256u >> 4,
-                                       instr_desc(64, LY::np(l, L), 1, 1), (uint32_t)(NG * HP + l * HP), (uint32_t)(TILE / 16), 1u, 0u, 0u};
+        } else {                       // dW_l[features x Np] += A_l^T dZ_l, K = the tile's 128 samples, both MN-major
+            prog[2 * L + l] = StageRec{smem_desc(smem_u32(a_buf(l)), 128, SLAB), smem_desc(smem_u32(dz_buf(l)), 128, SLAB), 256u >> 4, 256u >> 4,
+                                       instr_desc(64, Np, 1, 1), (uint32_t)(NG * HP + l * HP), (uint32_t)(TILE / 16), 1u, 0u, 0u};
         }
     }
     const int tmem_need = MG::tmem_need(L, NG);
@@ -159,21 +166,23 @@ __global__ void __launch_bounds__(mg_max_groups<HP>() * TILE, 1) fused_mg_kernel
         tmem_st_wait();
     }
     tc_fence_before();
-    // Programmatic dependent launch: everything above overlaps the tail of the previous kernel in the stream; from here on
-    // we read what it produced (weight image, tile counter).  No-op without PDL.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (threadIdx.x == 0) {
+    __syncthreads();
+    tc_fence_after();
+    // Programmatic dependent launch: all of the above overlapped the tail of the previous kernel in the stream.  Only OUR
+    // reduce kernel triggers its dependents early, and the one thing of its output this kernel reads is the weight image:
+    // ONE thread waits for it and issues the bulk copy of the image; the others go straight to their first tile's features
+    // and meet the image at its mbarrier (which also orders their later global writes behind that kernel).  No-op without PDL.
+    if (threadIdx.x == 64) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         const uint32_t wb = (uint32_t)LY::wimg_bytes(L, K0P);
         mbar_expect_tx(bar_w, wb);
         bulk_g2s(smem_u32(Wbase), p.wimg, wb, bar_w);
     }
-    __syncthreads();
-    tc_fence_after();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     uint32_t phase = 0, xphase = 0, dwphase = 0;
     float loss_acc = 0.0f;
-    bool dw_pending = false;
-    mbar_wait(bar_w, 0); // weights + biases have landed
+    bool dw_pending = false, have_weights = false;
+    MG_STAMP(1);
 
     auto row_ptr = [&](uint8_t *buf, int slab) { return reinterpret_cast<uint4 *>(buf + slab * SLAB + tid * 16); };
     // issue K-steps [k0, k1) of one stage of the MMA program (one thread)
@@ -213,7 +222,9 @@ __global__ void __launch_bounds__(mg_max_groups<HP>() * TILE, 1) fused_mg_kernel
     };
     auto wait_dw = [&]() { mbar_wait(bar_dw, dwphase); dwphase ^= 1; tc_fence_after(); };
 
-    for (int tile = g * (int)gridDim.x + (int)blockIdx.x; tile < p.n_tiles;) {
+    // tiles are dealt statically (tile -> group fixed): with equal tile costs nothing is gained by claiming them, and
+    // nothing here then depends on the previous kernel in the stream except the weight image
+    for (int tile = g * (int)gridDim.x + (int)blockIdx.x; tile < p.n_tiles; tile += (int)gridDim.x * NG) {
         const long long row0 = (long long)tile * p.rows_per_tile;
         long long rem = p.N - row0;
         const int valid = rem < p.rows_per_tile ? (int)rem : p.rows_per_tile;
@@ -237,7 +248,6 @@ __global__ void __launch_bounds__(mg_max_groups<HP>() * TILE, 1) fused_mg_kernel
                 tg0 = __ldg(tg); tg1 = __ldg(tg + 1); tg2 = __ldg(tg + 2);
             }
         }
-        if (tid == 0) *next_tile_s = atomicAdd(p.tile_counter, 1) + (int)gridDim.x * NG;   // read after several group barriers
         if (RAYS) {
             // ---- features from rays: pts = o + d t (train_nerf.py:289-299), PE (pos_encoding.py:38-70),
             // dist = t[s+1] - t[s], last 1e8 (train_nerf.py:306-311); written straight into A_0
@@ -345,8 +355,12 @@ __global__ void __launch_bounds__(mg_max_groups<HP>() * TILE, 1) fused_mg_kernel
                 for (int c8 = 0; c8 < A0S; ++c8) *row_ptr(a0, c8) = make_uint4(0, 0, 0, 0);
             }
         }
+        if (!have_weights) {
+            mbar_wait(bar_w, 0);             // weights + biases have landed (and the previous kernel has completed)
+            have_weights = true;
+            MG_STAMP(2);
+        }
         publish_smem(); // also: every thread is done reading `stage` (the first epilogue overwrites it)
-        const int next_tile = *next_tile_s;   // thread 0 rewrites it only after the next tile's first barrier
         // ---- forward
         float hz[4];
         for (int l = 0; l < L; ++l) {
@@ -510,8 +524,12 @@ __global__ void __launch_bounds__(mg_max_groups<HP>() * TILE, 1) fused_mg_kernel
         }
         issue_dw(0);                           // dW_0 = A_0^T dZ_0 in the background; awaited at the top of the next tile
         dw_pending = true;
-        tile = next_tile;
+#ifdef LNB_TC_CLK
+        if (stamp[3] == 0) MG_STAMP(3);
+        MG_STAMP(4);
+#endif
     }
+    if (!have_weights) mbar_wait(bar_w, 0);    // a group without tiles still orders its partial writes behind the previous kernel
 
     // ---- epilogue: this CTA's partials.  loss, then per layer the valid (in_l+1) x out_l block.
     if (dw_pending) wait_dw();
@@ -521,6 +539,7 @@ __global__ void __launch_bounds__(mg_max_groups<HP>() * TILE, 1) fused_mg_kernel
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    MG_STAMP(5);
     float *part = p.part + (size_t)blockIdx.x * p.part_stride;
     if (threadIdx.x == 0) {
         float s = 0.0f;
@@ -557,4 +576,11 @@ __global__ void __launch_bounds__(mg_max_groups<HP>() * TILE, 1) fused_mg_kernel
     tc_fence_before();
     __syncthreads();
     if (g == 0 && warp == 0) tmem_dealloc(tmem, tmem_cols);
+#ifdef LNB_TC_CLK
+    MG_STAMP(6);
+    if (p.dbg && tid == 0) {
+        unsigned long long *o = reinterpret_cast<unsigned long long *>(p.dbg) + ((size_t)blockIdx.x * NG + g) * 8;
+        for (int i = 0; i < 8; ++i) o[i] = stamp[i];
+    }
+#endif
 }

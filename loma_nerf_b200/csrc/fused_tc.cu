@@ -865,21 +865,29 @@ struct AdamArgs {
 
 // the reference's AdamOptimizer.update (train_nerf.py:133-161, double bias correction kept) on
 // one parameter; python-float scalars meet float32 arrays exactly as in optim.cu
-__device__ __forceinline__ float adam_one(const AdamArgs &a, long long i, float g)
+// the step's scalar factors: Python doubles in the reference (lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t)), rounded to float32
+// once where they meet the arrays.  Two double-precision pow() are ~1 us of dependent arithmetic: computed by ONE thread
+// per block, off the other threads' critical path (see tc_reduce_kernel).
+struct AdamScalars { float lr_t, c1, c2; };
+__device__ __forceinline__ AdamScalars adam_scalars(const AdamArgs &a)
+{
+    if (a.sgd) return AdamScalars{0.f, 1.f, 1.f};
+    const int t = a.t_dev[0];
+    const double c1 = 1.0 - pow(a.b1, (double)t), c2 = 1.0 - pow(a.b2, (double)t);
+    return AdamScalars{(float)(a.lr * (sqrt(c2) / c1)), (float)c1, (float)c2};
+}
+__device__ __forceinline__ float adam_one(const AdamArgs &a, long long i, float g, const AdamScalars &sc)
 {
     if (a.sgd) {
         const float pn = a.param[i] - (float)a.lr * g;
         a.param[i] = pn;
         return pn;
     }
-    const int t = a.t_dev[0];
-    const double c1 = 1.0 - pow(a.b1, (double)t), c2 = 1.0 - pow(a.b2, (double)t);
-    const float lr_t = (float)(a.lr * (sqrt(c2) / c1));
     const float mi = (float)a.b1 * a.m[i] + (float)(1.0 - a.b1) * g;
     const float vi = (float)a.b2 * a.v[i] + (float)(1.0 - a.b2) * (g * g);
     a.m[i] = mi;
     a.v[i] = vi;
-    const float pnew = a.param[i] - lr_t * (mi / (float)c1) / (sqrtf(vi / (float)c2) + (float)a.eps);
+    const float pnew = a.param[i] - sc.lr_t * (mi / sc.c1) / (sqrtf(vi / sc.c2) + (float)a.eps);
     a.param[i] = pnew;
     return pnew;
 }
@@ -905,8 +913,10 @@ __global__ void __launch_bounds__(1024) tc_reduce_kernel(const float *__restrict
                                  lnb_tc_comm cm)
 {
     __shared__ float sloss;
+    __shared__ AdamScalars s_adam;
     asm volatile("griddepcontrol.wait;" ::: "memory");              // the fused kernel's partials are complete
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); // the next step may start its prologue
+    if (fuse_adam && threadIdx.x == 1023) s_adam = adam_scalars(ad); // while the other warps gather the partials
     // every block sums the loss partials itself (same order everywhere) so the seed needs no second pass
     if (threadIdx.x < 32) {
         float s = 0.0f;
@@ -1006,7 +1016,7 @@ __global__ void __launch_bounds__(1024) tc_reduce_kernel(const float *__restrict
         *dst = g;
         if (fuse_adam) {
             const long long pi = is_w ? ((long long)l * p.max_in + k) * p.max_out + j : ad.n_w + (long long)l * p.max_out + j;
-            const float pn = adam_one(ad, pi, g);
+            const float pn = adam_one(ad, pi, g, s_adam);
             if (ad.wimg) { if (is_w) im.put_w(ad.wimg, l, k, j, pn); else im.put_b(ad.wimg, l, j, pn); }
         }
     }
@@ -1023,7 +1033,7 @@ __global__ void tc_adam_img_kernel(TcParams p, const float *__restrict__ grad, A
     const int out_l = p.dims[l + 1], k = e / out_l, j = e % out_l;
     const bool is_w = k < p.dims[l];
     const long long pi = is_w ? ((long long)l * p.max_in + k) * p.max_out + j : ad.n_w + (long long)l * p.max_out + j;
-    const float pn = adam_one(ad, pi, grad[pi]);
+    const float pn = adam_one(ad, pi, grad[pi], adam_scalars(ad));
     if (ad.wimg) { if (is_w) im.put_w(ad.wimg, l, k, j, pn); else im.put_b(ad.wimg, l, j, pn); }
 }
 
@@ -1215,8 +1225,8 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     float *loss = a->loss ? a->loss : (float *)lnb_arena_take(ctx, 16);
 #ifdef LNB_TC_CLK
     float *dbg_dev = nullptr;
-    cudaMalloc(&dbg_dev, (size_t)grid * 28 * sizeof(float));
-    cudaMemset(dbg_dev, 0, (size_t)grid * 28 * sizeof(float));
+    cudaMalloc(&dbg_dev, (size_t)grid * 28 * sizeof(float) * 8);
+    cudaMemset(dbg_dev, 0, (size_t)grid * 28 * sizeof(float) * 8);
     p.dbg = dbg_dev;
 #endif
     cudaLaunchAttribute pdl_attr[1];
@@ -1259,10 +1269,27 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     {
         cudaStreamSynchronize(ctx->stream);
         std::vector<float> h((size_t)grid * 28);
-        cudaMemcpy(h.data(), dbg_dev, h.size() * sizeof(float), cudaMemcpyDeviceToHost);
-        cudaFree(dbg_dev);
+        if (!mg) {
+            cudaMemcpy(h.data(), dbg_dev, h.size() * sizeof(float), cudaMemcpyDeviceToHost);
+            cudaFree(dbg_dev);
+        }
         static int calls = 0;
-        if (++calls % 150 == 20) {
+        if (mg) {
+            std::vector<unsigned long long> hs((size_t)grid * ng * 8);
+            cudaMemcpy(hs.data(), dbg_dev, hs.size() * 8, cudaMemcpyDeviceToHost);
+            cudaFree(dbg_dev);
+            if (++calls % 50 == 20) {
+                unsigned long long t0 = ~0ull;
+                for (size_t i = 0; i < hs.size(); i += 8) t0 = hs[i] < t0 ? hs[i] : t0;
+                const char *nm[7] = {"CTA start", "prologue done", "weights landed", "first tile done", "last tile done", "all groups done", "end"};
+                fprintf(stderr, "[mg clk] grid %d x %d groups, %d tiles: us from the first CTA start (min / mean / max over groups that have the stamp)\n", grid, ng, p.n_tiles);
+                for (int k = 0; k < 7; ++k) {
+                    double mn = 1e30, mx = 0, sum = 0; int n = 0;
+                    for (size_t i = 0; i < hs.size(); i += 8) if (hs[i + k]) { const double v = (hs[i + k] - t0) * 1e-3; mn = v < mn ? v : mn; mx = v > mx ? v : mx; sum += v; ++n; }
+                    if (n) fprintf(stderr, "   %-16s %7.2f %7.2f %7.2f   (%d)\n", nm[k], mn, sum / n, mx, n);
+                }
+            }
+        } else if (++calls % 150 == 20) {
             double acc[24] = {0};
             for (int b = 0; b < grid; ++b) for (int i = 0; i < 24; ++i) acc[i] += h[(size_t)b * 24 + i];
             const char *nm[24] = {"wait X", "convert+publish", "issue fwd", "wait fwd mma", "fwd epilogue", "fwd publish", "issue fwd AGAIN (experiment)", "dz publish",
