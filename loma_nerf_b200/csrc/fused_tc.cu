@@ -916,41 +916,42 @@ __global__ void __launch_bounds__(1024) tc_reduce_kernel(const float *__restrict
     __shared__ AdamScalars s_adam;
     asm volatile("griddepcontrol.wait;" ::: "memory");              // the fused kernel's partials are complete
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); // the next step may start its prologue
-    if (fuse_adam && threadIdx.x == 1023) s_adam = adam_scalars(ad); // while the other warps gather the partials
-    // every block sums the loss partials itself (same order everywhere) so the seed needs no second pass
-    if (threadIdx.x < 32) {
+    // Three things run side by side, one barrier at the end: warp 31 sums the loss partials (every block itself, same order
+    // everywhere, so the seed needs no second pass), one thread of warp 30 derives the Adam scalars (two double-precision
+    // pow()), warps 0-29 gather the gradient partials: 32 consecutive elements per block (one coalesced 128 B line per
+    // partial), the warps stride over the partials with all their loads in flight, fixed-order combine through shared memory.
+    __shared__ float acc[30][33];
+    const int el = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int n_el = part_stride - 1;
+    const int e_glob = blockIdx.x * 32 + el;
+    if (grp == 31) {
         float s = 0.0f;
-        for (int i = threadIdx.x; i < n_part; i += 32) s += part[(size_t)i * part_stride];
+        for (int i = el; i < n_part; i += 32) s += part[(size_t)i * part_stride];
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-        if (threadIdx.x == 0) {
+        if (el == 0) {
             sloss = s;
             if (blockIdx.x == 0 && loss) loss[0] = s;
             if (blockIdx.x == 0 && p.tile_counter) p.tile_counter[0] = 0; // ready for the next launch
         }
+    } else if (grp == 30) {
+        if (fuse_adam && el == 0 && d_ws) s_adam = adam_scalars(ad);
+    } else if (d_ws) {
+        float s = 0.0f;
+        if (e_glob < n_el) {
+            const float *src = part + 1 + e_glob;
+#pragma unroll 5
+            for (int i = grp; i < n_part; i += 30) s += src[(size_t)i * part_stride];
+        }
+        acc[grp][el] = s;
     }
     __syncthreads();
     if (!d_ws) return;
     const float scale = seed_is_loss ? sloss * seed_value : seed_value;
-    // 32 consecutive elements per block (one coalesced 128 B line per partial), 32 warps stride over
-    // the partials with all their loads in flight, fixed-order combine through shared memory
-    __shared__ float acc[32][33];
-    const int el = threadIdx.x & 31, grp = threadIdx.x >> 5;
-    const int n_el = part_stride - 1;
-    const int e_glob = blockIdx.x * 32 + el;
-    float s = 0.0f;
-    if (e_glob < n_el) {
-        const float *src = part + 1 + e_glob;
-#pragma unroll 8
-        for (int i = grp; i < n_part; i += 32) s += src[(size_t)i * part_stride];
-    }
-    acc[grp][el] = s;
-    __syncthreads();
-    float g_local = 0.0f;
+    float g_local = 0.0f, s = 0.0f;
     if (grp == 0) {
-        s = 0.0f;
 #pragma unroll
-        for (int w2 = 0; w2 < 32; ++w2) s += acc[w2][el];
+        for (int w2 = 0; w2 < 30; ++w2) s += acc[w2][el];
         g_local = scale * s;
     }
     float loss_total = sloss;
