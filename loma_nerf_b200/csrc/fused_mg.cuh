@@ -593,6 +593,7 @@ __global__ void __launch_bounds__(mg_max_groups<HP>() * TILE, 1) fused_mg_kernel
             }
         }
     }
+    MG_STAMP(7);
     tc_fence_before();
     __syncthreads();
     if (g == 0 && warp == 0) tmem_dealloc(tmem, tmem_cols);

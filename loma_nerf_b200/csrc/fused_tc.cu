@@ -1282,9 +1282,9 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
             if (++calls % 50 == 20) {
                 unsigned long long t0 = ~0ull;
                 for (size_t i = 0; i < hs.size(); i += 8) t0 = hs[i] < t0 ? hs[i] : t0;
-                const char *nm[7] = {"CTA start", "prologue done", "weights landed", "first tile done", "last tile done", "all groups done", "end"};
+                const char *nm[8] = {"CTA start", "prologue done", "weights landed", "first tile done", "last tile done", "all groups done", "end", "partials written"};
                 fprintf(stderr, "[mg clk] grid %d x %d groups, %d tiles: us from the first CTA start (min / mean / max over groups that have the stamp)\n", grid, ng, p.n_tiles);
-                for (int k = 0; k < 7; ++k) {
+                for (int k = 0; k < 8; ++k) {
                     double mn = 1e30, mx = 0, sum = 0; int n = 0;
                     for (size_t i = 0; i < hs.size(); i += 8) if (hs[i + k]) { const double v = (hs[i + k] - t0) * 1e-3; mn = v < mn ? v : mn; mx = v > mx ? v : mx; sum += v; ++n; }
                     if (n) fprintf(stderr, "   %-16s %7.2f %7.2f %7.2f   (%d)\n", nm[k], mn, sum / n, mx, n);

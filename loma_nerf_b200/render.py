@@ -96,12 +96,51 @@ def pose_spherical(theta_deg, phi_deg, radius):
     return flip @ rot_th @ rot_phi @ trans
 
 
+def write_mjpeg_avi(path, frames, fps=30, quality=90):
+    """Motion-JPEG in an AVI container (RIFF: hdrl with avih / strh / strf, movi of '00dc' chunks, idx1), written with PIL
+    alone: the video a stock Python can produce without ffmpeg / imageio (the hosts' make_nerf_video.py:21-38 asks imageio
+    for an mp4).  frames: uint8 [F][H][W][3]."""
+    import io
+    import struct
+    from PIL import Image
+    frames = np.asarray(frames, np.uint8)
+    n, h, w = int(frames.shape[0]), int(frames.shape[1]), int(frames.shape[2])
+    jpgs = []
+    for f in frames:
+        b = io.BytesIO()
+        Image.fromarray(f).save(b, format="JPEG", quality=quality)
+        jpgs.append(b.getvalue())
+
+    def chunk(tag, data):
+        return tag + struct.pack("<I", len(data)) + data + (b"\0" if len(data) & 1 else b"")
+
+    def lst(tag, data):
+        return b"LIST" + struct.pack("<I", len(data) + 4) + tag + data
+
+    biggest = max((len(j) for j in jpgs), default=0)
+    avih = struct.pack("<IIIIIIIIII4I", int(1e6 / fps), biggest * fps, 0, 0x10, n, 0, 1, biggest, w, h, 0, 0, 0, 0)
+    strh = struct.pack("<4s4sIHHIIIIIIIIhhhh", b"vids", b"MJPG", 0, 0, 0, 0, 1, fps, 0, n, biggest, 0xFFFFFFFF, 0, 0, 0, w, h)
+    strf = struct.pack("<IiiHH4sIiiII", 40, w, h, 1, 24, b"MJPG", w * h * 3, 0, 0, 0, 0)
+    hdrl = lst(b"hdrl", chunk(b"avih", avih) + lst(b"strl", chunk(b"strh", strh) + chunk(b"strf", strf)))
+    movi, idx, off = b"", b"", 4
+    for j in jpgs:
+        c = chunk(b"00dc", j)
+        idx += struct.pack("<4sIII", b"00dc", 0x10, off, len(j))
+        movi += c
+        off += len(c)
+    body = b"AVI " + hdrl + lst(b"movi", movi) + chunk(b"idx1", idx)
+    with open(path, "wb") as fh:
+        fh.write(b"RIFF" + struct.pack("<I", len(body)) + body)
+    return path
+
+
 def render_video(ctx, dims, ws, bs, height, width, normalized_K, poses, n_samples, pe_bands, out_dir=None, near=2.0, far=6.0,
                  path="tc", ground_truth=None, fps=30, frame_fn=None):
     """What make_nerf_video.py is named for but does not do (it stitches ground-truth PNGs): render one frame per
     camera pose with the trained weights, optionally score each against its ground-truth image
-    (train_nerf.py:163-183) and write frame_%04d.png plus an animated orbit.gif into out_dir (PIL; mp4 needs
-    imageio/ffmpeg, which the hosts' environment may not have).  Returns (frames uint8 [F][H][W][3], psnr list | None).
+    (train_nerf.py:163-183) and write frame_%04d.png, an animated orbit.gif and a Motion-JPEG orbit.avi into out_dir (PIL
+    only; an mp4 needs imageio/ffmpeg, which the hosts' environment may not have).  Returns (frames uint8 [F][H][W][3],
+    psnr list | None).
     frame_fn(i, pose) -> float image may replace the device render (tests of the host side)."""
     frames, psnr = [], ([] if ground_truth is not None else None)
     for i, pose in enumerate(poses):
@@ -120,4 +159,5 @@ def render_video(ctx, dims, ws, bs, height, width, normalized_K, poses, n_sample
         for i, im in enumerate(pil):
             im.save(os.path.join(out_dir, "frame_%04d.png" % i))
         pil[0].save(os.path.join(out_dir, "orbit.gif"), save_all=True, append_images=pil[1:], duration=max(1, int(1000 / fps)), loop=0)
+        write_mjpeg_avi(os.path.join(out_dir, "orbit.avi"), frames, fps=fps)
     return frames, psnr

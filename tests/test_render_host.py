@@ -85,3 +85,28 @@ def test_render_video_writes_frames_gif_and_psnr(tmp_path):
         assert np.array(Image.open(tmp_path / ("frame_%04d.png" % i))).shape == (H, H, 3)
     gif = Image.open(tmp_path / "orbit.gif")
     assert getattr(gif, "n_frames", 1) == 3
+    # the Motion-JPEG AVI: walk the RIFF structure and decode every frame chunk
+    import io
+    import struct
+    raw = open(tmp_path / "orbit.avi", "rb").read()
+    assert raw[:4] == b"RIFF" and raw[8:12] == b"AVI " and struct.unpack("<I", raw[4:8])[0] == len(raw) - 8
+    pos, got, n_idx = 12, [], 0
+    while pos < len(raw):
+        tag, size = raw[pos:pos + 4], struct.unpack("<I", raw[pos + 4:pos + 8])[0]
+        if tag == b"LIST" and raw[pos + 8:pos + 12] == b"hdrl":
+            avih = raw[pos + 20:pos + 20 + 56]
+            assert raw[pos + 12:pos + 16] == b"avih" and struct.unpack("<I", avih[16:20])[0] == 3          # total frames
+            assert struct.unpack("<II", avih[32:40]) == (H, H)
+        if tag == b"LIST" and raw[pos + 8:pos + 12] == b"movi":
+            q = pos + 12
+            while q < pos + 8 + size:
+                ctag, csize = raw[q:q + 4], struct.unpack("<I", raw[q + 4:q + 8])[0]
+                assert ctag == b"00dc"
+                got.append(np.array(Image.open(io.BytesIO(raw[q + 8:q + 8 + csize]))))
+                q += 8 + csize + (csize & 1)
+        if tag == b"idx1":
+            n_idx = size // 16
+        pos += 8 + size + (size & 1)
+    assert len(got) == 3 and n_idx == 3
+    for i in range(3):
+        assert got[i].shape == (H, H, 3) and np.abs(got[i].astype(int) - frames[i].astype(int)).max() <= 6   # JPEG
