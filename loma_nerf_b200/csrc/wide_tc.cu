@@ -11,7 +11,7 @@
 // Kernels (all warp-specialised and persistent, one CTA per SM, TMA + mbarrier pipelines):
 //   chain_tc_kernel  the forward pass and the adjoint pass, each ONE launch: a CTA takes blocks of its 128-sample
 //                    tiles through all layers, the layer's weights in shared memory, the activations handed from
-//                    layer to layer through L2; tcgen05.mma (M = 128 or, on CTA pairs, 256; N <= 256; K = 16) into
+//                    layer to layer through L2; tcgen05.mma (M = 128, N <= 256, K = 16) into
 //                    two TMEM accumulators, 16 epilogue warps (tcgen05.ld -> bias / ReLU + bit pattern / mask ->
 //                    bf16 -> swizzled staging -> TMA store).  The default.
 //   gemm_tc_kernel   the same GEMM + epilogues as one launch per layer (tests, ray slabs, LNB_WIDE_NO_CHAIN).
@@ -404,55 +404,18 @@ __device__ __forceinline__ void bulk_wait_group_n(int n)
     else asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-// ---- CTA pairs (cta_group::2): two CTAs of a cluster run ONE tcgen05.mma of M = 256 -- each supplies its own 128
-// rows of A and HALF of B's rows (N/2), so an SM reads 4 + 4 KB of operands per MMA instead of 4 + 8 and holds half
-// the weights.  The leader (cluster rank 0) issues the MMAs; its "full" barriers collect the TMA bytes of both
-// CTAs (the peer's loads name the leader's barrier), and tcgen05.commit multicasts completions to both.
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta)
-{
-    asm volatile("{\n\t.reg .b32 r;\n\tmapa.shared::cluster.u32 r, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [r];\n\t}" ::"r"(bar), "r"(cta) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar)
-{   // the barrier operand with the peer bit cleared is the LEADER's barrier at this offset
-    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar)
-{
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst, uint32_t cols)
-{
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t cols) { asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory"); }
-
-template <bool PAIR>
 __global__ void __launch_bounds__(CHAIN_THREADS, 1)
 chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = (p.M + BM - 1) / BM;
-    // work units: a tile, or (PAIR) two consecutive tiles, one per CTA of the pair
-    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
-    const bool leader = rank == 0;
-    const int n_units = PAIR ? (n_tiles + 1) / 2 : n_tiles, n_workers = PAIR ? (int)gridDim.x / 2 : (int)gridDim.x;
-    const int unit0 = PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x;
+    // work units: tiles, dealt round-robin over the CTAs
+    const int n_units = n_tiles, n_workers = (int)gridDim.x;
+    const int unit0 = (int)blockIdx.x;
     const int n_my = unit0 < n_units ? (n_units - unit0 + n_workers - 1) / n_workers : 0;
-    auto tile_of = [&](int i) { const int u = unit0 + i * n_workers; return PAIR ? 2 * u + (int)rank : u; };
-    constexpr int B_CHUNK = PAIR ? 128 * BK * 2 : 256 * BK * 2;     // bytes between weight chunks (uniform for all layers)
+    auto tile_of = [&](int i) { return unit0 + i * n_workers; };
+    constexpr int B_CHUNK = 256 * BK * 2;     // bytes between weight chunks (uniform for all layers)
     const int AS = p.a_stages;
     uint8_t *sB = smem, *sA = smem + p.b_region;
     uint8_t *sC = sA + AS * A_STAGE_BYTES;
@@ -464,15 +427,15 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
     constexpr uint32_t acc_cols = 256;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < AS; ++s) { mbar_init(full0 + 8 * s, PAIR ? 2 : 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, PAIR ? 32 : 16); }   // one arrival per epilogue warp
-        for (int k = 0; k < 4; ++k) { mbar_init(bfull0 + 8 * k, PAIR ? 2 : 1); mbar_init(bempty0 + 8 * k, 1); }
+        for (int s = 0; s < AS; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 16); }   // one arrival per epilogue warp
+        for (int k = 0; k < 4; ++k) { mbar_init(bfull0 + 8 * k, 1); mbar_init(bempty0 + 8 * k, 1); }
         for (int j = 0; j < CHAIN_MAX_G; ++j) mbar_init(done0 + 8 * j, 16);     // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) { if (PAIR) tmem_alloc_2sm(smem_u32(tmem_slot), 2 * acc_cols); else tmem_alloc(smem_u32(tmem_slot), 2 * acc_cols); }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * acc_cols);
     tc_fence_before();
-    if (PAIR) cluster_sync_all(); else __syncthreads();
+    __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
@@ -487,25 +450,17 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                 for (int li = 0; li < p.n_layers; ++li, ++round) {
                     // weight chunk kb always sits at kb * 32 KB whatever the layer's N, so "chunk kb released" means the same
                     // bytes for every layer
-                    const int kb_count = p.layer[li].K / BK, b_rows = PAIR ? p.layer[li].N / 2 : p.layer[li].N, b_bytes = b_rows * BK * 2;
+                    const int kb_count = p.layer[li].K / BK, b_rows = p.layer[li].N, b_bytes = b_rows * BK * 2;
                     for (int kb = 0; kb < 4; ++kb) {
                         // last round's MMAs on this chunk have retired.  Also for a chunk this layer does not use: its
                         // "full" barrier is advanced by a plain arrive below, and that must not overtake the MMA
                         // thread's wait for the previous phase (it can when a round has a single tile)
                         if (round > 0) mbar_wait(bempty0 + 8 * kb, (round - 1) & 1);
                         if (kb < kb_count) {
-                            if (PAIR) {
-                                if (leader) mbar_expect_tx(bfull0 + 8 * kb, (uint32_t)(2 * b_bytes));   // both CTAs' halves land on this barrier
-                                tma_load_2d_2sm(smem_u32(sB + kb * B_CHUNK), &maps.B[li], kb * BK, (int)rank * b_rows, bfull0 + 8 * kb);
-                                if (!leader) mbar_arrive_remote(bfull0 + 8 * kb, 0);
-                            } else {
-                                mbar_expect_tx(bfull0 + 8 * kb, (uint32_t)b_bytes);
-                                tma_load_2d(smem_u32(sB + kb * B_CHUNK), &maps.B[li], kb * BK, 0, bfull0 + 8 * kb);
-                            }
-                        } else if (PAIR && !leader) {
-                            mbar_arrive_remote(bfull0 + 8 * kb, 0);                         // keep the phases of unused chunks in step
+                            mbar_expect_tx(bfull0 + 8 * kb, (uint32_t)b_bytes);
+                            tma_load_2d(smem_u32(sB + kb * B_CHUNK), &maps.B[li], kb * BK, 0, bfull0 + 8 * kb);
                         } else {
-                            mbar_arrive(bfull0 + 8 * kb);
+                            mbar_arrive(bfull0 + 8 * kb);                                   // keep the phases of unused chunks in step
                         }
                     }
                     for (int j = 0; j < g_cnt; ++j) {
@@ -516,15 +471,9 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                         }
                         for (int kb = 0; kb < kb_count; ++kb) {
                             mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                            if (PAIR) {
-                                if (leader) mbar_expect_tx(full0 + 8 * stage, (uint32_t)(2 * A_STAGE_BYTES));
-                                tma_load_2d_2sm(smem_u32(sA + stage * A_STAGE_BYTES), &maps.A[li], kb * BK, tile * BM, full0 + 8 * stage);
-                                if (!leader) mbar_arrive_remote(full0 + 8 * stage, 0);
-                            } else {
-                                mbar_expect_tx(full0 + 8 * stage, (uint32_t)A_STAGE_BYTES);
-                                if (p.l2_hints & 1) tma_load_2d_hint(smem_u32(sA + stage * A_STAGE_BYTES), &maps.A[li], kb * BK, tile * BM, full0 + 8 * stage, L2_EVICT_FIRST);
-                                else tma_load_2d(smem_u32(sA + stage * A_STAGE_BYTES), &maps.A[li], kb * BK, tile * BM, full0 + 8 * stage);
-                            }
+                            mbar_expect_tx(full0 + 8 * stage, (uint32_t)A_STAGE_BYTES);
+                            if (p.l2_hints & 1) tma_load_2d_hint(smem_u32(sA + stage * A_STAGE_BYTES), &maps.A[li], kb * BK, tile * BM, full0 + 8 * stage, L2_EVICT_FIRST);
+                            else tma_load_2d(smem_u32(sA + stage * A_STAGE_BYTES), &maps.A[li], kb * BK, tile * BM, full0 + 8 * stage);
                             if (++stage == (uint32_t)AS) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -532,10 +481,10 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        // ---- MMA issuer (the leader CTA of a pair only)
-        if (lane == 0 && leader) {
+        // ---- MMA issuer
+        if (lane == 0) {
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, round = 0;
-            auto commit = [](uint32_t bar) { if (PAIR) umma_commit_2sm(bar); else umma_commit(bar); };   // pairs: to both CTAs
+            auto commit = [](uint32_t bar) { umma_commit(bar); };
 #ifdef LNB_WIDE_CLK
             const long long t_begin = clock64();
 #endif
@@ -543,7 +492,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                 const int g_cnt = n_my - blk < p.G ? n_my - blk : p.G;
                 for (int li = 0; li < p.n_layers; ++li, ++round) {
                     const int kb_count = p.layer[li].K / BK;
-                    const uint32_t idesc = instr_desc(PAIR ? 256 : 128, p.layer[li].N, 0, 0);
+                    const uint32_t idesc = instr_desc(128, p.layer[li].N, 0, 0);
                     for (int j = 0; j < g_cnt; ++j) {
                         { WCLK_T0(); mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1); WCLK_ADD(0); }
                         tc_fence_after();
@@ -554,9 +503,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                             const uint32_t a0 = smem_u32(sA + stage * A_STAGE_BYTES), b0 = smem_u32(sB + kb * B_CHUNK);
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k) {
-                                if (PAIR) umma_bf16_2sm(tmem + acc * acc_cols, sw128_desc(a0 + k * 32, 16, 1024), sw128_desc(b0 + k * 32, 16, 1024), idesc,
-                                                        (kb > 0 || k > 0) ? 1u : 0u);
-                                else umma_bf16(tmem + acc * acc_cols, sw128_desc(a0 + k * 32, 16, 1024), sw128_desc(b0 + k * 32, 16, 1024), idesc,
+                                umma_bf16(tmem + acc * acc_cols, sw128_desc(a0 + k * 32, 16, 1024), sw128_desc(b0 + k * 32, 16, 1024), idesc,
                                                (kb > 0 || k > 0) ? 1u : 0u);
                             }
                             commit(empty0 + 8 * stage);
@@ -669,7 +616,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
                     }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) { if (PAIR && !leader) mbar_arrive_remote(tempty0 + 8 * acc, 0); else mbar_arrive(tempty0 + 8 * acc); }
+                    if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
 #ifdef LNB_WIDE_CLK
                     if (threadIdx.x == 64) atomicAdd(&g_wide_clk[5], (unsigned long long)(clock64() - t_epi));
@@ -688,8 +635,8 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
     }
     if (warp >= 2) tma_store_wait_all();
     tc_fence_before();
-    if (PAIR) cluster_sync_all(); else __syncthreads();
-    if (warp == 1) { if (PAIR) tmem_dealloc_2sm(tmem, 2 * acc_cols); else tmem_dealloc(tmem, 2 * acc_cols); }
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 2 * acc_cols);
 }
 
 // ---- host helpers ------------------------------------------------------------------------------
@@ -1064,14 +1011,11 @@ int lnb_wide_chain(lnb_ctx *ctx, const ChainDesc *d, int n, long long M, int hea
     ChainMaps maps;              // 6 KB, passed by value at launch
     ChainParams p{};
     size_t b_region = 0;
-    // CTA pairs (cta_group::2, see the kernel): LNB_WIDE_CTA_PAIR=0 turns them off
-    static const bool pair_on = [] { const char *e = getenv("LNB_WIDE_CTA_PAIR"); return e ? atoi(e) != 0 : false; }();
-    const bool pair = pair_on && ctx->sm_count % 2 == 0 && (M + BM - 1) / BM >= 2 * (long long)ctx->sm_count;
     for (int i = 0; i < n; ++i) {
         const ChainDesc &c = d[i];
         LNB_ARG(c.N >= 16 && c.N <= 256 && c.N % 16 == 0 && c.K >= 64 && c.K <= 256 && c.K % 64 == 0 && c.lda % 8 == 0 && c.ldb % 8 == 0, "wide chain: shape");
         LNB_TRY(make_map(ctx, &maps.A[i], c.A, M, c.K, c.lda, BM));
-        LNB_TRY(make_map(ctx, &maps.B[i], c.B, c.N, c.K, c.ldb, pair ? c.N / 2 : c.N));
+        LNB_TRY(make_map(ctx, &maps.B[i], c.B, c.N, c.K, c.ldb, c.N));
         maps.C[i] = maps.A[i];
         if (c.epi == EPI_RELU_BF16 || c.epi == EPI_MASK_BF16) {
             LNB_ARG(c.N % 64 == 0 && c.ldc % 8 == 0 && c.ldc >= c.N, "wide chain: bf16 layers are multiples of 64 wide");
@@ -1083,7 +1027,7 @@ int lnb_wide_chain(lnb_ctx *ctx, const ChainDesc *d, int n, long long M, int hea
         ChainLayer &l = p.layer[i];
         l.bias = c.bias; l.bits_in = c.bits_in; l.bits_out = c.bits_out; l.head_out = c.epi == EPI_HEAD_F32 ? (float *)c.C : nullptr;
         l.ldbits = c.ldbits; l.N = c.N; l.K = c.K; l.epi = c.epi;
-        const size_t chunk = pair ? 128 * BK * 2 : 256 * BK * 2, rows = pair ? c.N / 2 : c.N;   // chunks 16 / 32 KB apart
+        const size_t chunk = 256 * BK * 2, rows = c.N;   // chunks 32 KB apart
         const size_t need = (size_t)(c.K / BK - 1) * chunk + ((rows * BK * 2 + 1023) / 1024 * 1024);
         b_region = need > b_region ? need : b_region;
     }
@@ -1097,22 +1041,13 @@ int lnb_wide_chain(lnb_ctx *ctx, const ChainDesc *d, int n, long long M, int hea
     LNB_ARG(p.a_stages >= 2, "wide chain: shared memory");
     const size_t smem = b_region + (size_t)p.a_stages * A_STAGE_BYTES + 16 * 2048 + (28 + CHAIN_MAX_G + 2) * 8 + 1024 + 16;
     const int n_tiles = (int)((M + BM - 1) / BM);
-    const int grid = pair ? ctx->sm_count : (n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count);
+    const int grid = n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count;
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[2];
     pdl_config(&cfg, attr, grid, CHAIN_THREADS, smem, ctx->stream);
-    if (pair) {
-        LNB_CUDA(cudaFuncSetAttribute(chain_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr[cfg.numAttrs].id = cudaLaunchAttributeClusterDimension;
-        attr[cfg.numAttrs].val.clusterDim.x = 2; attr[cfg.numAttrs].val.clusterDim.y = 1; attr[cfg.numAttrs].val.clusterDim.z = 1;
-        ++cfg.numAttrs;
-        lnb_prof_begin(ctx, "chain_tc_kernel");
-        LNB_CUDA(cudaLaunchKernelEx(&cfg, chain_tc_kernel<true>, maps, p));
-    } else {
-        LNB_CUDA(cudaFuncSetAttribute(chain_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        lnb_prof_begin(ctx, "chain_tc_kernel");
-        LNB_CUDA(cudaLaunchKernelEx(&cfg, chain_tc_kernel<false>, maps, p));
-    }
+    LNB_CUDA(cudaFuncSetAttribute(chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lnb_prof_begin(ctx, "chain_tc_kernel");
+    LNB_CUDA(cudaLaunchKernelEx(&cfg, chain_tc_kernel, maps, p));
     lnb_prof_end(ctx);
     LNB_CHECK_LAUNCH();
     return LNB_OK;

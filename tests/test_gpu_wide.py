@@ -248,7 +248,7 @@ def test_chain_kernel_equals_one_launch_per_layer():
         return tok[1], tok[3], np.array([float(tok[5]), float(tok[7]), float(tok[9])])
 
     a, b, c = run({}), run({"LNB_WIDE_NO_CHAIN": "1"}), run({"LNB_WIDE_CHAIN_G": "3"})
-    d = run({"LNB_WIDE_CTA_PAIR": "1", "LNB_WIDE_CHAIN_G": "1"})      # CTA pairs (tcgen05.mma.cta_group::2), single-tile blocks
+    d = run({"LNB_WIDE_CHAIN_G": "1"})                                # single-tile blocks
     assert a[0] == b[0] == c[0] == d[0] and a[1] == b[1] == c[1] == d[1], (a, b, c, d)
     assert np.allclose(a[2], b[2], rtol=1e-5) and np.allclose(a[2], c[2], rtol=1e-5) and np.allclose(a[2], d[2], rtol=1e-5), (a, b, c, d)
 
