@@ -304,8 +304,10 @@ __global__ void tc_prep_kernel(const TcParams p, uint8_t *__restrict__ img)
 // fp32 sin/cos of the positional encoding (pos_encoding.py:38-70): one accurate sincosf per
 // coordinate, higher bands by angle doubling (sin 2a = 2 s c, cos 2a = 1 - 2 s^2).  The doubling
 // amplifies the base error by 2^(E-1): ~1e-6 at E = 5, far below the bf16 operand rounding.
-template <bool RAYS, int HP>
-__global__ void __launch_bounds__(TILE) fused_v1_kernel(const TcParams p)
+// FWD: the forward-only (render) form, compiled separately: nothing of the backward pass in its register budget (56
+// registers: nine CTAs per SM instead of seven)
+template <bool RAYS, int HP, bool FWD>
+__global__ void __launch_bounds__(TILE, FWD ? 9 : 1) fused_v1_kernel(const TcParams p)
 {
     using LY = TcLayout<HP>;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -316,14 +318,14 @@ __global__ void __launch_bounds__(TILE) fused_v1_kernel(const TcParams p)
 #endif
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = p.L, K0P = p.K0P, c_in = p.dims[0], S = p.S;
-    const int act_bytes = LY::act_bytes(L, K0P, p.want_grad != 0);
+    const int act_bytes = LY::act_bytes(L, K0P, !FWD);
     uint8_t *const Wbase = smem + act_bytes;
     const float *const bias_s = reinterpret_cast<const float *>(Wbase + LY::w_off(L, L, K0P));
     float *const stage = reinterpret_cast<float *>(Wbase + LY::wimg_bytes(L, K0P));
     const int stage_sz = RAYS ? 0 : LY::stage_bytes(c_in, K0P);
     // per-ray colour / target scratch aliases dZ_0: it is dead from the top of a tile (the previous
     // tile's dW MMAs have been awaited) until the last backward epilogue writes it
-    const bool fwd_only = p.want_grad == 0;
+    constexpr bool fwd_only = FWD;
     float *const color_s = reinterpret_cast<float *>(smem + (fwd_only ? LY::fwd_slabs(K0P) * SLAB : LY::dz_off(0, L, K0P)));
     float *const tgt_s = color_s + TILE * 3;
     float *const tailp = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(stage) + stage_sz); // [4] inclusive product at lane 31
@@ -385,7 +387,7 @@ __global__ void __launch_bounds__(TILE) fused_v1_kernel(const TcParams p)
                                    instr_desc(128, LY::ndw(L), 1, 1), (uint32_t)HP, (uint32_t)(TILE / 16), 2u, 0u, 0u};
         }
     }
-    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), LY::tmem_cols(L, p.want_grad != 0));
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), LY::tmem_cols(L, !FWD));
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -706,7 +708,7 @@ __global__ void __launch_bounds__(TILE) fused_v1_kernel(const TcParams p)
                     dc0 = 2.0f * d0; dc1 = 2.0f * d1; dc2 = 2.0f * d2;
                 }
             }
-            if (p.want_grad && p.target) {
+            if (!FWD && p.target) {
                 // G_s = dT_s + q_{s+1} G_{s+1}: suffix scan of affine maps; B = 0 at a ray's last sample
                 const float d_w = cr * dc0 + cg * dc1 + cb * dc2;
                 const float dT = (smp == 0 || !live) ? 0.0f : d_w * a;
@@ -739,7 +741,7 @@ __global__ void __launch_bounds__(TILE) fused_v1_kernel(const TcParams p)
             }
         }
         CLK(23);
-        if (!p.want_grad) { __syncthreads(); tile = *next_tile_s; continue; }
+        if (FWD) { __syncthreads(); tile = *next_tile_s; continue; }
         // ---- backward.  dZ_{L-1}: 4 live features, the rest of the 16 stay zero
         *row_ptr(dz_buf(L - 1), 0) = make_uint4(pack_bf16(dz[0], dz[1]), pack_bf16(dz[2], dz[3]), 0u, 0u);
         publish_smem();
@@ -794,7 +796,7 @@ __global__ void __launch_bounds__(TILE) fused_v1_kernel(const TcParams p)
     __syncthreads();
     if (tid == 0) part[0] = red_s[0] + red_s[1] + red_s[2] + red_s[3];
     if (tid == 0 && blockIdx.x == 0 && p.t_dev) p.t_dev[0] += 1; // read by the kernels that follow in the stream
-    if (p.want_grad) {
+    if (!FWD) {
         // accumulator row (TMEM lane) = feature index over the concatenated A buffers; thread tid
         // owns row tid: find the layer whose feature range contains it
         for (int l = 0; l < L; ++l) {
@@ -821,7 +823,7 @@ __global__ void __launch_bounds__(TILE) fused_v1_kernel(const TcParams p)
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, LY::tmem_cols(L, p.want_grad != 0));
+    if (warp == 0) tmem_dealloc(tmem, LY::tmem_cols(L, !FWD));
 #ifdef LNB_TC_CLK
     clk_acc[13] += clock64() - clk_t; // (issue dW slot reused: epilogue after the last tile)
     unsigned long long gt_end;
@@ -1246,7 +1248,8 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
 #define LNB_TC(HPV)                                                                              \
     do {                                                                                         \
         if (mg) { if (rays) LNB_LAUNCH((fused_mg_kernel<true, HPV>)); else LNB_LAUNCH((fused_mg_kernel<false, HPV>)); } \
-        else { if (rays) LNB_LAUNCH((fused_v1_kernel<true, HPV>)); else LNB_LAUNCH((fused_v1_kernel<false, HPV>)); } \
+        else if (grad) { if (rays) LNB_LAUNCH((fused_v1_kernel<true, HPV, false>)); else LNB_LAUNCH((fused_v1_kernel<false, HPV, false>)); } \
+        else { if (rays) LNB_LAUNCH((fused_v1_kernel<true, HPV, true>)); else LNB_LAUNCH((fused_v1_kernel<false, HPV, true>)); } \
     } while (0)
         if (!(ex && ex->wimg)) {
             if (HP == 16) tc_prep_kernel<16><<<1, 256, 0, ctx->stream>>>(p, wimg);
