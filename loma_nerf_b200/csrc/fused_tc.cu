@@ -123,6 +123,22 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from tensor memory (M = 128 rows = TMEM lanes; a 16-bit K-step of 16 is 8 columns, element 2c in the low half
+// of column c), B from shared memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait_() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -233,16 +249,16 @@ struct TcLayout {
     // forward only (render): no adjoint buffers, no dW accumulator -> more CTAs per SM
     __host__ __device__ static uint32_t tmem_cols(int L, bool grad = true)
     {
-        const int need = grad ? HP + ndw(L) : HP;
+        const int need = grad ? HP + ndw(L) : HP + HP / 2;   // forward only: result columns + the next layer's bf16 A operand
         return need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512)));
     }
     static constexpr int MAX_STAGES = 2 * MAXL + 1; // records of the per-CTA MMA program
     __host__ __device__ static int a_off(int l, int K0P) { return l == 0 ? 0 : (K0P / 8 + (l - 1) * HSL) * SLAB; }
     __host__ __device__ static int dz_off(int l, int L, int K0P) { return (K0P / 8 + (L - 1) * HSL + l * HSL) * SLAB; }
-    // forward only (render): nothing is kept for a weight gradient, so every layer's input lives in the SAME buffer -- A_{l+1}
-    // overwrites A_l once layer l's MMA has completed -- followed by two slabs of per-ray colour / target scratch.  That is
-    // 16 KB + the weight image per CTA in rays mode: 9 tiles in flight per SM instead of 5.
-    __host__ __device__ static int fwd_slabs(int K0P) { return K0P / 8 > HSL ? K0P / 8 : HSL; }
+    // forward only (render): nothing is kept for a weight gradient, so only A_0 is in shared memory; the hidden activations
+    // go from the epilogue's registers straight into TENSOR MEMORY (tcgen05.st) and the next layer's MMA takes its A operand
+    // from there: no shared-memory store, no operand fetch.  A_0 is followed by two slabs of per-ray colour / target scratch.
+    __host__ __device__ static int fwd_slabs(int K0P) { return K0P / 8; }
     __host__ __device__ static int act_bytes(int L, int K0P, bool grad = true)
     {
         return grad ? (K0P / 8 + 2 * (L - 1) * HSL + 2) * SLAB : (fwd_slabs(K0P) + 2) * SLAB;
@@ -374,6 +390,7 @@ __global__ void __launch_bounds__(TILE, FWD ? 9 : 1) fused_v1_kernel(const TcPar
             const uint32_t a0 = smem_u32(smem + (fwd_only ? 0 : LY::a_off(l, K0P))), b0 = smem_u32(Wbase + LY::w_off(l, L, K0P));
             prog[l] = StageRec{smem_desc(a0, SLAB, 128), smem_desc(b0, Np * 16, 128), (uint32_t)(2 * SLAB) >> 4, (uint32_t)(2 * Np * 16) >> 4,
                                instr_desc(128, Np, 0, 0), 0u, (uint32_t)(Kp / 16), 0u, 0u, 0u};
+            if (fwd_only && l > 0) { prog[l].a = (uint64_t)HP; prog[l].inc_a = 8u; prog[l].pad0 = 1u; }   // A from TMEM, 8 columns per K-step
         }
         for (int l = 1; l < L; ++l) {          // dH_l[128 x Kp] = dZ_l[128 x Np] * W_l^T (same W bytes, MN-major)
             const int Np = LY::np(l, L), Kp = LY::kp(l, K0P);
@@ -428,6 +445,13 @@ __global__ void __launch_bounds__(TILE, FWD ? 9 : 1) fused_v1_kernel(const TcPar
         const uint32_t ahi = r0.y, bhi = r0.w;
         uint32_t acc = r2.y == 2u ? (dw_started ? 1u : 0u) : r2.y;
         const uint32_t d = tmem + r1.w;
+        if (FWD && r2.z) {               // A operand in tensor memory
+            for (uint32_t k = 0; k < r2.x; ++k) {
+                umma_bf16_ts(d, tmem + alo, ((uint64_t)bhi << 32) | blo, r1.z, acc);
+                alo += r1.x; blo += r1.y; acc = 1u;
+            }
+            return;
+        }
         for (uint32_t k = 0; k < r2.x; ++k) {
             umma_bf16(d, ((uint64_t)ahi << 32) | alo, ((uint64_t)bhi << 32) | blo, r1.z, acc);
             alo += r1.x; blo += r1.y; acc = 1u;
@@ -619,9 +643,14 @@ __global__ void __launch_bounds__(TILE, FWD ? 9 : 1) fused_v1_kernel(const TcPar
                     uint32_t o[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) o[j] = pack_relu_bf16(__uint_as_float(v[c16][2 * j]), __uint_as_float(v[c16][2 * j + 1]));
-                    *row_ptr(an, c16 * 2) = make_uint4(o[0], o[1], o[2], o[3]);
-                    *row_ptr(an, c16 * 2 + 1) = make_uint4(o[4], o[5], o[6], o[7]);
+                    if (FWD) {
+                        tmem_st8(tmem + lane_base + (uint32_t)(HP + c16 * 8), o);
+                    } else {
+                        *row_ptr(an, c16 * 2) = make_uint4(o[0], o[1], o[2], o[3]);
+                        *row_ptr(an, c16 * 2 + 1) = make_uint4(o[4], o[5], o[6], o[7]);
+                    }
                 }
+                if (FWD) tmem_st_wait_();
                 CLK(4);
                 publish_smem();
                 CLK(5);
