@@ -45,7 +45,8 @@ struct MgLayout {
         return nat;
     }
     __host__ __device__ static int ndw(int L) { return (L - 1) * HP + 16; }
-    __host__ __device__ static int tmem_need(int L, int ng) { return ng * HP + ndw(L); }
+    // per group HP result columns + HP/2 columns of bf16 A operand (the forward / dH MMAs of layers >= 1 take A from TMEM)
+    __host__ __device__ static int tmem_need(int L, int ng) { return ng * (HP + HP / 2) + ndw(L); }
     __host__ __device__ static size_t total(int L, int c_in, int K0P, bool rays, int ng)
     {
         const int A0S = a0s(c_in);
@@ -153,15 +154,16 @@ __global__ void __launch_bounds__(mg_max_groups<HP>() * TILE, 1) fused_mg_kernel
     // the MMA program: one record per stage, one THREAD per record (a single thread building all of them cost 3 us)
     if (tid >= 32 && tid < 32 + 3 * L) {
         const int r = tid - 32, kind = r / L, l = r % L;
-        const uint32_t dcol = (uint32_t)(g * HP);
+        const uint32_t dcol = (uint32_t)(g * HP), acol = (uint32_t)(NG * HP + MG::ndw(L) + g * (HP / 2));
         const int Np = LY::np(l, L), Kp = LY::kp(l, K0P);
         const uint32_t wl = smem_u32(Wbase + LY::w_off(l, L, K0P));
         if (kind == 0) {               // D[128 x Np] = A_l[128 x Kp] * W_l   (A, B K-major)
             prog[l] = StageRec{smem_desc(smem_u32(a_buf(l)), SLAB, 128), smem_desc(wl, Np * 16, 128), (uint32_t)(2 * SLAB) >> 4, (uint32_t)(2 * Np * 16) >> 4,
                                instr_desc(128, Np, 0, 0), dcol, (uint32_t)(Kp / 16), 0u, 0u, 0u};
+            if (l > 0) { prog[l].a = (uint64_t)acol; prog[l].inc_a = 8u; prog[l].pad0 = 1u; }    // A from TMEM, 8 columns per K-step
         } else if (kind == 1) {        // dH_l[128 x Kp] = dZ_l[128 x Np] * W_l^T (same W bytes, MN-major); unused for l = 0
-            prog[L + l] = StageRec{smem_desc(smem_u32(dz_buf(l)), SLAB, 128), smem_desc(wl, 128, Np * 16), (uint32_t)(2 * SLAB) >> 4, 256u >> 4,
-                                   instr_desc(128, Kp, 0, 1), dcol, (uint32_t)(Np / 16), 0u, 0u, 0u};
+            prog[L + l] = StageRec{(uint64_t)acol, smem_desc(wl, 128, Np * 16), 8u, 256u >> 4,
+                                   instr_desc(128, Kp, 0, 1), dcol, (uint32_t)(Np / 16), 0u, 1u, 0u};       // A = dZ_l from TMEM
         } else {                       // dW_l[features x Np] += A_l^T dZ_l, K = the tile's 128 samples, both MN-major
             prog[2 * L + l] = StageRec{smem_desc(smem_u32(a_buf(l)), 128, SLAB), smem_desc(smem_u32(dz_buf(l)), 128, SLAB), 256u >> 4, 256u >> 4,
                                        instr_desc(64, Np, 1, 1), (uint32_t)(NG * HP + l * HP), (uint32_t)(TILE / 16), 1u, 0u, 0u};
@@ -211,11 +213,19 @@ __global__ void __launch_bounds__(mg_max_groups<HP>() * TILE, 1) fused_mg_kernel
         const uint32_t ahi = r0.y, bhi = r0.w;
         uint32_t acc = (k0 > 0) ? 1u : r2.y;
         const uint32_t d = tmem + r1.w;
+        if (r2.z) {                        // A operand in tensor memory
+            for (uint32_t k = k0; k < k1; ++k) {
+                umma_bf16_ts(d, tmem + alo, ((uint64_t)bhi << 32) | blo, r1.z, acc);
+                alo += r1.x; blo += r1.y; acc = 1u;
+            }
+            return;
+        }
         for (uint32_t k = k0; k < k1; ++k) {
             umma_bf16(d, ((uint64_t)ahi << 32) | alo, ((uint64_t)bhi << 32) | blo, r1.z, acc);
             alo += r1.x; blo += r1.y; acc = 1u;
         }
     };
+    const uint32_t a_tm = tmem + lane_base + (uint32_t)(NG * HP + MG::ndw(L) + g * (HP / 2));   // this row's bf16 A operand
     auto commit_and_wait = [&]() {
         if (tid == 0) umma_commit(bar_mma);
         mbar_wait(bar_mma, phase);
@@ -400,9 +410,11 @@ __global__ void __launch_bounds__(mg_max_groups<HP>() * TILE, 1) fused_mg_kernel
                     uint32_t o[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) o[j] = pack_relu_bf16(__uint_as_float(v[c16][2 * j]), __uint_as_float(v[c16][2 * j + 1]));
-                    *row_ptr(an, c16 * 2) = make_uint4(o[0], o[1], o[2], o[3]);
+                    *row_ptr(an, c16 * 2) = make_uint4(o[0], o[1], o[2], o[3]);       // for the weight gradient (MN-major operand)
                     *row_ptr(an, c16 * 2 + 1) = make_uint4(o[4], o[5], o[6], o[7]);
+                    tmem_st8(a_tm + (uint32_t)(c16 * 8), o);                          // for the next layer's MMA (A from TMEM)
                 }
+                tmem_st_wait_();
                 publish_smem();
             } else {
                 uint32_t v[16];
@@ -510,7 +522,12 @@ __global__ void __launch_bounds__(mg_max_groups<HP>() * TILE, 1) fused_mg_kernel
             }
         }
         // ---- backward.  dZ_{L-1}: 4 live features of its one slab
-        *row_ptr(dzl_buf, 0) = make_uint4(pack_bf16(dz[0], dz[1]), pack_bf16(dz[2], dz[3]), 0u, 0u);
+        {
+            const uint32_t o[8] = {pack_bf16(dz[0], dz[1]), pack_bf16(dz[2], dz[3]), 0u, 0u, 0u, 0u, 0u, 0u};
+            *row_ptr(dzl_buf, 0) = make_uint4(o[0], o[1], 0u, 0u);
+            tmem_st8(a_tm, o);
+            tmem_st_wait_();
+        }
         publish_smem();
         for (int l = L - 1; l >= 1; --l) {
             if (tid == 0) issue_steps(L + l, 0u, 64u);
@@ -536,6 +553,14 @@ __global__ void __launch_bounds__(mg_max_groups<HP>() * TILE, 1) fused_mg_kernel
                     o[j] = pack_bf16(__uint_as_float(v[c8 >> 1][e]), __uint_as_float(v[c8 >> 1][e + 1])) & gt0_mask_bf16x2(hw[j]);
                 }
                 oz[c8] = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            if (l > 1) {                       // dZ_{l-1} is the A operand of the next dH MMA
+#pragma unroll
+                for (int c16 = 0; c16 < HP / 16; ++c16) {
+                    const uint32_t o[8] = {oz[2 * c16].x, oz[2 * c16].y, oz[2 * c16].z, oz[2 * c16].w, oz[2 * c16 + 1].x, oz[2 * c16 + 1].y, oz[2 * c16 + 1].z, oz[2 * c16 + 1].w};
+                    tmem_st8(a_tm + (uint32_t)(c16 * 8), o);
+                }
+                tmem_st_wait_();
             }
             wait_dw();                         // ... and only now may A_l become dZ_{l-1}
 #pragma unroll
