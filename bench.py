@@ -580,7 +580,7 @@ def roofline_record(run, prof, m, peaks):
         peak = peaks.get("hbm_gbs", 6650.0)
         ach = alg_bytes / sec / 1e9
         traffic, traffic_src = None, None
-        for prof_csv in ("r02_fused_tc_features_ncu_full_summary.csv", "r01_fused_tc_features_ncu_full_summary.csv"):
+        for prof_csv in ("r02_mg_feat_ncu_full_summary.csv", "r01_fused_tc_features_ncu_full_summary.csv"):
             p = os.path.join(ROOT, "profiles", prof_csv)
             if run.wname == "c2" and traffic is None and os.path.exists(p):
                 # DRAM bytes of one launch of this kernel on this workload, from the committed ncu --set full capture

@@ -12,4 +12,4 @@ python tools/t_one_f32.py         > $O/p4.log 2>&1 && $NCU -k regex:fused_f32_ke
 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-render --no-extra --eager > $O/p5.log 2>&1 && \
   ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/r02_bench_launches.csv \
       python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-render --no-extra --eager > $O/n5.log 2>&1
-tail -1 $O/p1.log $O/p2.log $O/p3.log $O/p4.log
+for f in p1 p2 p3 p4; do tail -n 1 $O/$f.log; done
