@@ -120,7 +120,11 @@ enum { LNB_SEED_VALUE = 0,    /* backward seed _dreturn = args->seed            
 enum { LNB_PATH_F32 = 0,      /* fp32 CUDA-core kernels, <=1e-5 of the reference: the fused  */
                               /* kernel when the problem fits it, else the layerwise kernels */
        LNB_PATH_TC = 1,       /* tcgen05 tensor-core kernels (bf16 operands, fp32 accumulate);*/
-                              /* LNB_ERR_UNSUPPORTED when the problem does not fit them       */
+                              /* LNB_ERR_UNSUPPORTED when the problem does not fit them.      */
+                              /* Weight gradients are summed in tensor memory in MMA          */
+                              /* completion order: their last bits may differ between launches*/
+                              /* (colours and losses are bit-stable; LNB_PATH_F32 is fully    */
+                              /* reproducible)                                                */
        LNB_PATH_F32_LAYERWISE = 2 }; /* force the layerwise fp32 kernels (all intermediates)  */
 
 /* The MLP: weights in the reference's padded layout (mlp_utils.py:272-313):

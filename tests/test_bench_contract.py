@@ -45,3 +45,19 @@ def test_product_arm_has_no_cpu_fallback():
     out = _run(["--steps", "1", "--warmup", "0"], timeout=120)
     assert out.returncode != 0
     assert "CUDA" in (out.stderr + out.stdout)
+
+
+def test_timed_region_is_cut_into_whole_rotations_of_the_batch_pool():
+    """bench.py replays CUDA graphs of consecutive steps; every graph but a last remainder must be a multiple of the batch
+    pool, so each replay walks the whole rotation from batch 0 and no batch is revisited while it can still sit in L2."""
+    import types
+    sys.path.insert(0, ROOT)
+    import bench
+    for n_pool in (2, 6, 7):
+        for T in (1, 2, 5, 6, 7, 50, 240, 241, 1100, 5000):
+            obj = types.SimpleNamespace(n_pool=n_pool, CHUNK=bench.TrainRun.CHUNK)
+            plan = bench.TrainRun.chunk_plan(obj, T)
+            assert sum(plan) == T and all(c > 0 for c in plan)
+            if T > n_pool:
+                assert all(c % n_pool == 0 for c in plan[:-1]) and max(plan) <= bench.TrainRun.CHUNK
+                assert len(set(plan[:-1])) <= 1          # one graph for the full chunks, one for the remainder
