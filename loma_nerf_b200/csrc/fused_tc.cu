@@ -1,6 +1,11 @@
 // fused_tc.cu -- the fused tensor-core train / render step for small coordinate MLPs (sm_100a).
 //
-// ONE kernel does, per 128-sample tile held by a persistent CTA:
+// Two kernels share this file's machinery (PTX wrappers, slab layout, weight image, reduce + Adam + peer all-reduce):
+//   fused_v1_kernel  (below)        one 128-sample tile per 128-thread CTA.  Its FWD instantiation is the forward-only
+//                                   (render) kernel: hidden activations live in tensor memory and registers only.
+//   fused_mg_kernel  (fused_mg.cuh) the train step: one CTA per SM, up to seven 128-thread groups, adjoints in place.
+//
+// ONE kernel does, per 128-sample tile held by a persistent CTA (or group):
 //   features -> bf16 A tile in shared memory            (scripts/nerf.py layer_input)
 //   L x [ tcgen05.mma (M=128 samples, N=width, fp32 accumulators in TMEM)
 //         -> tcgen05.ld epilogue: +bias, ReLU -> bf16 -> next layer's A tile ]  (nerf.py:67-146)
