@@ -1144,8 +1144,9 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
     for (int l = 0; l <= L; ++l)
         if (mlp->dims[l] > 256) return unsupported("layer widths above 256");
     if (mlp->dims[L] > 16) return unsupported("more than 16 output channels");
-    if (a->inter || a->rgba || a->alpha || a->cumprod || a->weights || a->d_X || a->d_target || a->d_dists || a->d_color || a->d_inter)
-        return unsupported("only loss, colour, d_ws and d_bs are produced (use the fp32 path for the rest)");
+    if (a->inter || a->d_X || a->d_inter)
+        return unsupported("per-layer intermediates and d_layer_input are not produced here (use the fp32 path)");
+    if (!nerf && (a->d_target || a->d_color)) return unsupported("mlp_fit adjoints other than d_ws / d_bs are not produced here (use the fp32 path)");
     if (a->color && a->color_accumulate) return unsupported("colour accumulation");
     const int R = a->R, S = a->S;
     const long long N = a->n_rows > 0 ? a->n_rows : (long long)R * S;
@@ -1187,6 +1188,8 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
     if (grad)
         for (int l = 0; l < L; ++l) { add((size_t)n_slabs * n_part * in_pad[l] * out_pad[l] * 4); add((size_t)n_slabs * n_part * out_pad[l] * 4); }
     add((size_t)R * 4 + 16); add((size_t)R * 12 + 16); add(64);
+    if (grad && a->d_dists) add((size_t)N * 4);
+    if (grad && (a->d_color || a->d_target)) add((size_t)R * 12 + 16);
     LNB_TRY(lnb_arena_reserve(ctx, need));
     auto take = [&](size_t bytes) { return lnb_arena_take(ctx, bytes); };
     __nv_bfloat16 *H[LNB_MAX_LAYERS], *dZ[LNB_MAX_LAYERS];
@@ -1225,6 +1228,10 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
     float *ray_sse = (float *)take((size_t)R * 4 + 16);
     float *color = a->color ? a->color : (float *)take((size_t)R * 12 + 16);
     float *loss = a->loss ? a->loss : (float *)take(64);
+    // compositing by-products and the adjoints of dists / colour / target come from the fp32 compositing kernels this path
+    // shares with the exact one (their inputs, the head outputs, carry the bf16 error of the MLP)
+    float *d_dists_u = (grad && a->d_dists) ? (float *)take((size_t)N * 4) : nullptr;
+    float *d_color_u = (grad && (a->d_color || a->d_target)) ? (float *)take((size_t)R * 12 + 16) : nullptr;
     if (N == 0) {
         if (a->loss) LNB_TRY(lnb_launch_fill(ctx, loss, 1, 0.0f));
         return LNB_OK;
@@ -1282,15 +1289,16 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
                               nullptr, nullptr, 0, head + n0 * 4, 4, EPI_HEAD_F32, mlp->head, next_dir()));
         }
         if (nerf) {
-            LNB_TRY(lnb_launch_composite_fwd(ctx, head + n0 * 4, 4, dists + n0, a->target ? a->target + (size_t)r0 * 3 : nullptr, Rs, S, nullptr, nullptr,
-                                             nullptr, nullptr, color + (size_t)r0 * 3, 0, ray_sse + r0));
+            LNB_TRY(lnb_launch_composite_fwd(ctx, head + n0 * 4, 4, dists + n0, a->target ? a->target + (size_t)r0 * 3 : nullptr, Rs, S,
+                                             a->rgba ? a->rgba + n0 * 4 : nullptr, a->alpha ? a->alpha + n0 : nullptr, a->cumprod ? a->cumprod + n0 : nullptr,
+                                             a->weights ? a->weights + n0 : nullptr, color + (size_t)r0 * 3, 0, ray_sse + r0));
         } else if (a->target) {   // mlp_fit: the prediction is the sigmoid head itself, SSE over target_w channels (mlp_fit.py:140-145)
             LNB_TRY(lnb_launch_fit_loss(ctx, head + n0 * 4, 4, a->target + (size_t)r0 * a->target_w, Rs, a->target_w, ray_sse + r0));
         }
         if (!grad) continue;
         if (nerf)
             LNB_TRY(lnb_launch_composite_bwd(ctx, head + n0 * 4, 4, dists + n0, a->target + (size_t)r0 * 3, color + (size_t)r0 * 3, Rs, S, dzh + n0 * 4, 4, 4,
-                                             nullptr, nullptr));
+                                             d_dists_u ? d_dists_u + n0 : nullptr, d_color_u ? d_color_u + (size_t)r0 * 3 : nullptr));
         else
             LNB_TRY(lnb_launch_fit_head_bwd(ctx, head + n0 * 4, 4, a->target + (size_t)r0 * a->target_w, Rs, a->target_w, Rs, 4, dzh + n0 * 4, 4, nullptr));
         {
@@ -1343,6 +1351,10 @@ int lnb_wide_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, b
     jobs.seed_dev = a->seed_mode == LNB_SEED_LOSS ? loss : nullptr;
     wide_reduce_all_kernel<<<blocks, 256, 0, ctx->stream>>>(jobs);
     LNB_CHECK_LAUNCH();
+    // += seed x unit-seed adjoint (the seed may be the loss just computed on the device)
+    if (a->d_dists) LNB_TRY(lnb_launch_axpy2d(ctx, a->d_dists, S, d_dists_u, S, R, S, 1.0f, jobs.seed_value, jobs.seed_dev));
+    if (a->d_color) LNB_TRY(lnb_launch_axpy2d(ctx, a->d_color, 3, d_color_u, 3, R, 3, 1.0f, jobs.seed_value, jobs.seed_dev));
+    if (a->d_target) LNB_TRY(lnb_launch_axpy2d(ctx, a->d_target, 3, d_color_u, 3, R, 3, -1.0f, jobs.seed_value, jobs.seed_dev));
     return LNB_OK;
 }
 

@@ -319,3 +319,25 @@ def test_wide_path_random_shapes(ctx, torch_cuda):
         assert all(np.isfinite(v) for v in errs.values()) and max(errs.values()) <= bound, (shape, errs)
         worst = max(worst, max(errs.values()))
     _log("wide random worst %.3g" % worst)
+
+
+@pytest.mark.parametrize("R,S,width,layers", [(96, 64, 128, 4), (40, 192, 256, 9)])
+def test_wide_path_compositing_by_products_and_ray_adjoints(ctx, torch_cuda, R, S, width, layers):
+    """rgba / alpha / cumprod / weights and d_dists / d_accumulated_color / d_target on the layerwise tensor-core path (they
+    come from the fp32 compositing kernels fed with the tensor-core head), seed = loss, += into the caller's buffers."""
+    torch = torch_cuda
+    case = O.make_nerf_case(3300 + width, R, S, E=10, width=width, n_layers=layers)
+    cv = lambda a: torch.as_tensor(np.ascontiguousarray(a, np.float32)).cuda()  # noqa: E731
+    outs = ("color", "loss", "rgba", "alpha", "cumprod", "weights", "d_dists", "d_color", "d_target")
+    pre = {k: torch.full(shape, 0.5, device="cuda") for k, shape in (("d_dists", (R, S)), ("d_color", (R, 3)), ("d_target", (R, 3)))}
+    out = ctx.nerf_step([int(v) for v in case["dims"]], cv(case["X"]), cv(case["ws"]), cv(case["bs"]), cv(case["dists"]), cv(case["target"]),
+                        R=R, S=S, grad=True, seed="loss", outputs=outs, out=dict(pre), path="tc")
+    ctx.synchronize()
+    f = O.nerf_f64(case["X"], case["ws"], case["bs"], case["dims"], case["target"], case["dists"], R, S, g="loss")
+    o = {k: v.cpu().numpy() for k, v in out.items()}
+    for k in ("rgba", "alpha", "cumprod", "weights", "color"):
+        assert rel_err(o[k].reshape(np.asarray(f[k]).shape), f[k]) <= WIDE_TOL, k
+    for k, fk in (("d_dists", "d_dists"), ("d_color", "d_acc"), ("d_target", "d_target")):
+        got = o[k] - 0.5                                            # accumulated onto the 0.5 already there
+        assert rel_err(got.reshape(np.asarray(f[fk]).shape), f[fk]) <= 2 * WIDE_TOL, k
+    assert rel_err(o["d_ws"], f["d_ws"]) <= 2 * WIDE_TOL            # seed = loss carries the loss's own error too
