@@ -1225,9 +1225,14 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
         else if (HP == 32) LNB_MG_PICK(32);
         else LNB_MG_PICK(64);
 #undef LNB_MG_PICK
-        cudaFuncAttributes fa;
-        LNB_CUDA(cudaFuncGetAttributes(&fa, mg_fn));
-        while (ng > 1 && (long long)ng * TILE * ((fa.numRegs + 7) / 8 * 8) > 65536) --ng;
+        static int mg_regs[2][3] = {{0, 0, 0}, {0, 0, 0}};    // registers per thread of each instantiation, asked once
+        int &regs = mg_regs[rays ? 1 : 0][HP == 16 ? 0 : (HP == 32 ? 1 : 2)];
+        if (regs == 0) {
+            cudaFuncAttributes fa;
+            LNB_CUDA(cudaFuncGetAttributes(&fa, mg_fn));
+            regs = fa.numRegs;
+        }
+        while (ng > 1 && (long long)ng * TILE * ((regs + 7) / 8 * 8) > 65536) --ng;
         if (const char *e = getenv("LNB_TC_GROUPS")) { const int v = atoi(e); if (v >= 1 && v < ng) ng = v; }
         const int per_sm = (p.n_tiles + ctx->sm_count - 1) / ctx->sm_count;   // small batches: no idle groups
         if (ng > per_sm) ng = per_sm < 1 ? 1 : per_sm;
@@ -1276,7 +1281,9 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
     cfg.attrs = pdl_attr; cfg.numAttrs = use_pdl ? 1 : 0;
 #define LNB_LAUNCH(KERNEL)                                                                        \
     do {                                                                                         \
-        LNB_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        static size_t smem_set[64] = {};   /* per expansion = per kernel instantiation, per device: raise the limit only when it grows */ \
+        size_t &lim = smem_set[ctx->device & 63];                                                 \
+        if (smem > lim || ctx->device > 63) { LNB_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); lim = smem; } \
         LNB_CUDA(cudaLaunchKernelEx(&cfg, KERNEL, p));                                           \
     } while (0)
 #define LNB_TC(HPV)                                                                              \
