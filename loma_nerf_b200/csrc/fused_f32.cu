@@ -454,32 +454,34 @@ __global__ void __launch_bounds__(1024) fused_f32_reduce_kernel(const float *__r
                                                                  int overwrite)
 {
     __shared__ float sloss;
-    __shared__ float acc[32][33];
-    if (threadIdx.x < 32) {
+    __shared__ float acc[31][33];
+    // the loss sum (warp 31) and the gradient gather (warps 0-30) run side by side under one barrier
+    const int el = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int n_el = p.part_stride - 1;
+    const int e_glob = blockIdx.x * 32 + el;
+    if (grp == 31) {
         float s = 0.0f;
-        for (int i = threadIdx.x; i < n_part; i += 32) s += part[(size_t)i * p.part_stride];
+#pragma unroll 8
+        for (int i = el; i < n_part; i += 32) s += part[(size_t)i * p.part_stride];
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-        if (threadIdx.x == 0) { sloss = s; if (blockIdx.x == 0 && loss) loss[0] = s; }
+        if (el == 0) { sloss = s; if (blockIdx.x == 0 && loss) loss[0] = s; }
+    } else if (d_ws) {
+        float s = 0.0f;
+        if (e_glob < n_el) {
+            const float *src = part + 1 + e_glob;
+#pragma unroll 8
+            for (int i = grp; i < n_part; i += 31) s += src[(size_t)i * p.part_stride];
+        }
+        acc[grp][el] = s;
     }
     __syncthreads();
     if (!d_ws) return;
     const float scale = seed_is_loss ? sloss * seed_value : seed_value;
-    const int el = threadIdx.x & 31, grp = threadIdx.x >> 5;
-    const int n_el = p.part_stride - 1;
-    const int e_glob = blockIdx.x * 32 + el;
-    float s = 0.0f;
-    if (e_glob < n_el) {
-        const float *src = part + 1 + e_glob;
-#pragma unroll 8
-        for (int i = grp; i < n_part; i += 32) s += src[(size_t)i * p.part_stride];
-    }
-    acc[grp][el] = s;
-    __syncthreads();
     if (grp != 0 || e_glob >= n_el) return;
-    s = 0.0f;
+    float s = 0.0f;
 #pragma unroll
-    for (int w2 = 0; w2 < 32; ++w2) s += acc[w2][el];
+    for (int w2 = 0; w2 < 31; ++w2) s += acc[w2][el];
     int e = e_glob + 1, l = 0;
     while (l + 1 < p.L && e >= p.part_off[l + 1]) ++l;
     e -= p.part_off[l];

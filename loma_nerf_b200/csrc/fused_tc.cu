@@ -962,6 +962,7 @@ __global__ void __launch_bounds__(1024) tc_reduce_kernel(const float *__restrict
     const int e_glob = blockIdx.x * 32 + el;
     if (grp == 31) {
         float s = 0.0f;
+#pragma unroll 5
         for (int i = el; i < n_part; i += 32) s += part[(size_t)i * part_stride];
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
