@@ -408,28 +408,41 @@ class Trainer:
             a.seed_mode, a.seed = L.SEED_VALUE, float(seed)
         return a, int(nerf)
 
+    def prepare(self, **batch):
+        """A batch marshalled once (the lnb_step_args struct and the buffers it points at), to be handed to step(),
+        step_host() or submit_host() any number of times: a hosts' loop that cycles through pre-built batches pays one ctypes
+        call per step instead of rebuilding the struct in Python."""
+        a, nerf = self._batch(**batch)
+        return PreparedBatch(a, nerf, batch)
+
     def _order(self, batch):
         self.ctx.order_after_torch()
         self.ctx._hold(*[v for v in batch.values() if _is_cuda(v)], *[x for x in (batch.get("rays") or ()) if _is_cuda(x)])
 
-    def step(self, **batch):
-        """forward + backward + optimiser update on one batch."""
-        a, nerf = self._batch(**batch)
+    def step(self, prepared=None, **batch):
+        """forward + backward + optimiser update on one batch (keyword arguments, or a prepare()d batch)."""
+        if prepared is not None:
+            a, nerf, batch = prepared.args, prepared.nerf, prepared.batch
+        else:
+            a, nerf = self._batch(**batch)
         self._order(batch)
         self.ctx._check(self.lib.lnb_trainer_step(self.h, ctypes.byref(a), nerf))
 
-    def step_host(self, **batch):
+    def step_host(self, prepared=None, **batch):
         """step() with the batch in host memory (numpy arrays / pinned CPU tensors): the C library
         stages it to the device, steps, and returns the loss.  Synchronous."""
-        a, nerf = self._batch(**batch)
+        a, nerf = (prepared.args, prepared.nerf) if prepared is not None else self._batch(**batch)
         loss = ctypes.c_float()
         self.ctx._check(self.lib.lnb_trainer_step_host(self.h, ctypes.byref(a), nerf, ctypes.byref(loss)))
         return float(loss.value)
 
-    def submit_host(self, **batch):
+    def submit_host(self, prepared=None, **batch):
         """step_host() without the wait: the batch is staged on a copy stream while the previous step still runs
         (lnb_trainer_submit_host).  Pinned host buffers must stay unchanged until the submission after next."""
-        a, nerf = self._batch(**batch)
+        if prepared is not None:
+            a, nerf, batch = prepared.args, prepared.nerf, prepared
+        else:
+            a, nerf = self._batch(**batch)
         self._keep = (self.__dict__.get("_keep", []) + [batch])[-3:]
         self.ctx._check(self.lib.lnb_trainer_submit_host(self.h, ctypes.byref(a), nerf))
 
@@ -488,6 +501,14 @@ class Trainer:
         loss = np.empty(1, np.float32)
         self.ctx._check(self.lib.lnb_trainer_read(self.h, ws.ctypes.data, bs.ctypes.data, loss.ctypes.data))
         return ws, bs, float(loss[0])
+
+
+class PreparedBatch:
+    """Trainer.prepare(): the marshalled lnb_step_args of one batch plus references that keep its buffers alive."""
+    __slots__ = ("args", "nerf", "batch")
+
+    def __init__(self, args, nerf, batch):
+        self.args, self.nerf, self.batch = args, nerf, batch
 
 
 def _torch_view(ptr, n_floats, device):

@@ -304,7 +304,7 @@ def test_pipelined_host_steps_equal_the_synchronous_ones(ctx, torch_cuda, pinned
         tb.submit_host(**b)
     got = tb.wait()
     for b in batches[3:]:
-        tb.submit_host(**b)
+        tb.submit_host(tb.prepare(**b))          # a batch marshalled once and handed over as such
     got += tb.wait()
     assert tb.wait() == []
     wb, bb, _ = tb.read()
