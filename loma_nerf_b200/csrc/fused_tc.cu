@@ -912,18 +912,19 @@ __device__ __forceinline__ AdamScalars adam_scalars(const AdamArgs &a)
     const double c1 = 1.0 - pow(a.b1, (double)t), c2 = 1.0 - pow(a.b2, (double)t);
     return AdamScalars{(float)(a.lr * (sqrt(c2) / c1)), (float)c1, (float)c2};
 }
-__device__ __forceinline__ float adam_one(const AdamArgs &a, long long i, float g, const AdamScalars &sc)
+// p0, m0, v0: the element's parameter and moments, loaded by the caller (early, off the critical path)
+__device__ __forceinline__ float adam_one(const AdamArgs &a, long long i, float g, const AdamScalars &sc, float p0, float m0, float v0)
 {
     if (a.sgd) {
-        const float pn = a.param[i] - (float)a.lr * g;
+        const float pn = p0 - (float)a.lr * g;
         a.param[i] = pn;
         return pn;
     }
-    const float mi = (float)a.b1 * a.m[i] + (float)(1.0 - a.b1) * g;
-    const float vi = (float)a.b2 * a.v[i] + (float)(1.0 - a.b2) * (g * g);
+    const float mi = (float)a.b1 * m0 + (float)(1.0 - a.b1) * g;
+    const float vi = (float)a.b2 * v0 + (float)(1.0 - a.b2) * (g * g);
     a.m[i] = mi;
     a.v[i] = vi;
-    const float pnew = a.param[i] - sc.lr_t * (mi / sc.c1) / (sqrtf(vi / sc.c2) + (float)a.eps);
+    const float pnew = p0 - sc.lr_t * (mi / sc.c1) / (sqrtf(vi / sc.c2) + (float)a.eps);
     a.param[i] = pnew;
     return pnew;
 }
@@ -960,6 +961,25 @@ __global__ void __launch_bounds__(1024) tc_reduce_kernel(const float *__restrict
     const int el = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int n_el = part_stride - 1;
     const int e_glob = blockIdx.x * 32 + el;
+    // the element this thread of warp 0 will update: its parameter and moments are fetched now, under the gather
+    const bool mine_el = grp == 0 && e_glob < n_el && d_ws;
+    int ml = 0, mk = 0, mj = 0;
+    bool m_is_w = false;
+    long long m_pi = 0;
+    float *m_dst = nullptr;
+    float pf_p = 0.0f, pf_m = 0.0f, pf_v = 0.0f, pf_d = 0.0f;
+    if (mine_el) {
+        int e = e_glob + 1;
+        while (ml + 1 < p.L && e >= p.part_off[ml + 1]) ++ml;
+        e -= p.part_off[ml];
+        const int out_l = p.dims[ml + 1];
+        mk = e / out_l; mj = e % out_l;
+        m_is_w = mk < p.dims[ml];
+        m_dst = m_is_w ? d_ws + ((size_t)ml * p.max_in + mk) * p.max_out + mj : d_bs + (size_t)ml * p.max_out + mj;
+        m_pi = m_is_w ? ((long long)ml * p.max_in + mk) * p.max_out + mj : ad.n_w + (long long)ml * p.max_out + mj;
+        if (!overwrite) pf_d = *m_dst;
+        if (fuse_adam) { pf_p = ad.param[m_pi]; if (!ad.sgd) { pf_m = ad.m[m_pi]; pf_v = ad.v[m_pi]; } }
+    }
     if (grp == 31) {
         float s = 0.0f;
 #pragma unroll 5
@@ -1060,19 +1080,12 @@ __global__ void __launch_bounds__(1024) tc_reduce_kernel(const float *__restrict
         }
     }
     (void)loss_total;
-    if (grp == 0 && e_glob < n_el) {
-        int e = e_glob + 1, l = 0;
-        while (l + 1 < p.L && e >= p.part_off[l + 1]) ++l;
-        e -= p.part_off[l];
-        const int out_l = p.dims[l + 1], k = e / out_l, j = e % out_l;
-        const bool is_w = k < p.dims[l];
-        float *dst = is_w ? d_ws + ((size_t)l * p.max_in + k) * p.max_out + j : d_bs + (size_t)l * p.max_out + j;
-        const float g = overwrite ? g_local : *dst + g_local;
-        *dst = g;
+    if (mine_el) {
+        const float g = overwrite ? g_local : pf_d + g_local;
+        *m_dst = g;
         if (fuse_adam) {
-            const long long pi = is_w ? ((long long)l * p.max_in + k) * p.max_out + j : ad.n_w + (long long)l * p.max_out + j;
-            const float pn = adam_one(ad, pi, g, s_adam);
-            if (ad.wimg) { if (is_w) im.put_w(ad.wimg, l, k, j, pn); else im.put_b(ad.wimg, l, j, pn); }
+            const float pn = adam_one(ad, m_pi, g, s_adam, pf_p, pf_m, pf_v);
+            if (ad.wimg) { if (m_is_w) im.put_w(ad.wimg, ml, mk, mj, pn); else im.put_b(ad.wimg, ml, mj, pn); }
         }
     }
 }
@@ -1088,7 +1101,7 @@ __global__ void tc_adam_img_kernel(TcParams p, const float *__restrict__ grad, A
     const int out_l = p.dims[l + 1], k = e / out_l, j = e % out_l;
     const bool is_w = k < p.dims[l];
     const long long pi = is_w ? ((long long)l * p.max_in + k) * p.max_out + j : ad.n_w + (long long)l * p.max_out + j;
-    const float pn = adam_one(ad, pi, grad[pi], adam_scalars(ad));
+    const float pn = adam_one(ad, pi, grad[pi], adam_scalars(ad), ad.param[pi], ad.sgd ? 0.0f : ad.m[pi], ad.sgd ? 0.0f : ad.v[pi]);
     if (ad.wimg) { if (is_w) im.put_w(ad.wimg, l, k, j, pn); else im.put_b(ad.wimg, l, j, pn); }
 }
 
