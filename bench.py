@@ -600,6 +600,9 @@ def roofline_record(run, prof, m, peaks):
                 "traffic": traffic, "traffic_source": traffic_src, "kernel": prof["kernel"], "us_per_launch": sec * 1e6,
                 "launches_timed": prof["launches"], "algorithmic_bytes_per_launch": alg_bytes,
                 "algorithmic_tflops": N * fl / sec / 1e12, "tensor_frac": N * fl / sec / 1e12 / peaks.get("bf16_tflops", 1590.0),
+                "note": "us_per_launch: CUDA events around each EAGER launch of the kernel (the events see ~3 us of launch gap that the graph "
+                        "of consecutive steps hides under the previous kernel: there the whole step, reduce + Adam kernel included, is "
+                        "ms_per_step); frac is computed from the eager figure",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"}
     # no single dominant kernel (layerwise kernels): report the whole step against HBM
     peak = peaks.get("hbm_gbs", 6650.0)
