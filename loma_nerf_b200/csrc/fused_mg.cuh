@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(mg_max_groups<HP>() * TILE, 1) fused_mg_kernel
         const long long row0 = (long long)tile * p.rows_per_tile;
         long long rem = p.N - row0;
         const int valid = rem < p.rows_per_tile ? (int)rem : p.rows_per_tile;
-        const int rays_here = valid / S;
+        const int rays_here = valid == p.rows_per_tile ? p.G : valid / S;
         const int smp = tid % S, ray_l = tid / S;        // this thread's sample within its ray
         const bool live = tid < rays_here * S;
         // the previous tile's last weight-gradient MMAs read A_0 and A_1's buffer (dZ_0): both are rewritten below
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(mg_max_groups<HP>() * TILE, 1) fused_mg_kernel
         if (p.head == LNB_HEAD_NERF && live) {
             if (!RAYS) my_dist = __ldg(p.dists + row0 + tid);
             if (p.target && smp == 0) {
-                const float *tg = p.target + (row0 / S + ray_l) * 3;
+                const float *tg = p.target + (size_t)(tile * p.G + ray_l) * 3   /* ray = row0 / S + ray_l: a tile holds G whole rays; R is an int */;
                 tg0 = __ldg(tg); tg1 = __ldg(tg + 1); tg2 = __ldg(tg + 2);
             }
         }
@@ -304,9 +304,10 @@ __global__ void __launch_bounds__(mg_max_groups<HP>() * TILE, 1) fused_mg_kernel
                 // ray of pixel q and depth of sample smp straight from the pose (get_rays, train_nerf.py:23-62; linspace /
                 // stratified depths, train_nerf.py:289-311): no per-ray or per-sample input at all
                 const CamF32 &c = p.cam;
-                const long long ray = row0 / S + ray_l;
+                const long long ray = tile * p.G + ray_l;
                 const long long q = c.pixels ? (long long)__ldg(c.pixels + ray) : c.first_pixel + ray;
-                const unsigned uq = (unsigned)q, col = uq % (unsigned)c.width, row = uq / (unsigned)c.width;
+                // q / width by the 64-bit reciprocal the launcher computed (exact for every 32-bit q)
+                const unsigned uq = (unsigned)q, row = c.width == 1 ? uq : (unsigned)__umul64hi((unsigned long long)uq, c.w_magic), col = uq - row * (unsigned)c.width;
                 const float fi = col == (unsigned)c.width - 1 ? 1.0f : (float)col * c.step, fj = row == (unsigned)c.width - 1 ? 1.0f : (float)row * c.step;
                 const float dx = (fi - c.cx) * c.inv_fx, dy = (c.cy - fj) * c.inv_fy;
                 float tt, tn;
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(mg_max_groups<HP>() * TILE, 1) fused_mg_kernel
                     x[k] = fmaf(dk, tt, c.c2w[4 * k + 3]);
                 }
             } else if (live) {
-                const long long ray = row0 / S + ray_l, smpl = row0 + tid;
+                const long long ray = tile * p.G + ray_l, smpl = row0 + tid;
                 if (p.ray_f64) {
                     const double *o = reinterpret_cast<const double *>(p.rays_o) + ray * 3;
                     const double *d = reinterpret_cast<const double *>(p.rays_d) + ray * 3;
@@ -502,7 +503,7 @@ __global__ void __launch_bounds__(mg_max_groups<HP>() * TILE, 1) fused_mg_kernel
             if (live) {
                 const float c0 = color_s[ray_l * 3], c1 = color_s[ray_l * 3 + 1], c2 = color_s[ray_l * 3 + 2];
                 if (smp == 0 && p.color) {
-                    float *co = p.color + (row0 / S + ray_l) * 3;
+                    float *co = p.color + (size_t)(tile * p.G + ray_l) * 3;
                     co[0] = c0; co[1] = c1; co[2] = c2;
                 }
                 const float d0 = c0 - tgt_s[ray_l * 3], d1 = c1 - tgt_s[ray_l * 3 + 1], d2 = c2 - tgt_s[ray_l * 3 + 2];

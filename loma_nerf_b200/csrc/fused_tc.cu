@@ -53,6 +53,7 @@ struct CamF32 {
     long long first_pixel;
     const int *pixels;
     unsigned long long seed;
+    unsigned long long w_magic;      // floor(2^64 / width) + 1 (width >= 2): q / width = umul64hi(q, w_magic) for every 32-bit q
     int width, stratified;
 };
 
@@ -61,6 +62,7 @@ struct TcParams {
     float *color;      // [R][3] or NULL
     float *part;       // [grid][part_stride]
     float *dbg;        // optional [N][4] head outputs (debug)
+    int poll_ns;       // sleep between polls of the MMA-completion barrier (forward-only kernel)
     const void *wimg;  // weight image built by tc_prep_kernel (TcLayout::wimg_bytes)
     // rays mode (X == NULL): features are computed in the kernel from rays and sample depths
     const void *rays_o, *rays_d, *tvals; // [R][3], [R][3], [R][S]; float64 when ray_f64 else float32
@@ -464,7 +466,21 @@ __global__ void __launch_bounds__(TILE, FWD ? 9 : 1) fused_v1_kernel(const TcPar
     };
     auto commit_and_wait = [&]() {
         if (tid == 0) umma_commit(bar_mma);
-        mbar_wait(bar_mma, phase);
+        if (FWD && p.poll_ns > 0) {
+            uint32_t done = 0;
+            for (uint32_t it = 0; !done; ++it) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done) : "r"(bar_mma), "r"(phase), "r"(100000u) : "memory");
+                if (!done) {
+                    __nanosleep(p.poll_ns);
+                    if (it > (1u << 24)) __trap();
+                }
+            }
+        } else
+            mbar_wait(bar_mma, phase);
         phase ^= 1;
         tc_fence_after();
     };
@@ -483,20 +499,21 @@ __global__ void __launch_bounds__(TILE, FWD ? 9 : 1) fused_v1_kernel(const TcPar
 #define CLK(i)
 #endif
     int *const next_tile_s = reinterpret_cast<int *>(tailp + 32);
+    const int smp = tid % S, ray_l = tid / S;            // this thread's sample within its ray (the same in every tile)
     for (int tile = blockIdx.x; tile < p.n_tiles;) {
         const long long row0 = (long long)tile * p.rows_per_tile;
         long long rem = p.N - row0;
         const int valid = rem < p.rows_per_tile ? (int)rem : p.rows_per_tile;
-        const int rays_here = valid / S;
+        const int rays_here = valid == p.rows_per_tile ? p.G : valid / S;
+        const int ray0 = tile * p.G;      // = row0 / S: a tile holds G whole rays (R is an int)
         CLK(15);
-        const int smp = tid % S, ray_l = tid / S;        // this thread's sample within its ray
         const bool live = tid < rays_here * S;
         // early, latency-tolerant loads for this tile (consumed after the MLP forward)
         float my_dist = 0.0f, tg0 = 0.0f, tg1 = 0.0f, tg2 = 0.0f;
         if (p.head == LNB_HEAD_NERF && live) {
             if (!RAYS) my_dist = __ldg(p.dists + row0 + tid);
             if (p.target && smp == 0) {
-                const float *tg = p.target + (row0 / S + ray_l) * 3;
+                const float *tg = p.target + (size_t)(ray0 + ray_l) * 3;
                 tg0 = __ldg(tg); tg1 = __ldg(tg + 1); tg2 = __ldg(tg + 2);
             }
         }
@@ -508,9 +525,10 @@ __global__ void __launch_bounds__(TILE, FWD ? 9 : 1) fused_v1_kernel(const TcPar
                 // ray of pixel q and depth of sample smp straight from the pose (get_rays, train_nerf.py:23-62; linspace /
                 // stratified depths, train_nerf.py:289-311): no per-ray or per-sample input at all
                 const CamF32 &c = p.cam;
-                const long long ray = row0 / S + ray_l;
+                const long long ray = ray0 + ray_l;
                 const long long q = c.pixels ? (long long)__ldg(c.pixels + ray) : c.first_pixel + ray;
-                const unsigned uq = (unsigned)q, col = uq % (unsigned)c.width, row = uq / (unsigned)c.width;
+                // q / width by the 64-bit reciprocal the launcher computed (exact for every 32-bit q)
+                const unsigned uq = (unsigned)q, row = c.width == 1 ? uq : (unsigned)__umul64hi((unsigned long long)uq, c.w_magic), col = uq - row * (unsigned)c.width;
                 const float fi = col == (unsigned)c.width - 1 ? 1.0f : (float)col * c.step, fj = row == (unsigned)c.width - 1 ? 1.0f : (float)row * c.step;
                 const float dx = (fi - c.cx) * c.inv_fx, dy = (c.cy - fj) * c.inv_fy;
                 float tt, tn;
@@ -528,7 +546,7 @@ __global__ void __launch_bounds__(TILE, FWD ? 9 : 1) fused_v1_kernel(const TcPar
                     x[k] = fmaf(dk, tt, c.c2w[4 * k + 3]);
                 }
             } else if (live) {
-                const long long ray = row0 / S + ray_l, smpl = row0 + tid;
+                const long long ray = ray0 + ray_l, smpl = row0 + tid;
                 if (p.ray_f64) {
                     const double *o = reinterpret_cast<const double *>(p.rays_o) + ray * 3;
                     const double *d = reinterpret_cast<const double *>(p.rays_d) + ray * 3;
@@ -733,7 +751,7 @@ __global__ void __launch_bounds__(TILE, FWD ? 9 : 1) fused_v1_kernel(const TcPar
             if (live) {
                 const float c0 = color_s[ray_l * 3], c1 = color_s[ray_l * 3 + 1], c2 = color_s[ray_l * 3 + 2];
                 if (smp == 0 && p.color) {
-                    float *co = p.color + (row0 / S + ray_l) * 3;
+                    float *co = p.color + (size_t)(ray0 + ray_l) * 3;
                     co[0] = c0; co[1] = c1; co[2] = c2;
                 }
                 if (p.target) {
@@ -1217,6 +1235,7 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
         p.cam.step = (float)(1.0 / (double)(c.width - 1)); p.cam.near = (float)c.near; p.cam.far = (float)c.far;
         p.cam.dt_lin = (float)((c.far - c.near) / (double)(a->S > 1 ? a->S - 1 : 1)); p.cam.dt_str = (float)((c.far - c.near) / (double)a->S);
         p.cam.first_pixel = c.first_pixel; p.cam.pixels = c.pixels; p.cam.seed = c.seed; p.cam.width = c.width; p.cam.stratified = c.stratified;
+        p.cam.w_magic = c.width >= 2 ? ~0ull / (unsigned long long)c.width + 1ull : 0ull;
     }
     p.color = nerf ? a->color : nullptr;
     p.N = N; p.R = R; p.S = S;
@@ -1234,6 +1253,10 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
 
     const int c_in = mlp->dims[0];
     const bool grad = a->want_grad != 0;
+    // forward-only kernel: 100 ns between polls of the MMA-completion barrier (nine CTAs per SM wake each other's sleeping
+    // try_wait ~10 times per wait; the polls were 23 % of the kernel's issued instructions)
+    p.poll_ns = 100;
+    if (const char *e = getenv("LNB_TC_POLL_NS")) p.poll_ns = atoi(e);
     if (!rays && (reinterpret_cast<uintptr_t>(a->X) & 3) != 0) return unsupported("X must be 4-byte aligned");
     // Train steps run on the multi-group kernel (fused_mg.cuh: one CTA per SM, up to seven 128-thread groups, adjoints in
     // place); forward-only launches and LNB_TC_V1=1 on the one-tile-per-CTA kernel above.
