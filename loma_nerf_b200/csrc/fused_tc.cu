@@ -583,19 +583,25 @@ __global__ void __launch_bounds__(TILE, FWD ? 9 : 1) fused_v1_kernel(const TcPar
                     q4[j & 3] = v;
                     if ((j & 3) == 3) { if ((j >> 2) < live_slabs) *row_ptr(a0, j >> 2) = make_uint4(q4[0], q4[1], q4[2], q4[3]); q4[0] = q4[1] = q4[2] = q4[3] = 0u; }
                 };
+                // warp-uniform branches: the bands that are off cost nothing
 #pragma unroll
                 for (int i = 0; i < 10; ++i) {
-                    const bool on = i < p.pe_bands;
-                    const bool close = !closed && !on;
-                    put(1 + 3 * i, on ? pack_bf16(pend, sn[0]) : (close ? pack_bf16(pend, 1.0f) : 0u));
-                    put(2 + 3 * i, on ? pack_bf16(sn[1], sn[2]) : 0u);
-                    put(3 + 3 * i, on ? pack_bf16(cs[0], cs[1]) : 0u);
-                    closed = closed || close;
-                    pend = cs[2];
+                    if (i < p.pe_bands) {
+                        put(1 + 3 * i, pack_bf16(pend, sn[0]));
+                        put(2 + 3 * i, pack_bf16(sn[1], sn[2]));
+                        put(3 + 3 * i, pack_bf16(cs[0], cs[1]));
+                        pend = cs[2];
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const float s2 = 2.0f * sn[c] * cs[c], c2 = fmaf(-2.0f * sn[c], sn[c], 1.0f);
-                        sn[c] = s2; cs[c] = c2;
+                        for (int c = 0; c < 3; ++c) {
+                            const float s2 = 2.0f * sn[c] * cs[c], c2 = fmaf(-2.0f * sn[c], sn[c], 1.0f);
+                            sn[c] = s2; cs[c] = c2;
+                        }
+                    } else {
+                        if (closed && ((1 + 3 * i) >> 2) >= live_slabs) break;   // no live slab left to store (slab 7 then is not live either)
+                        put(1 + 3 * i, closed ? 0u : pack_bf16(pend, 1.0f));
+                        put(2 + 3 * i, 0u);
+                        put(3 + 3 * i, 0u);
+                        closed = true;
                     }
                 }
                 put(31, closed ? 0u : pack_bf16(pend, 1.0f));
