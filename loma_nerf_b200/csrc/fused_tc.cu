@@ -62,7 +62,6 @@ struct TcParams {
     float *color;      // [R][3] or NULL
     float *part;       // [grid][part_stride]
     float *dbg;        // optional [N][4] head outputs (debug)
-    int poll_ns;       // sleep between polls of the MMA-completion barrier (forward-only kernel)
     const void *wimg;  // weight image built by tc_prep_kernel (TcLayout::wimg_bytes)
     // rays mode (X == NULL): features are computed in the kernel from rays and sample depths
     const void *rays_o, *rays_d, *tvals; // [R][3], [R][3], [R][S]; float64 when ray_f64 else float32
@@ -108,6 +107,34 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
             else if (now - t0 > 10000000000ull) __trap();
         }
     }
+}
+// The forward-only kernel's wait for an MMA stage: nine CTAs share an SM and a stage takes ~1 us there, during which the
+// hardware-suspended try_wait comes back ~10 times (any barrier event of the SM wakes it).  The render kernel is bound by
+// instruction issue and these polls were 30 % of its instructions at nine per iteration (counter, time-out test, sleep);
+// here an iteration is the try_wait and one branch, the counter ticks once per four polls.
+__device__ __forceinline__ void mbar_wait_tight(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .u32 n;\n\t"
+        "mov.u32 n, 0;\n"
+        "LNB_WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra LNB_WAIT_DONE;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra LNB_WAIT_DONE;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra LNB_WAIT_DONE;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra LNB_WAIT_DONE;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.lt.u32 q, n, 0x1000000;\n\t"
+        "@q bra LNB_WAIT_LOOP;\n\t"
+        "trap;\n"                       // never hang the GPU: a lost arrival is a bug, fail loudly (seconds)
+        "LNB_WAIT_DONE:\n\t"
+        "}"
+        :: "r"(bar), "r"(parity), "r"(100000u) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -466,20 +493,8 @@ __global__ void __launch_bounds__(TILE, FWD ? 9 : 1) fused_v1_kernel(const TcPar
     };
     auto commit_and_wait = [&]() {
         if (tid == 0) umma_commit(bar_mma);
-        if (FWD && p.poll_ns > 0) {
-            uint32_t done = 0;
-            for (uint32_t it = 0; !done; ++it) {
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\t"
-                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-                    "selp.u32 %0, 1, 0, p;\n\t}"
-                    : "=r"(done) : "r"(bar_mma), "r"(phase), "r"(100000u) : "memory");
-                if (!done) {
-                    __nanosleep(p.poll_ns);
-                    if (it > (1u << 24)) __trap();
-                }
-            }
-        } else
+        if (FWD) mbar_wait_tight(bar_mma, phase);
+        else
             mbar_wait(bar_mma, phase);
         phase ^= 1;
         tc_fence_after();
@@ -1259,10 +1274,6 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
 
     const int c_in = mlp->dims[0];
     const bool grad = a->want_grad != 0;
-    // forward-only kernel: 100 ns between polls of the MMA-completion barrier (nine CTAs per SM wake each other's sleeping
-    // try_wait ~10 times per wait; the polls were 23 % of the kernel's issued instructions)
-    p.poll_ns = 100;
-    if (const char *e = getenv("LNB_TC_POLL_NS")) p.poll_ns = atoi(e);
     if (!rays && (reinterpret_cast<uintptr_t>(a->X) & 3) != 0) return unsupported("X must be 4-byte aligned");
     // Train steps run on the multi-group kernel (fused_mg.cuh: one CTA per SM, up to seven 128-thread groups, adjoints in
     // place); forward-only launches and LNB_TC_V1=1 on the one-tile-per-CTA kernel above.
