@@ -155,3 +155,22 @@ def test_trainer_steps_from_a_camera_batch_on_host_and_device(env):
     tol = lambda a, b: float(np.abs(a - b).max()) <= 2e-5 * float(np.abs(b).max())  # noqa: E731
     assert tol(wd, wh) and tol(bd, bh) and abs(loss_d - loss_h) <= 1e-5 * abs(loss_h)
     tr_d.close(); tr_h.close()
+
+
+@pytest.mark.parametrize("W", [37, 100])
+def test_frame_of_a_width_that_is_no_power_of_two_or_tile_multiple(env, W):
+    """Pixel row / column come from a 64-bit reciprocal multiply in the fused kernels (no integer division per tile): a
+    width that divides nothing, rendered in calls that start in the middle of a pixel row."""
+    torch, api, ctx = env
+    from loma_nerf_b200 import render
+    S, E = 24, 5
+    K, pose = _scene(W, theta=75.0)
+    dims = O.mlp_dims(3 + 6 * E, 30, 3, 4)
+    ws, bs = O.init_mlp(np.random.default_rng(48), dims, 1.0)
+    ref = render.render_frame(ctx, dims, ws, bs, W, W, K, pose, S, E, path="f32")
+    want = np.rint(255 * ref.clip(0, 1)).astype(np.int32)
+    cv = lambda a: torch.as_tensor(np.ascontiguousarray(a, np.float32)).cuda()  # noqa: E731
+    for path, tol in (("f32", 1), ("tc", 4)):
+        img = render.render_frame_device(ctx, dims, cv(ws), cv(bs), W, W, K, pose, S, E, path=path, rays_per_call=W * 3 + 11)
+        ctx.synchronize()
+        assert np.abs(img.cpu().numpy().astype(np.int32) - want).max() <= tol, (W, path)
