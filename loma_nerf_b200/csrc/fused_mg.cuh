@@ -59,24 +59,10 @@ struct MgLayout {
     }
 };
 
-// mbarrier wait of the group threads: a short sleep between polls.  With seven groups on an SM a sleeping try_wait is woken
-// by the other groups' barrier traffic and re-polls ~5 times per wait; the polls travel down the shared-memory pipe, which
-// is what bounds this kernel (measured: 2.7 % on a 2 M-sample launch, 100 ns and 300 ns alike).
-__device__ __forceinline__ void mbar_wait_mg(uint32_t bar, uint32_t parity)
-{
-    uint32_t done = 0;
-    for (uint32_t it = 0; !done; ++it) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity), "r"(100000u) : "memory");
-        if (!done) {
-            __nanosleep(100);
-            if (it > (1u << 24)) __trap();      // never hang the GPU: a lost arrival is a bug, fail loudly (seconds)
-        }
-    }
-}
+// mbarrier wait of the group threads.  With seven groups on an SM a hardware-suspended try_wait is woken by the other groups'
+// barrier traffic and re-polls several times per wait; mbar_wait_tight (fused_tc.cu) keeps an iteration at the try_wait and one
+// branch (an explicit __nanosleep between polls, tried before, does not actually sleep here and costs five instructions).
+__device__ __forceinline__ void mbar_wait_mg(uint32_t bar, uint32_t parity) { mbar_wait_tight(bar, parity); }
 __device__ __forceinline__ void bar_group(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(TILE) : "memory"); }
 __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr)
 {
