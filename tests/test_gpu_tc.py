@@ -311,3 +311,17 @@ def test_pipelined_host_steps_equal_the_synchronous_ones(ctx, torch_cuda, pinned
     tb.close()
     assert len(got) == len(want) and rel_err(got, want) <= 1e-5, (got, want)
     assert rel_err(wb, wa) <= 2e-5 and rel_err(bb, ba) <= 2e-5
+
+
+@pytest.mark.parametrize("R,S,E", [(500, 64, 2), (257, 40, 8), (64, 64, 10), (300, 16, 0)])
+def test_forward_only_kernel_rays_mode_band_counts(ctx, torch_cuda, R, S, E):
+    """The forward-only kernel skips the positional-encoding bands that are switched off by warp-uniform branches: every band
+    count from none to the maximum must fill exactly the slabs the first-layer MMA reads."""
+    torch = torch_cuda
+    case = O.make_nerf_case(900 + S + E, R, S, E=E, width=30)
+    d64 = lambda a: torch.as_tensor(np.ascontiguousarray(a, np.float64)).cuda().contiguous()  # noqa: E731
+    out = ctx.nerf_step_rays([int(v) for v in case["dims"]], d64(case["rays_o"]), d64(case["rays_d"]), d64(case["t"]), E,
+                             dev(torch, case["ws"]), dev(torch, case["bs"]), None, grad=False, outputs=("color",), path="tc")
+    ctx.synchronize()
+    f = O.nerf_f64(case["X"], case["ws"], case["bs"], case["dims"], case["target"], case["dists"], R, S, g=None)
+    assert rel_err(host(out["color"]), f["color"]) <= TC_TOL

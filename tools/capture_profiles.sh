@@ -13,3 +13,5 @@ python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-render --no-extra -
   ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/r02_bench_launches.csv \
       python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-render --no-extra --eager > $O/n5.log 2>&1
 for f in p1 p2 p3 p4; do tail -n 1 $O/$f.log; done
+python tools/t_render.py 8        > $O/p6.log 2>&1 && $NCU -k regex:fused_v1         -o $O/r02_render_fwd   python tools/t_render.py 2        > $O/n6.log 2>&1
+tail -n 1 $O/p6.log
