@@ -189,6 +189,19 @@ class Env:
                              "(use --impl reference for the CPU arm)")
         torch.cuda.set_device(self.local)
         self.device = torch.device("cuda", self.local)
+        self.numa = None
+        if self.world > 1 and not os.environ.get("LNB_BENCH_NO_AFFINITY"):
+            # several GPUs on a multi-socket host: run this rank (and so first-touch its pinned host buffers) on the cores
+            # next to its GPU, or the end-to-end legs measure the socket interconnect instead of PCIe
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                pr = torch.cuda.get_device_properties(self.local)
+                bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+                pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode()))
+                self.numa = "rank bound to its GPU's NUMA-local cores (NVML ideal CPU affinity, %d cores)" % len(os.sched_getaffinity(0))
+            except Exception as e:      # no NVML, no permission: measure as launched
+                self.numa = "unchanged (%s)" % type(e).__name__
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             dist.init_process_group("nccl", device_id=self.device)
@@ -838,6 +851,7 @@ def run_ours(args):
             "render": render}
     if pm is not None:
         line["parity_multi"] = pm
+        line["host_affinity"] = env.numa
     if world == 1 and not args.no_cpu_baseline and rank == 0:
         line["cpu_baseline"] = cpu_baseline_record(wname, S)
     run.close()
