@@ -737,7 +737,7 @@ def render_record(env, run, n_poses=120):
                            "algorithmic_flops_per_launch": per_launch * S * fwd_flops,
                            "output_gbs": per_launch * 12 / s_l / 1e9,
                            "note": "forward only: no per-ray input, 12 B of colour written per ray -- nothing for HBM to bound; the roof "
-                                   "is the tensor pipe (SURVEY 8d F_fwd per sample), and what limits it is tcgen05 latency on a tiny MLP"}
+                                   "is the tensor pipe (SURVEY 8d F_fwd per sample), and what limits it is instruction issue (ncu: 75 % of the issue slots, tensor pipe 33 %; profiles/r02_render_fwd_*): N <= 32 MMAs and the per-sample prologue / compositing arithmetic around them"}
     del color, u8, host
     return rec
 

@@ -1369,7 +1369,8 @@ int lnb_fused_tc_step(lnb_ctx *ctx, const lnb_mlp *mlp, const lnb_step_args *a, 
             else tc_prep_kernel<64><<<1, 256, 0, ctx->stream>>>(p, wimg);
             LNB_CHECK_LAUNCH();
         }
-        lnb_prof_begin(ctx, rays ? "fused_tc_kernel<rays>" : "fused_tc_kernel<features>");
+        lnb_prof_begin(ctx, mg ? (rays ? "fused_mg_kernel<rays>" : "fused_mg_kernel<features>")
+                              : (rays ? "fused_v1_kernel<rays>" : "fused_v1_kernel<features>"));      // the symbols ncu lists
         if (HP == 16) LNB_TC(16);
         else if (HP == 32) LNB_TC(32);
         else LNB_TC(64);

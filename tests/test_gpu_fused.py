@@ -162,7 +162,7 @@ def test_multi_group_kernel_shapes_against_f64_restatement(ctx, torch_cuda, R, S
     torch = torch_cuda
     case = O.make_nerf_case(5000 + R + width, R, S, E=E, width=width, n_layers=layers)
     f = O.nerf_f64(case["X"], case["ws"], case["bs"], case["dims"], case["target"], case["dists"], R, S, g=1.0)
-    o = nerf_step(ctx, torch, case, "tc", expect_kernel="fused_tc_kernel")
+    o = nerf_step(ctx, torch, case, "tc", expect_kernel="fused_mg_kernel")
     tc_check(o, f)
     # rays input: features generated in the kernel
     out = ctx.nerf_step_rays([int(v) for v in case["dims"]], dev(torch, case["rays_o"], np.float64), dev(torch, case["rays_d"], np.float64),
