@@ -539,7 +539,7 @@ def roofline_record(run, prof, m, peaks):
         f_adj = 2.0 * sum(dims[l] * dims[l + 1] for l in range(1, len(dims) - 1))
         flops_launch = N * (f_fwd + f_adj) / 2
         ach = flops_launch / sec / 1e12
-        traffic, traffic_src = ncu_traffic("r01_wide_chain_ncu_full_per_launch.csv", "chain_tc_kernel")
+        traffic, traffic_src = ncu_traffic("r02_wide_chain_ncu_full_per_launch.csv", "chain_tc_kernel")
         b_fwd = N * (pad(dims[0]) * 2 + sum(pad(dims[l + 1]) * 2 + pad(dims[l + 1]) // 8 for l in range(Lw - 1)) + 16)
         b_adj = N * (pad(dims[Lw]) * 2 + sum(pad(dims[l]) * 2 + pad(dims[l]) // 8 for l in range(1, Lw)))
         return {"bound": "tensor", "achieved": ach, "peak": tpeak_s, "unit": "TFLOP/s", "frac": ach / tpeak_s,
