@@ -941,14 +941,25 @@ struct AdamArgs {
 // the reference's AdamOptimizer.update (train_nerf.py:133-161, double bias correction kept) on
 // one parameter; python-float scalars meet float32 arrays exactly as in optim.cu
 // the step's scalar factors: Python doubles in the reference (lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t)), rounded to float32
-// once where they meet the arrays.  Two double-precision pow() are ~1 us of dependent arithmetic: computed by ONE thread
-// per block, off the other threads' critical path (see tc_reduce_kernel).
+// once where they meet the arrays; computed by ONE thread per block, beside the gather (see tc_reduce_kernel).
 struct AdamScalars { float lr_t, c1, c2; };
+// beta^t for an integer step count by squaring: ~2 log2(t) dependent double multiplies where pow() is ~1 us of dependent
+// arithmetic (it was hidden behind the gather: the step time did not change).  Both are within a few ulps of double; the
+// results are rounded to float32.
+__device__ __forceinline__ double pow_int(double b, int t)
+{
+    double r = 1.0;
+    for (; t > 0; t >>= 1) {
+        if (t & 1) r *= b;
+        b *= b;
+    }
+    return r;
+}
 __device__ __forceinline__ AdamScalars adam_scalars(const AdamArgs &a)
 {
     if (a.sgd) return AdamScalars{0.f, 1.f, 1.f};
     const int t = a.t_dev[0];
-    const double c1 = 1.0 - pow(a.b1, (double)t), c2 = 1.0 - pow(a.b2, (double)t);
+    const double c1 = 1.0 - pow_int(a.b1, t), c2 = 1.0 - pow_int(a.b2, t);
     return AdamScalars{(float)(a.lr * (sqrt(c2) / c1)), (float)c1, (float)c2};
 }
 // p0, m0, v0: the element's parameter and moments, loaded by the caller (early, off the critical path)
