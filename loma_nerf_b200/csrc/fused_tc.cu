@@ -694,9 +694,14 @@ __global__ void __launch_bounds__(TILE, FWD ? 9 : 1) fused_v1_kernel(const TcPar
                         *row_ptr(an, c16 * 2 + 1) = make_uint4(o[4], o[5], o[6], o[7]);
                     }
                 }
-                if (FWD) tmem_st_wait_();
                 CLK(4);
-                publish_smem();
+                if (FWD) {              // nothing went to shared memory: the activations are in tensor memory
+                    tmem_st_wait_();
+                    tc_fence_before();
+                    __syncthreads();
+                    tc_fence_after();
+                } else
+                    publish_smem();
                 CLK(5);
             } else {
                 uint32_t v[16];
