@@ -357,7 +357,7 @@ __global__ void tc_prep_kernel(const TcParams p, uint8_t *__restrict__ img)
 // FWD: the forward-only (render) form, compiled separately: nothing of the backward pass in its register budget (56
 // registers: nine CTAs per SM instead of seven)
 template <bool RAYS, int HP, bool FWD>
-__global__ void __launch_bounds__(TILE, FWD ? 9 : 1) fused_v1_kernel(const TcParams p)
+__global__ void __launch_bounds__(TILE, FWD ? 8 : 1) fused_v1_kernel(const TcParams p)
 {
     using LY = TcLayout<HP>;
     extern __shared__ __align__(1024) uint8_t smem[];
