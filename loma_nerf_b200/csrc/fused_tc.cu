@@ -354,10 +354,11 @@ __global__ void tc_prep_kernel(const TcParams p, uint8_t *__restrict__ img)
 // fp32 sin/cos of the positional encoding (pos_encoding.py:38-70): one accurate sincosf per
 // coordinate, higher bands by angle doubling (sin 2a = 2 s c, cos 2a = 1 - 2 s^2).  The doubling
 // amplifies the base error by 2^(E-1): ~1e-6 at E = 5, far below the bf16 operand rounding.
-// FWD: the forward-only (render) form, compiled separately: nothing of the backward pass in its register budget (56
-// registers: nine CTAs per SM instead of seven)
+// FWD: the forward-only (render) form, compiled separately: nothing of the backward pass in its register budget.  Its
+// launch bounds are the CTAs per SM that tensor memory admits (512 columns / 64 per CTA = 8; 4 for the 64-wide form), not
+// more: a ninth CTA could never allocate its columns and the tighter register budget only bought a spill.
 template <bool RAYS, int HP, bool FWD>
-__global__ void __launch_bounds__(TILE, FWD ? 8 : 1) fused_v1_kernel(const TcParams p)
+__global__ void __launch_bounds__(TILE, FWD ? (HP == 64 ? 4 : 8) : 1) fused_v1_kernel(const TcParams p)
 {
     using LY = TcLayout<HP>;
     extern __shared__ __align__(1024) uint8_t smem[];
